@@ -1,0 +1,464 @@
+// tcgen05 implicit-GEMM kernel for every convolution-shaped contraction of the CP-CSV step.
+//
+// One persistent, warp-specialised kernel (sm_100a):
+//   warp 0      TMA producer   : 5-D tiled tensor-map loads (128B swizzle) of the A pixel box
+//                                (shifted per filter tap; TMA zero-fill = conv padding) and of
+//                                the B tile, into a multi-stage shared-memory ring
+//   warp 1      MMA issuer     : tcgen05.mma kind::f16 (bf16/fp16 in, fp32 accumulate in TMEM),
+//                                1 or 3 MMAs per k-step (hi/lo split operands), tcgen05.commit
+//                                releases smem stages / publishes the accumulator
+//   warps 2..5  epilogue       : tcgen05.ld TMEM -> registers -> fp32 global (store or red.add)
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the main
+// loop of tile i+1.
+//
+// mode 0 (fprop / dgrad): D[pix, n] = sum_{tap, k} A[pix + tap, k] * B[tap][n, k]
+//        A, B K-major; M tile = 128 output pixels (tile_n x tile_h x tile_w box)
+// mode 1 (wgrad):         D[tap][ca, cb] = sum_pix A[pix + tapA, ca] * B[pix + tapB, cb]
+//        A, B MN-major (channels contiguous); K step = 64 pixels
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cpcsv {
+
+constexpr int kThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kAPlaneBytes = kBlockM * 128;  // 128 rows x 64 16-bit (mode 0) / 2 x [64 pix x 64 ch] (mode 1)
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kBarrierBytes = 256;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccStride = 256;  // columns between the two accumulator stages
+
+struct GemmParams {
+  int32_t mode, planes;
+  int32_t N, H, W;
+  int32_t tile_n, tile_h, tile_w;
+  int32_t tiles_n, tiles_h, tiles_w;
+  int32_t groups, taps_per_group, k_blocks;
+  int32_t m_tiles, n_tiles, block_n;
+  int32_t m_valid, n_valid;
+  int32_t splits, iters_total;
+  int32_t accumulate;
+  int32_t stages, b_plane_bytes, stage_bytes;
+  uint32_t idesc;
+  uint32_t total_tiles;
+  int64_t osn, osh, osw, ldc;
+  const float* alpha;
+  float* out;
+  cpcsv_tap_t taps[CPCSV_MAX_TAPS];
+};
+
+struct TileCoord {
+  int32_t group, split, n_idx, m_idx;
+  int32_t it0, it1;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, uint32_t t) {
+  TileCoord c;
+  c.m_idx = t % P.m_tiles;
+  t /= P.m_tiles;
+  c.n_idx = t % P.n_tiles;
+  t /= P.n_tiles;
+  c.split = t % P.splits;
+  c.group = t / P.splits;
+  c.it0 = static_cast<int32_t>((static_cast<int64_t>(P.iters_total) * c.split) / P.splits);
+  c.it1 = static_cast<int32_t>((static_cast<int64_t>(P.iters_total) * (c.split + 1)) / P.splits);
+  return c;
+}
+
+// pixel-tile index -> origin of the (n, h, w) box
+__device__ __forceinline__ void pixel_tile_origin(const GemmParams& P, int32_t q, int32_t& n0,
+                                                  int32_t& h0, int32_t& w0) {
+  w0 = (q % P.tiles_w) * P.tile_w;
+  q /= P.tiles_w;
+  h0 = (q % P.tiles_h) * P.tile_h;
+  n0 = (q / P.tiles_h) * P.tile_n;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P.stages * P.stage_bytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (P.planes == 2) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < P.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t stage_tx = static_cast<uint32_t>(P.planes) * (kAPlaneBytes + P.b_plane_bytes);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(P, tile);
+        int32_t n0 = 0, h0 = 0, w0 = 0;
+        if (P.mode == 0) pixel_tile_origin(P, tc.m_idx, n0, h0, w0);
+        for (int32_t it = tc.it0; it < tc.it1; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          uint8_t* sa = smem + stage * P.stage_bytes;
+          uint8_t* sb = sa + P.planes * kAPlaneBytes;
+          if (P.mode == 0) {
+            const int32_t t = it / P.k_blocks;
+            const int32_t kb = it - t * P.k_blocks;
+            const cpcsv_tap_t& tap = P.taps[tc.group * P.taps_per_group + t];
+            for (int pl = 0; pl < P.planes; ++pl) {
+              tma_load_5d(pl ? &tmA1 : &tmA0, &full_bar[stage], sa + pl * kAPlaneBytes,
+                          tap.a[0] + kb * 64, w0 + tap.a[1], tap.a[2], h0 + tap.a[3], n0);
+              tma_load_5d(pl ? &tmB1 : &tmB0, &full_bar[stage], sb + pl * P.b_plane_bytes, kb * 64,
+                          tap.b[0] + tc.n_idx * P.block_n, 0, 0, 0);
+            }
+          } else {
+            const cpcsv_tap_t& tap = P.taps[tc.group];
+            pixel_tile_origin(P, it, n0, h0, w0);
+            for (int pl = 0; pl < P.planes; ++pl) {
+              for (int j = 0; j < 2; ++j)
+                tma_load_5d(pl ? &tmA1 : &tmA0, &full_bar[stage], sa + pl * kAPlaneBytes + j * 8192,
+                            tap.a[0] + tc.m_idx * kBlockM + j * 64, w0 + tap.a[1], tap.a[2],
+                            h0 + tap.a[3], n0);
+              for (int j = 0; j < P.block_n / 64; ++j)
+                tma_load_5d(pl ? &tmB1 : &tmB0, &full_bar[stage],
+                            sb + pl * P.b_plane_bytes + j * 8192,
+                            tap.b[0] + tc.n_idx * P.block_n + j * 64, w0 + tap.b[1], tap.b[2],
+                            h0 + tap.b[3], n0);
+            }
+          }
+          if (++stage == P.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(P, tile);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kAccStride;
+        for (int32_t it = tc.it0; it < tc.it1; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * P.stage_bytes);
+          const uint32_t sb = sa + P.planes * kAPlaneBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // K-major: 16 elements (32 B) along the 128 B swizzled row per MMA;
+            // MN-major: 16 k-rows (2048 B) per MMA, 64-channel atoms 8192 B apart.
+            const uint32_t koff = (P.mode == 0) ? k * 32 : k * 2048;
+            const uint32_t lbo = (P.mode == 0) ? 16 : 8192;
+            const uint64_t a_hi = make_smem_desc(sa + koff, lbo, 1024);
+            const uint64_t b_hi = make_smem_desc(sb + koff, lbo, 1024);
+            const uint32_t first = (it > tc.it0 || k > 0) ? 1u : 0u;
+            umma_f16(tmem_d, a_hi, b_hi, P.idesc, first);
+            if (P.planes == 2) {
+              const uint64_t a_lo = make_smem_desc(sa + kAPlaneBytes + koff, lbo, 1024);
+              const uint64_t b_lo = make_smem_desc(sb + P.b_plane_bytes + koff, lbo, 1024);
+              umma_f16(tmem_d, a_lo, b_hi, P.idesc, 1u);
+              umma_f16(tmem_d, a_hi, b_lo, P.idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == P.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    const float alpha = P.alpha ? __ldg(P.alpha) : 1.0f;
+    const bool atomic = (P.accumulate != 0) || (P.splits > 1);
+    for (uint32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(P, tile);
+      float* row_ptr;
+      bool row_valid;
+      if (P.mode == 0) {
+        int32_t n0, h0, w0;
+        pixel_tile_origin(P, tc.m_idx, n0, h0, w0);
+        const int32_t rw = row % P.tile_w;
+        const int32_t rh = (row / P.tile_w) % P.tile_h;
+        const int32_t rn = row / (P.tile_w * P.tile_h);
+        const int32_t n = n0 + rn, h = h0 + rh, w = w0 + rw;
+        row_valid = (n < P.N) && (h < P.H) && (w < P.W);
+        row_ptr = P.out + P.taps[tc.group * P.taps_per_group].out_off + n * P.osn + h * P.osh +
+                  w * P.osw;
+      } else {
+        const int32_t m = tc.m_idx * kBlockM + row;
+        row_valid = m < P.m_valid;
+        row_ptr = P.out + P.taps[tc.group].out_off + static_cast<int64_t>(m) * P.ldc;
+      }
+      const int32_t col0 = tc.n_idx * P.block_n;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
+      for (int32_t c0 = 0; c0 < P.block_n; c0 += 32) {
+        uint32_t r[32];
+        int width = 32;
+        if (P.block_n - c0 >= 32) {
+          tmem_ld_32x32(taddr + c0, r);
+        } else {
+          uint32_t r16[16];
+          tmem_ld_32x16(taddr + c0, r16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = r16[j];
+          width = 16;
+        }
+        tmem_ld_wait();
+        if (row_valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int32_t col = col0 + c0 + j;
+            if (j < width && col < P.n_valid) {
+              float4 v;
+              v.x = __uint_as_float(r[j]) * alpha;
+              v.y = __uint_as_float(r[j + 1]) * alpha;
+              v.z = __uint_as_float(r[j + 2]) * alpha;
+              v.w = __uint_as_float(r[j + 3]) * alpha;
+              float* dst = row_ptr + col;
+              if (atomic) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x),
+                             "f"(v.y), "f"(v.z), "f"(v.w)
+                             : "memory");
+              } else {
+                *reinterpret_cast<float4*>(dst) = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+static int make_map(CUtensorMap* tm, const cpcsv_view5_t& v, const uint32_t box[5], int dtype,
+                    const char* what) {
+  auto fn = encode_fn();
+  if (!fn) return fail(-2, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < 5; ++i) {
+    gdim[i] = static_cast<cuuint64_t>(v.dims[i]);
+    bx[i] = box[i];
+    es[i] = 1;
+    if (v.dims[i] <= 0) return fail(-1, "%s: dim %d is %lld", what, i, (long long)v.dims[i]);
+    if (box[i] == 0 || box[i] > 256) return fail(-1, "%s: box %d is %u", what, i, box[i]);
+  }
+  for (int i = 1; i < 5; ++i) {
+    if (v.strides[i] <= 0 || (v.strides[i] & 15))
+      return fail(-1, "%s: stride %d = %lld not a positive multiple of 16 B", what, i,
+                  (long long)v.strides[i]);
+    gstr[i - 1] = static_cast<cuuint64_t>(v.strides[i]);
+  }
+  if (reinterpret_cast<uintptr_t>(v.ptr) & 15) return fail(-1, "%s: base not 16 B aligned", what);
+  CUresult r = fn(tm, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  5, const_cast<void*>(v.ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-3, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+  return 0;
+}
+
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+}  // namespace cpcsv
+
+using namespace cpcsv;
+
+extern "C" int cpcsv_conv_gemm(const cpcsv_gemm_t* job, cpcsv_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CPCSV_REQUIRE(job != nullptr, "conv_gemm: null job");
+  const cpcsv_gemm_t& J = *job;
+  CPCSV_REQUIRE(J.mode == 0 || J.mode == 1, "conv_gemm: mode %d", J.mode);
+  CPCSV_REQUIRE(J.dtype == 0 || J.dtype == 1, "conv_gemm: dtype %d", J.dtype);
+  CPCSV_REQUIRE(J.planes == 1 || J.planes == 2, "conv_gemm: planes %d", J.planes);
+  CPCSV_REQUIRE(J.N > 0 && J.H > 0 && J.W > 0, "conv_gemm: empty pixel grid");
+  const int box_pix = J.tile_n * J.tile_h * J.tile_w;
+  CPCSV_REQUIRE(J.tile_n > 0 && J.tile_h > 0 && J.tile_w > 0 && box_pix == (J.mode == 0 ? 128 : 64),
+                "conv_gemm: pixel box %dx%dx%d", J.tile_n, J.tile_h, J.tile_w);
+  CPCSV_REQUIRE(J.block_n >= 16 && J.block_n <= 256 && J.block_n % 16 == 0, "conv_gemm: block_n %d",
+                J.block_n);
+  CPCSV_REQUIRE(J.mode == 0 || J.block_n % 64 == 0, "conv_gemm: mode 1 needs block_n %% 64 == 0");
+  CPCSV_REQUIRE(J.n_tiles > 0 && J.n_valid > 0 && J.n_valid <= J.n_tiles * J.block_n &&
+                    J.n_valid % 4 == 0,
+                "conv_gemm: n_valid %d", J.n_valid);
+  CPCSV_REQUIRE(J.groups > 0 && J.splits > 0, "conv_gemm: groups/splits");
+  CPCSV_REQUIRE(J.out != nullptr && (reinterpret_cast<uintptr_t>(J.out) & 15) == 0,
+                "conv_gemm: out pointer");
+
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.mode = J.mode;
+  P.planes = J.planes;
+  P.N = J.N; P.H = J.H; P.W = J.W;
+  P.tile_n = J.tile_n; P.tile_h = J.tile_h; P.tile_w = J.tile_w;
+  P.tiles_n = static_cast<int32_t>(ceil_div(J.N, J.tile_n));
+  P.tiles_h = static_cast<int32_t>(ceil_div(J.H, J.tile_h));
+  P.tiles_w = static_cast<int32_t>(ceil_div(J.W, J.tile_w));
+  const int64_t pixel_tiles = static_cast<int64_t>(P.tiles_n) * P.tiles_h * P.tiles_w;
+  P.groups = J.groups;
+  P.block_n = J.block_n;
+  P.n_tiles = J.n_tiles;
+  P.n_valid = J.n_valid;
+  P.splits = J.splits;
+  P.accumulate = J.accumulate;
+  P.alpha = J.alpha;
+  P.out = J.out;
+  int ntaps;
+  if (J.mode == 0) {
+    CPCSV_REQUIRE(J.taps_per_group > 0 && J.k_blocks > 0, "conv_gemm: taps/k_blocks");
+    ntaps = J.groups * J.taps_per_group;
+    P.taps_per_group = J.taps_per_group;
+    P.k_blocks = J.k_blocks;
+    P.m_tiles = static_cast<int32_t>(pixel_tiles);
+    P.iters_total = J.taps_per_group * J.k_blocks;
+    P.osn = J.out_stride_n; P.osh = J.out_stride_h; P.osw = J.out_stride_w;
+    CPCSV_REQUIRE((P.osn % 4) == 0 && (P.osh % 4) == 0 && (P.osw % 4) == 0,
+                  "conv_gemm: output strides must be multiples of 4 elements");
+  } else {
+    ntaps = J.groups;
+    P.taps_per_group = 1;
+    CPCSV_REQUIRE(J.m_valid > 0, "conv_gemm: m_valid");
+    P.m_valid = J.m_valid;
+    P.m_tiles = static_cast<int32_t>(ceil_div(J.m_valid, kBlockM));
+    CPCSV_REQUIRE(pixel_tiles < (1ll << 31), "conv_gemm: too many pixel tiles");
+    P.iters_total = static_cast<int32_t>(pixel_tiles);
+    P.ldc = J.ldc;
+    CPCSV_REQUIRE(J.ldc % 4 == 0 && J.ldc >= J.n_valid, "conv_gemm: ldc %lld", (long long)J.ldc);
+  }
+  CPCSV_REQUIRE(ntaps <= CPCSV_MAX_TAPS, "conv_gemm: %d taps > %d", ntaps, CPCSV_MAX_TAPS);
+  CPCSV_REQUIRE(J.splits <= P.iters_total, "conv_gemm: splits %d > iterations %d", J.splits,
+                P.iters_total);
+  for (int i = 0; i < ntaps; ++i) {
+    P.taps[i] = J.taps[i];
+    CPCSV_REQUIRE(J.taps[i].out_off % 4 == 0, "conv_gemm: tap %d out_off alignment", i);
+  }
+  const int64_t total = static_cast<int64_t>(P.groups) * P.splits * P.n_tiles * P.m_tiles;
+  CPCSV_REQUIRE(total > 0 && total < (1ll << 31), "conv_gemm: tile count %lld", (long long)total);
+  P.total_tiles = static_cast<uint32_t>(total);
+  P.idesc = make_idesc(static_cast<uint32_t>(J.dtype), static_cast<uint32_t>(J.mode), kBlockM,
+                       static_cast<uint32_t>(J.block_n));
+  P.b_plane_bytes = J.block_n * 128;
+  P.stage_bytes = J.planes * (kAPlaneBytes + P.b_plane_bytes);
+  int stages = (kSmemLimit - 1024 - kBarrierBytes) / P.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  CPCSV_REQUIRE(stages >= 2, "conv_gemm: tile does not fit shared memory");
+  P.stages = stages;
+  const size_t smem_bytes = static_cast<size_t>(stages) * P.stage_bytes + 1024 + kBarrierBytes;
+
+  CUtensorMap tmA[2], tmB[2];
+  uint32_t boxA[5], boxB[5];
+  boxA[0] = 64; boxA[1] = J.tile_w; boxA[2] = 1; boxA[3] = J.tile_h; boxA[4] = J.tile_n;
+  if (J.mode == 0) {
+    boxB[0] = 64; boxB[1] = J.block_n; boxB[2] = 1; boxB[3] = 1; boxB[4] = 1;
+  } else {
+    for (int i = 0; i < 5; ++i) boxB[i] = boxA[i];
+  }
+  for (int pl = 0; pl < 2; ++pl) {
+    const int src = pl < J.planes ? pl : 0;
+    int rc = make_map(&tmA[pl], J.a[src], boxA, J.dtype, "conv_gemm A");
+    if (rc) return rc;
+    rc = make_map(&tmB[pl], J.b[src], boxB, J.dtype, "conv_gemm B");
+    if (rc) return rc;
+  }
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemLimit);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(static_cast<int>(attr_err), "conv_gemm: cudaFuncSetAttribute: %s",
+                cudaGetErrorString(attr_err));
+
+  uint32_t grid = P.total_tiles < static_cast<uint32_t>(num_sms()) ? P.total_tiles
+                                                                  : static_cast<uint32_t>(num_sms());
+  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA[0], tmA[1], tmB[0], tmB[1], P);
+  return launched("conv_gemm");
+}

@@ -1,0 +1,701 @@
+// HBM-bound kernels around the tcgen05 GEMMs: BatchNorm statistics / apply / backward fused
+// with the activation and with the split of fp32 activations into 16-bit hi/lo operand planes,
+// plus the layout kernels (NCHW <-> NHWC, im2col of the 1/3-channel images, head tanh).
+// All are coalesced along the channel (innermost NHWC) dimension and vectorised 4-8 wide.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.h"
+
+namespace cpcsv {
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return v > 0.f ? v : 0.f;
+  if (act == 2) return v > 0.f ? v : 0.2f * v;
+  return v;
+}
+__device__ __forceinline__ float act_grad(float pre, int act) {
+  if (act == 1) return pre > 0.f ? 1.f : 0.f;
+  if (act == 2) return pre > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+
+// split v into a 16-bit hi part and the 16-bit rounding of the remainder
+__device__ __forceinline__ void split16(float v, int dtype, uint16_t& hi, uint16_t& lo) {
+  if (dtype == 1) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+  } else {
+    __half h = __float2half_rn(v);
+    __half l = __float2half_rn(v - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+  }
+}
+__device__ __forceinline__ uint16_t to16(float v, int dtype) {
+  return dtype == 1 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+}
+
+static inline int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
+  int64_t blocks = ceil_div(work_items, threads);
+  int64_t cap = static_cast<int64_t>(num_sms()) * max_blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// ------------------------------------------------------------------------- bn_stats
+// block = 32 channel-quads x 8 row lanes; grid.x over 128-channel groups, grid.y over rows.
+__global__ void bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx,
+                                double* __restrict__ stats) {
+  const int cq = threadIdx.x & 31;
+  const int rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cq) * 4;
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  if (c < C) {
+    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + rl; r < rows;
+         r += static_cast<int64_t>(gridDim.y) * 8) {
+      const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+      s[0] += v.x; ss[0] += static_cast<double>(v.x) * v.x;
+      s[1] += v.y; ss[1] += static_cast<double>(v.y) * v.y;
+      s[2] += v.z; ss[2] += static_cast<double>(v.z) * v.z;
+      s[3] += v.w; ss[3] += static_cast<double>(v.w) * v.w;
+    }
+  }
+  __shared__ double sh[8][32][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sh[rl][cq][j] = s[j];
+    sh[rl][cq][4 + j] = ss[j];
+  }
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double t = 0;
+      for (int k = 0; k < 8; ++k) t += sh[k][cq][j];
+      if (j < 4) atomicAdd(&stats[c + j], t);
+      else atomicAdd(&stats[C + c + (j - 4)], t);
+    }
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t rows, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var,
+                                   const int32_t* __restrict__ chan_map, int C_valid, float eps,
+                                   float momentum, float* mean, float* invstd, float* scale,
+                                   float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (c >= C_valid) {
+    mean[c] = 0.f; invstd[c] = 0.f; scale[c] = 0.f; shift[c] = 0.f;
+    return;
+  }
+  const double n = static_cast<double>(rows);
+  const double m = stats[c] / n;
+  double var = stats[C + c] / n - m * m;
+  if (var < 0) var = 0;
+  const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const int p = chan_map ? chan_map[c] : c;
+  const float g = gamma[p], b = beta[p];
+  mean[c] = static_cast<float>(m);
+  invstd[c] = is;
+  scale[c] = g * is;
+  shift[c] = b - static_cast<float>(m) * g * is;
+  if (running_mean) {
+    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+    running_mean[p] = (1.f - momentum) * running_mean[p] + momentum * static_cast<float>(m);
+    running_var[p] = (1.f - momentum) * running_var[p] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// ------------------------------------------------------------------------- bn_act_pack
+__global__ void bn_act_pack_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx,
+                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                   int act, const float* __restrict__ mod, int64_t ldmod,
+                                   float* __restrict__ y, int64_t ldy, uint16_t* __restrict__ hi,
+                                   uint16_t* __restrict__ lo, int64_t ldp, int dtype) {
+  const int cq = C >> 2;
+  const int64_t total = rows * cq;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cq;
+    const int c = static_cast<int>(i - r * cq) * 4;
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    float v[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (scale) {
+      const float4 sc = *reinterpret_cast<const float4*>(scale + c);
+      const float4 sf = *reinterpret_cast<const float4*>(shift + c);
+      v[0] = fmaf(v[0], sc.x, sf.x); v[1] = fmaf(v[1], sc.y, sf.y);
+      v[2] = fmaf(v[2], sc.z, sf.z); v[3] = fmaf(v[3], sc.w, sf.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], act);
+    if (mod) {
+      const float4 mv = *reinterpret_cast<const float4*>(mod + r * ldmod + c);
+      v[0] *= 1.f + mv.x; v[1] *= 1.f + mv.y; v[2] *= 1.f + mv.z; v[3] *= 1.f + mv.w;
+    }
+    if (y) *reinterpret_cast<float4*>(y + r * ldy + c) = make_float4(v[0], v[1], v[2], v[3]);
+    if (hi) {
+      uint16_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split16(v[j], dtype, h[j], l[j]);
+      uint2 hv, lv;
+      hv.x = h[0] | (static_cast<uint32_t>(h[1]) << 16);
+      hv.y = h[2] | (static_cast<uint32_t>(h[3]) << 16);
+      *reinterpret_cast<uint2*>(hi + r * ldp + c) = hv;
+      if (lo) {
+        lv.x = l[0] | (static_cast<uint32_t>(l[1]) << 16);
+        lv.y = l[2] | (static_cast<uint32_t>(l[3]) << 16);
+        *reinterpret_cast<uint2*>(lo + r * ldp + c) = lv;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- bn backward
+// shared by reduce and apply: g = dL/d(pre-activation) and xhat for 4 channels
+struct BwdElem {
+  float g[4], xhat[4], a[4];
+};
+__device__ __forceinline__ BwdElem bwd_elem(const float* __restrict__ x, const float* __restrict__ dy,
+                                            int64_t r, int c, int64_t ldx, int64_t lddy,
+                                            const float* __restrict__ scale,
+                                            const float* __restrict__ shift,
+                                            const float* __restrict__ mean,
+                                            const float* __restrict__ invstd, int act,
+                                            const float* __restrict__ mod, int64_t ldmod) {
+  BwdElem e;
+  const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+  const float4 dv = *reinterpret_cast<const float4*>(dy + r * lddy + c);
+  const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+  const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+  float ms[4] = {0.f, 0.f, 0.f, 0.f};
+  if (mod) {
+    const float4 mv = *reinterpret_cast<const float4*>(mod + r * ldmod + c);
+    ms[0] = mv.x; ms[1] = mv.y; ms[2] = mv.z; ms[3] = mv.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float pre = xs[j];
+    if (scale) pre = fmaf(xs[j], scale[c + j], shift[c + j]);
+    e.a[j] = apply_act(pre, act);
+    const float da = ds[j] * (1.f + ms[j]);
+    e.g[j] = da * act_grad(pre, act);
+    e.xhat[j] = mean ? (xs[j] - mean[c + j]) * invstd[c + j] : 0.f;
+  }
+  return e;
+}
+
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                     int64_t rows, int C, int64_t ldx, int64_t lddy,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     int act, const float* __restrict__ mod, int64_t ldmod,
+                                     double* __restrict__ sums) {
+  const int cq = threadIdx.x & 31;
+  const int rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cq) * 4;
+  double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
+  if (c < C) {
+    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + rl; r < rows;
+         r += static_cast<int64_t>(gridDim.y) * 8) {
+      const BwdElem e = bwd_elem(x, dy, r, c, ldx, lddy, scale, shift, mean, invstd, act, mod, ldmod);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] += e.g[j];
+        sx[j] += static_cast<double>(e.g[j]) * e.xhat[j];
+      }
+    }
+  }
+  __shared__ double sh[8][32][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sh[rl][cq][j] = s[j];
+    sh[rl][cq][4 + j] = sx[j];
+  }
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double t = 0;
+      for (int k = 0; k < 8; ++k) t += sh[k][cq][j];
+      if (j < 4) atomicAdd(&sums[c + j], t);
+      else atomicAdd(&sums[C + c + (j - 4)], t);
+    }
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                    int64_t rows, int C, int64_t ldx, int64_t lddy,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma,
+                                    const int32_t* __restrict__ chan_map, int C_valid, int act,
+                                    const float* __restrict__ mod, int64_t ldmod,
+                                    const double* __restrict__ sums, int has_bn,
+                                    float* __restrict__ dx, int64_t lddx, uint16_t* __restrict__ dx16,
+                                    int64_t ld16, float* __restrict__ dmod, int64_t lddmod,
+                                    uint16_t* __restrict__ dmod16, int64_t lddmod16,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int cq = C >> 2;
+  const int64_t total = rows * cq;
+  const float inv_rows = 1.f / static_cast<float>(rows);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cq;
+    const int c = static_cast<int>(i - r * cq) * 4;
+    const BwdElem e = bwd_elem(x, dy, r, c, ldx, lddy, scale, shift, has_bn ? mean : nullptr,
+                               invstd, act, mod, ldmod);
+    float d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (has_bn) {
+        const float mg = static_cast<float>(sums[c + j]) * inv_rows;
+        const float mgx = static_cast<float>(sums[C + c + j]) * inv_rows;
+        // scale = gamma * invstd
+        d[j] = scale[c + j] * (e.g[j] - mg - e.xhat[j] * mgx);
+      } else {
+        d[j] = e.g[j];
+      }
+    }
+    if (dx) *reinterpret_cast<float4*>(dx + r * lddx + c) = make_float4(d[0], d[1], d[2], d[3]);
+    if (dx16) {
+      uint2 v;
+      v.x = to16(d[0], 1) | (static_cast<uint32_t>(to16(d[1], 1)) << 16);
+      v.y = to16(d[2], 1) | (static_cast<uint32_t>(to16(d[3], 1)) << 16);
+      *reinterpret_cast<uint2*>(dx16 + r * ld16 + c) = v;
+    }
+    if (dmod || dmod16) {
+      const float4 dv = *reinterpret_cast<const float4*>(dy + r * lddy + c);
+      const float m[4] = {dv.x * e.a[0], dv.y * e.a[1], dv.z * e.a[2], dv.w * e.a[3]};
+      if (dmod) *reinterpret_cast<float4*>(dmod + r * lddmod + c) = make_float4(m[0], m[1], m[2], m[3]);
+      if (dmod16) {
+        uint2 v;
+        v.x = to16(m[0], 1) | (static_cast<uint32_t>(to16(m[1], 1)) << 16);
+        v.y = to16(m[2], 1) | (static_cast<uint32_t>(to16(m[3], 1)) << 16);
+        *reinterpret_cast<uint2*>(dmod16 + r * lddmod16 + c) = v;
+      }
+    }
+    if (r == 0 && dgamma) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c + j < C_valid) {
+          const int p = chan_map ? chan_map[c + j] : c + j;
+          dgamma[p] = static_cast<float>(sums[C + c + j]);
+          dbeta[p] = static_cast<float>(sums[c + j]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- pack_nchw
+__global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C, int H, int W, int64_t sn,
+                                 int64_t sc, int64_t sh, int64_t sw, const float* __restrict__ bcast,
+                                 int Cb, int64_t ldb, uint16_t* __restrict__ hi,
+                                 uint16_t* __restrict__ lo, int Cpad, int dtype) {
+  const int64_t total = static_cast<int64_t>(N) * H * W * Cpad;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cpad);
+    int64_t p = i / Cpad;
+    const int w = static_cast<int>(p % W);
+    p /= W;
+    const int h = static_cast<int>(p % H);
+    const int n = static_cast<int>(p / H);
+    float v = 0.f;
+    if (c < C) v = x[n * sn + c * sc + h * sh + w * sw];
+    else if (c < C + Cb) v = bcast[n * ldb + (c - C)];
+    uint16_t hv, lv;
+    split16(v, dtype, hv, lv);
+    hi[i] = hv;
+    if (lo) lo[i] = lv;
+  }
+}
+
+// ------------------------------------------------------------------------- im2col (small C)
+__global__ void im2col_small_kernel(const float* __restrict__ x, int N, int C, int H, int W,
+                                    int64_t sn, int64_t sc, int64_t sh, int64_t sw, int k, int s,
+                                    int p, int OH, int OW, uint16_t* __restrict__ hi,
+                                    uint16_t* __restrict__ lo, int ldp, int dtype) {
+  const int64_t total = static_cast<int64_t>(N) * OH * OW * ldp;
+  const int kk = k * k * C;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % ldp);
+    int64_t q = i / ldp;
+    const int ow = static_cast<int>(q % OW);
+    q /= OW;
+    const int oh = static_cast<int>(q % OH);
+    const int n = static_cast<int>(q / OH);
+    float v = 0.f;
+    if (j < kk) {
+      const int tap = j / C, c = j - tap * C;
+      const int ky = tap / k, kx = tap - ky * k;
+      const int ih = oh * s - p + ky, iw = ow * s - p + kx;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[n * sn + c * sc + ih * sh + iw * sw];
+    }
+    uint16_t hv, lv;
+    split16(v, dtype, hv, lv);
+    hi[i] = hv;
+    if (lo) lo[i] = lv;
+  }
+}
+
+__global__ void col2im_small_kernel(const float* __restrict__ dcol, int64_t ldc, int N, int C, int H,
+                                    int W, int k, int s, int p, int OH, int OW,
+                                    float* __restrict__ dx) {
+  const int64_t total = static_cast<int64_t>(N) * C * H * W;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(i % W);
+    int64_t q = i / W;
+    const int h = static_cast<int>(q % H);
+    q /= H;
+    const int c = static_cast<int>(q % C);
+    const int n = static_cast<int>(q / C);
+    float acc = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int t = h + p - ky;
+      if (t < 0 || t % s) continue;
+      const int oh = t / s;
+      if (oh >= OH) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int u = w + p - kx;
+        if (u < 0 || u % s) continue;
+        const int ow = u / s;
+        if (ow >= OW) continue;
+        acc += dcol[(static_cast<int64_t>(n) * OH * OW + oh * OW + ow) * ldc + (ky * k + kx) * C + c];
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------- heads
+__global__ void tanh_to_nchw_kernel(const float* __restrict__ z, int64_t ldz, int N, int C, int H,
+                                    int W, float* __restrict__ y) {
+  const int64_t total = static_cast<int64_t>(N) * C * H * W;
+  const int64_t hw = static_cast<int64_t>(H) * W;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t pix_in_img = i % hw;
+    const int64_t q = i / hw;
+    const int c = static_cast<int>(q % C);
+    const int64_t n = q / C;
+    y[i] = tanhf(z[(n * hw + pix_in_img) * ldz + c]);
+  }
+}
+
+__global__ void tanh_bwd_im2col_kernel(const float* __restrict__ dy, int64_t sn, int64_t sc,
+                                       int64_t sh, int64_t sw, const float* __restrict__ y, int N,
+                                       int C, int H, int W, uint16_t* __restrict__ col, int ldp,
+                                       int dtype) {
+  const int64_t total = static_cast<int64_t>(N) * H * W * ldp;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % ldp);
+    int64_t q = i / ldp;
+    const int w = static_cast<int>(q % W);
+    q /= W;
+    const int h = static_cast<int>(q % H);
+    const int n = static_cast<int>(q / H);
+    float v = 0.f;
+    if (j < 9 * C) {
+      const int tap = j / C, c = j - tap * C;
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const int ih = h - (ky - 1), iw = w - (kx - 1);
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        const float yy = y[((static_cast<int64_t>(n) * C + c) * H + ih) * W + iw];
+        v = dy[n * sn + c * sc + ih * sh + iw * sw] * (1.f - yy * yy);
+      }
+    }
+    col[i] = to16(v, dtype);
+  }
+}
+
+// ------------------------------------------------------------------------- weight packing
+__global__ void pack_matrix_kernel(const float* __restrict__ w, int64_t rows_out, int64_t cols_out,
+                                   int64_t cols_valid, int64_t ld_r, int64_t ld_c,
+                                   const int32_t* __restrict__ row_map, uint16_t* __restrict__ hi,
+                                   uint16_t* __restrict__ lo, int64_t ldo, int dtype) {
+  const int64_t total = rows_out * cols_out;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols_out, c = i - r * cols_out;
+    float v = 0.f;
+    if (c < cols_valid) {
+      const int64_t rs = row_map ? row_map[r] : r;
+      if (rs >= 0) v = w[rs * ld_r + c * ld_c];
+    }
+    uint16_t hv, lv;
+    split16(v, dtype, hv, lv);
+    hi[r * ldo + c] = hv;
+    if (lo) lo[r * ldo + c] = lv;
+  }
+}
+
+// taps of the 3x3 kernel merged into sub-pixel tap i of phase a:
+//   a=0: i=0 -> {0},   i=1 -> {1,2};   a=1: i=0 -> {0,1}, i=1 -> {2}
+__device__ __forceinline__ void merged_range(int a, int i, int& lo, int& hi) {
+  if (a == 0) { lo = i == 0 ? 0 : 1; hi = i == 0 ? 0 : 2; }
+  else        { lo = i == 0 ? 0 : 2; hi = i == 0 ? 1 : 2; }
+}
+
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw,
+                                        int kind, int rows_pad, int cols_pad,
+                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                        int dtype) {
+  const int ntap = (kind >= 2) ? 16 : kh * kw;
+  const int64_t total = static_cast<int64_t>(ntap) * rows_pad * cols_pad;
+  const bool transposed = (kind == 1 || kind == 3);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cols_pad);
+    int64_t q = i / cols_pad;
+    const int r = static_cast<int>(q % rows_pad);
+    const int tap = static_cast<int>(q / rows_pad);
+    const int co = transposed ? c : r;
+    const int ci = transposed ? r : c;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) {
+      const float* base = w + (static_cast<int64_t>(co) * Cin + ci) * kh * kw;
+      if (kind < 2) {
+        v = base[tap];
+      } else {
+        const int a = tap >> 3, b = (tap >> 2) & 1, ti = (tap >> 1) & 1, tj = tap & 1;
+        int y0, y1, x0, x1;
+        merged_range(a, ti, y0, y1);
+        merged_range(b, tj, x0, x1);
+        for (int ky = y0; ky <= y1; ++ky)
+          for (int kx = x0; kx <= x1; ++kx) v += base[ky * 3 + kx];
+      }
+    }
+    uint16_t hv, lv;
+    split16(v, dtype, hv, lv);
+    hi[i] = hv;
+    if (lo) lo[i] = lv;
+  }
+}
+
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwt, int64_t mat_stride,
+                                         int64_t ldc, int Cout, int Cin, int kh, int kw, int kind,
+                                         const float* __restrict__ alpha, float* __restrict__ dw) {
+  const int64_t total = static_cast<int64_t>(Cout) * Cin * kh * kw;
+  const bool transposed = (kind == 1 || kind == 3);
+  const float a_ = alpha ? *alpha : 1.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i % (kh * kw));
+    int64_t q = i / (kh * kw);
+    const int ci = static_cast<int>(q % Cin);
+    const int co = static_cast<int>(q / Cin);
+    const int64_t elem = transposed ? static_cast<int64_t>(ci) * ldc + co
+                                    : static_cast<int64_t>(co) * ldc + ci;
+    float v = 0.f;
+    if (kind < 2) {
+      v = dwt[t * mat_stride + elem];
+    } else {
+      const int ky = t / 3, kx = t - ky * 3;
+      for (int a = 0; a < 2; ++a)
+        for (int ti = 0; ti < 2; ++ti) {
+          int y0, y1;
+          merged_range(a, ti, y0, y1);
+          if (ky < y0 || ky > y1) continue;
+          for (int b = 0; b < 2; ++b)
+            for (int tj = 0; tj < 2; ++tj) {
+              int x0, x1;
+              merged_range(b, tj, x0, x1);
+              if (kx < x0 || kx > x1) continue;
+              const int tap = (a << 3) | (b << 2) | (ti << 1) | tj;
+              v += dwt[tap * mat_stride + elem];
+            }
+        }
+    }
+    dw[i] = v * a_;
+  }
+}
+
+}  // namespace cpcsv
+
+using namespace cpcsv;
+
+#define STREAM(s) static_cast<cudaStream_t>(s)
+
+extern "C" int cpcsv_bn_stats(const float* x, int64_t rows, int32_t C, int64_t ldx, double* stats,
+                              cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(x && stats && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_stats: args");
+  cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, STREAM(stream));
+  dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), 1);
+  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 4, grid.x);
+  const int64_t max_gy = ceil_div(rows, 8);
+  if (gy > max_gy) gy = max_gy;
+  grid.y = static_cast<unsigned>(gy < 1 ? 1 : gy);
+  bn_stats_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, rows, C, ldx, stats);
+  return launched("bn_stats");
+}
+
+extern "C" int cpcsv_bn_finalize(const double* stats, int64_t rows, int32_t C, const float* gamma,
+                                 const float* beta, float* running_mean, float* running_var,
+                                 const int32_t* chan_map, int32_t C_valid, float eps, float momentum,
+                                 float* mean, float* invstd, float* scale, float* shift,
+                                 cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(stats && gamma && beta && mean && invstd && scale && shift && C > 0 && C_valid <= C,
+                "bn_finalize: args");
+  bn_finalize_kernel<<<static_cast<unsigned>(ceil_div(C, 256)), 256, 0, STREAM(stream)>>>(
+      stats, rows, C, gamma, beta, running_mean, running_var, chan_map, C_valid, eps, momentum, mean,
+      invstd, scale, shift);
+  return launched("bn_finalize");
+}
+
+extern "C" int cpcsv_bn_act_pack(const float* x, int64_t rows, int32_t C, int64_t ldx,
+                                 const float* scale, const float* shift, int32_t act,
+                                 const float* mod, int64_t ldmod, float* y, int64_t ldy, void* hi,
+                                 void* lo, int64_t ldp, int32_t dtype, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(x && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_act_pack: args");
+  CPCSV_REQUIRE((!mod || ldmod % 4 == 0) && (!y || ldy % 4 == 0) && (!hi || ldp % 4 == 0),
+                "bn_act_pack: pitches must be multiples of 4");
+  CPCSV_REQUIRE(hi || y, "bn_act_pack: no output");
+  CPCSV_REQUIRE(!lo || hi, "bn_act_pack: lo without hi");
+  const int64_t work = rows * (C / 4);
+  bn_act_pack_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
+      x, rows, C, ldx, scale, shift, act, mod, ldmod, y, ldy, static_cast<uint16_t*>(hi),
+      static_cast<uint16_t*>(lo), ldp, dtype);
+  return launched("bn_act_pack");
+}
+
+extern "C" int cpcsv_bn_bwd_reduce(const float* x, const float* dy, int64_t rows, int32_t C,
+                                   int64_t ldx, int64_t lddy, const float* scale, const float* shift,
+                                   const float* mean, const float* invstd, int32_t act,
+                                   const float* mod, int64_t ldmod, double* sums,
+                                   cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(x && dy && sums && mean && invstd && rows > 0 && C > 0 && C % 4 == 0 &&
+                    ldx % 4 == 0 && lddy % 4 == 0,
+                "bn_bwd_reduce: args");
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, STREAM(stream));
+  dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), 1);
+  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 4, grid.x);
+  const int64_t max_gy = ceil_div(rows, 8);
+  if (gy > max_gy) gy = max_gy;
+  grid.y = static_cast<unsigned>(gy < 1 ? 1 : gy);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, dy, rows, C, ldx, lddy, scale, shift, mean,
+                                                         invstd, act, mod, ldmod, sums);
+  return launched("bn_bwd_reduce");
+}
+
+extern "C" int cpcsv_bn_bwd_apply(const float* x, const float* dy, int64_t rows, int32_t C,
+                                  int64_t ldx, int64_t lddy, const float* scale, const float* shift,
+                                  const float* mean, const float* invstd, const float* gamma,
+                                  const int32_t* chan_map, int32_t C_valid, int32_t act,
+                                  const float* mod, int64_t ldmod, const double* sums, int32_t has_bn,
+                                  float* dx, int64_t lddx, void* dx16, int64_t ld16, float* dmod,
+                                  int64_t lddmod, void* dmod16, int64_t lddmod16, float* dgamma,
+                                  float* dbeta, cpcsv_stream_t stream) {
+  (void)gamma;
+  CPCSV_REQUIRE(x && dy && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0,
+                "bn_bwd_apply: args");
+  CPCSV_REQUIRE(!has_bn || (sums && scale && mean && invstd), "bn_bwd_apply: BN tensors missing");
+  const int64_t work = rows * (C / 4);
+  bn_bwd_apply_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
+      x, dy, rows, C, ldx, lddy, scale, shift, mean, invstd, gamma, chan_map, C_valid, act, mod, ldmod,
+      sums, has_bn, dx, lddx, static_cast<uint16_t*>(dx16), ld16, dmod, lddmod,
+      static_cast<uint16_t*>(dmod16), lddmod16, dgamma, dbeta);
+  return launched("bn_bwd_apply");
+}
+
+extern "C" int cpcsv_pack_nchw(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t sn,
+                               int64_t sc, int64_t sh, int64_t sw, const float* bcast, int32_t Cb,
+                               int64_t ldb, void* hi, void* lo, int32_t Cpad, int32_t dtype,
+                               cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(x && hi && N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C + Cb, "pack_nchw: args");
+  const int64_t work = static_cast<int64_t>(N) * H * W * Cpad;
+  pack_nchw_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
+      x, N, C, H, W, sn, sc, sh, sw, bcast, Cb, ldb, static_cast<uint16_t*>(hi),
+      static_cast<uint16_t*>(lo), Cpad, dtype);
+  return launched("pack_nchw");
+}
+
+extern "C" int cpcsv_im2col_small(const float* x, int32_t N, int32_t C, int32_t H, int32_t W,
+                                  int64_t sn, int64_t sc, int64_t sh, int64_t sw, int32_t k, int32_t s,
+                                  int32_t p, void* hi, void* lo, int32_t ldp, int32_t dtype,
+                                  cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(x && hi && N > 0 && C > 0 && k * k * C <= ldp, "im2col_small: args");
+  const int OH = (H + 2 * p - k) / s + 1, OW = (W + 2 * p - k) / s + 1;
+  const int64_t work = static_cast<int64_t>(N) * OH * OW * ldp;
+  im2col_small_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
+      x, N, C, H, W, sn, sc, sh, sw, k, s, p, OH, OW, static_cast<uint16_t*>(hi),
+      static_cast<uint16_t*>(lo), ldp, dtype);
+  return launched("im2col_small");
+}
+
+extern "C" int cpcsv_col2im_small(const float* dcol, int64_t ldc, int32_t N, int32_t C, int32_t H,
+                                  int32_t W, int32_t k, int32_t s, int32_t p, float* dx,
+                                  cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(dcol && dx && N > 0 && C > 0, "col2im_small: args");
+  const int OH = (H + 2 * p - k) / s + 1, OW = (W + 2 * p - k) / s + 1;
+  const int64_t work = static_cast<int64_t>(N) * C * H * W;
+  col2im_small_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(dcol, ldc, N, C, H, W, k, s, p,
+                                                                       OH, OW, dx);
+  return launched("col2im_small");
+}
+
+extern "C" int cpcsv_tanh_to_nchw(const float* z, int64_t ldz, int32_t N, int32_t C, int32_t H,
+                                  int32_t W, float* y, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(z && y && N > 0 && C > 0, "tanh_to_nchw: args");
+  const int64_t work = static_cast<int64_t>(N) * C * H * W;
+  tanh_to_nchw_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(z, ldz, N, C, H, W, y);
+  return launched("tanh_to_nchw");
+}
+
+extern "C" int cpcsv_tanh_bwd_im2col(const float* dy, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                                     const float* y, int32_t N, int32_t C, int32_t H, int32_t W,
+                                     void* col, int32_t ldp, int32_t dtype, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(dy && y && col && 9 * C <= ldp, "tanh_bwd_im2col: args");
+  const int64_t work = static_cast<int64_t>(N) * H * W * ldp;
+  tanh_bwd_im2col_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
+      dy, sn, sc, sh, sw, y, N, C, H, W, static_cast<uint16_t*>(col), ldp, dtype);
+  return launched("tanh_bwd_im2col");
+}
+
+extern "C" int cpcsv_pack_matrix(const float* w, int64_t rows_out, int64_t cols_out,
+                                 int64_t cols_valid, int64_t ld_r, int64_t ld_c,
+                                 const int32_t* row_map, void* hi, void* lo, int64_t ldo,
+                                 int32_t dtype, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(w && hi && rows_out > 0 && cols_out > 0 && ldo >= cols_out, "pack_matrix: args");
+  pack_matrix_kernel<<<grid_for(rows_out * cols_out, 256), 256, 0, STREAM(stream)>>>(
+      w, rows_out, cols_out, cols_valid, ld_r, ld_c, row_map, static_cast<uint16_t*>(hi),
+      static_cast<uint16_t*>(lo), ldo, dtype);
+  return launched("pack_matrix");
+}
+
+extern "C" int cpcsv_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t kh,
+                                      int32_t kw, int32_t kind, int32_t rows_pad, int32_t cols_pad,
+                                      void* hi, void* lo, int32_t dtype, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(w && hi && kind >= 0 && kind <= 3, "pack_conv_weight: args");
+  CPCSV_REQUIRE(kind < 2 || (kh == 3 && kw == 3), "pack_conv_weight: sub-pixel merge needs 3x3");
+  const bool tr = (kind == 1 || kind == 3);
+  CPCSV_REQUIRE(rows_pad >= (tr ? Cin : Cout) && cols_pad >= (tr ? Cout : Cin),
+                "pack_conv_weight: padding smaller than the matrix");
+  const int ntap = kind >= 2 ? 16 : kh * kw;
+  const int64_t work = static_cast<int64_t>(ntap) * rows_pad * cols_pad;
+  pack_conv_weight_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
+      w, Cout, Cin, kh, kw, kind, rows_pad, cols_pad, static_cast<uint16_t*>(hi),
+      static_cast<uint16_t*>(lo), dtype);
+  return launched("pack_conv_weight");
+}
+
+extern "C" int cpcsv_unpack_conv_wgrad(const float* dwt, int64_t mat_stride, int64_t ldc,
+                                       int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
+                                       int32_t kind, const float* alpha, float* dw,
+                                       cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(dwt && dw && kind >= 0 && kind <= 3, "unpack_conv_wgrad: args");
+  CPCSV_REQUIRE(kind < 2 || (kh == 3 && kw == 3), "unpack_conv_wgrad: sub-pixel merge needs 3x3");
+  const int64_t work = static_cast<int64_t>(Cout) * Cin * kh * kw;
+  unpack_conv_wgrad_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
+      dwt, mat_stride, ldc, Cout, Cin, kh, kw, kind, alpha, dw);
+  return launched("unpack_conv_wgrad");
+}
