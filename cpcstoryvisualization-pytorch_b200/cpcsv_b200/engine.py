@@ -1,0 +1,300 @@
+"""Layer-level execution engine: a tiny reverse-mode tape over NHWC buffers whose every
+arithmetic step is a libcpcsv.so kernel (``ops``).  ``model.py`` builds one tape per network
+call (generator trunk, discriminator encoder, logits head) and exposes it to PyTorch autograd
+as a single ``torch.autograd.Function``.
+
+Precision recipe: forward convolutions whose result feeds a backward
+pass run with hi/lo split bf16 operands (3 MMAs, ~16-bit significand); backward GEMMs (dgrad,
+wgrad) are single-pass bf16; statistics, normalisation and all gradients are fp32.
+"""
+import torch
+
+from . import conv, ops
+from .ops import ACT_NONE, ACT_RELU, ACT_LRELU, BF16  # noqa: F401
+
+
+def rup(x, m):
+    return (x + m - 1) // m * m
+
+
+class T4:
+    """NHWC tensor record: fp32 values and/or 16-bit operand planes, plus gradient slots."""
+
+    __slots__ = ("N", "H", "W", "C", "f32", "hi", "lo", "grad", "grad16", "needs_grad")
+
+    def __init__(self, N, H, W, C):
+        self.N, self.H, self.W, self.C = N, H, W, C
+        self.f32 = self.hi = self.lo = self.grad = self.grad16 = None
+        self.needs_grad = False
+
+    @property
+    def rows(self):
+        return self.N * self.H * self.W
+
+    def mat(self, t):
+        return t.view(self.rows, self.C)
+
+    def planes(self, n):
+        return [self.hi, self.lo if n == 2 else None]
+
+
+class WeightCache:
+    """16-bit operand planes of parameters, re-packed only when the parameter changed."""
+
+    def __init__(self):
+        self.d = {}
+        self.epoch = 0
+
+    def invalidate(self):
+        self.epoch += 1
+
+    def get(self, key, param, build):
+        tag = (param._version, param.data_ptr(), self.epoch)
+        ent = self.d.get(key)
+        if ent is not None and ent[0] == tag:
+            return ent[1]
+        val = build()
+        self.d[key] = (tag, val)
+        return val
+
+
+def _e(shape, dev, dtype=torch.float32):
+    return torch.empty(shape, device=dev, dtype=dtype)
+
+
+# ------------------------------------------------------------------------------ conv nodes
+CONV_GEOM = {
+    # kind: (kernel, fwd pack kind, dgrad pack kind, wgrad taps, unpack kind, out scale)
+    "s1": (3, 0, 1, 9, 0),
+    "up": (3, 2, 3, 16, 2),
+    "s2": (4, 0, 1, 16, 0),
+}
+
+
+class ConvNode:
+    """3x3 s1 / nearest-x2+3x3 / 4x4 s2 convolution, optionally spectrally normalised
+    (weight = weight_orig / sigma applied as the epilogue scalar alpha)."""
+
+    def __init__(self, tape, kind, x, weight, name, sn=None):
+        self.tape, self.kind, self.x, self.w, self.name, self.sn = tape, kind, x, weight, name, sn
+        Co, Ci = weight.shape[0], weight.shape[1]
+        self.Co, self.Ci = Co, Ci
+        self.Co_pad, self.Ci_pad = rup(Co, 64), x.C
+        assert rup(Ci, 64) == x.C, (name, Ci, x.C)
+        N, H, W = x.N, x.H, x.W
+        if kind == "up":
+            H, W = 2 * H, 2 * W
+        elif kind == "s2":
+            H, W = H // 2, W // 2
+        self.out = T4(N, H, W, self.Co_pad)
+        self.alpha = None
+        self.dW = None
+
+    def _pack(self, kindcode, rows_pad, cols_pad, planes):
+        w = self.w
+        ntap = CONV_GEOM[self.kind][3]
+
+        def build():
+            dev = w.device
+            hi = _e((ntap * rows_pad, cols_pad), dev, torch.bfloat16)
+            lo = _e((ntap * rows_pad, cols_pad), dev, torch.bfloat16) if planes == 2 else None
+            ops.pack_conv_weight(w.detach(), kindcode, rows_pad, cols_pad, hi, lo)
+            return [hi, lo]
+        return self.tape.cache.get((id(w), kindcode, planes), w, build)
+
+    def forward(self):
+        t, x, out = self.tape, self.x, self.out
+        dev = x.hi.device
+        if self.sn is not None:
+            self.alpha = self.sn.forward(self.w, t.training, t.need_grad)
+        wp = self._pack(CONV_GEOM[self.kind][1], self.Co_pad, self.Ci_pad, t.planes)
+        out.f32 = _e((out.N, out.H, out.W, out.C), dev)
+        xp = x.planes(t.planes)
+        if self.kind == "s1":
+            job = conv.conv_s1_fwd(xp, wp, out.f32, 3, self.alpha)
+        elif self.kind == "up":
+            job = conv.upconv_fwd(xp, wp, out.f32)
+        else:
+            job = conv.conv_s2_fwd(xp, wp, out.f32, self.alpha)
+        ops.conv_gemm(job)
+
+    def backward(self, need_wgrad=True):
+        x, out = self.x, self.out
+        dz = out.grad16
+        assert dz is not None, self.name
+        dev = dz.device
+        k, _, dkind, ntap, ukind = CONV_GEOM[self.kind]
+        if need_wgrad:
+            dwt = _e((ntap, self.Co_pad, self.Ci_pad), dev)
+            if self.kind == "s1":
+                job = conv.conv_s1_wgrad(dz, x.hi, dwt, 3)
+            elif self.kind == "up":
+                job = conv.upconv_wgrad(dz, x.hi, dwt)
+            else:
+                job = conv.conv_s2_wgrad(dz, x.hi, dwt)
+            ops.conv_gemm(job)
+            g = _e(tuple(self.w.shape), dev)
+            ops.unpack_conv_wgrad(dwt, self.Co_pad * self.Ci_pad, self.Ci_pad, ukind, None, g)
+            self.dW = self.sn.backward(g, self.w) if self.sn is not None else g
+        if x.needs_grad:
+            wt = self._pack(dkind, self.Ci_pad, self.Co_pad, 1)[0]
+            acc = x.grad is not None
+            if not acc:
+                x.grad = _e((x.N, x.H, x.W, x.C), dev)
+            if self.kind == "s1":
+                job = conv.conv_s1_dgrad(dz, wt, x.grad, 3, self.alpha, acc)
+            elif self.kind == "up":
+                job = conv.upconv_dgrad(dz, wt, x.grad, acc)
+            else:
+                assert not acc
+                job = conv.conv_s2_dgrad(dz, wt, x.grad, self.alpha)
+            ops.conv_gemm(job)
+        out.grad16 = None
+
+
+class SpectralNorm:
+    """Legacy torch spectral_norm semantics (1 power iteration per forward call in train mode,
+    u/v buffers updated in place; reference model.py:5,19,79)."""
+
+    def __init__(self, u, v):
+        self.u, self.v = u, v
+        self.saved = None
+
+    def forward(self, w_orig, training, need_grad):
+        dev = w_orig.device
+        R = w_orig.shape[0]
+        w2d = w_orig.detach().view(R, -1)
+        sig = _e((2,), dev)
+        scratch = _e((R + w2d.shape[1],), dev)
+        ops.spectral_sigma(w2d, self.u, self.v, training, sig[0:1], sig[1:2], scratch)
+        if need_grad:
+            self.saved = (self.u.clone(), self.v.clone(), sig)
+        return sig[1:2]
+
+    def backward(self, g, w_orig):
+        u, v, sig = self.saved
+        R = w_orig.shape[0]
+        dw = torch.empty_like(g)
+        ops.spectral_bwd(g.view(R, -1), w_orig.detach().view(R, -1), u, v, sig[0:1], dw.view(R, -1),
+                         _e((4,), g.device))
+        return dw
+
+
+class GemmNode:
+    """out[rows, Npad] = x[rows, K] @ W^T for a Linear whose packed weight is supplied by
+    ``pack(planes) -> [hi, lo]`` (row re-ordering / padding is the packer's business)."""
+
+    def __init__(self, tape, x, n_out_pad, pack_fwd, pack_bwd, name, out_shape=None):
+        self.tape, self.x, self.name = tape, x, name
+        self.pack_fwd, self.pack_bwd = pack_fwd, pack_bwd
+        N, H, W = out_shape if out_shape else (x.N, x.H, x.W)
+        self.out = T4(N, H, W, n_out_pad // (H * W) if out_shape else n_out_pad)
+        self.npad = n_out_pad
+        self.dwt = None
+
+    def forward(self):
+        t, x, out = self.tape, self.x, self.out
+        dev = x.hi.device
+        out.f32 = _e((out.N, out.H, out.W, out.C), dev)
+        a = [p.view(x.rows, x.C) if p is not None else None for p in x.planes(t.planes)]
+        ops.conv_gemm(conv.gemm_nt(a, self.pack_fwd(t.planes), out.f32.view(x.rows, self.npad)))
+
+    def backward(self, need_wgrad=True):
+        x, out = self.x, self.out
+        dz = out.grad16.view(x.rows, self.npad)
+        dev = dz.device
+        if need_wgrad:
+            self.dwt = _e((self.npad, x.C), dev)
+            ops.conv_gemm(conv.gemm_tn(dz, x.hi.view(x.rows, x.C), self.dwt))
+        if x.needs_grad:
+            acc = x.grad is not None
+            if not acc:
+                x.grad = _e((x.N, x.H, x.W, x.C), dev)
+            ops.conv_gemm(conv.gemm_nt([dz, None], [self.pack_bwd(), None], x.grad.view(x.rows, x.C),
+                                       accumulate=acc))
+        out.grad16 = None
+
+
+# ------------------------------------------------------------------------------ BN / act node
+class BnActNode:
+    """[BatchNorm (batch statistics)] -> activation -> [* (1 + mod)] -> operand planes / fp32."""
+
+    def __init__(self, tape, z, bn, act, name, mod=None, want_f32=False, want_planes=True,
+                 chan_map=None, c_valid=None):
+        self.tape, self.z, self.bn, self.act, self.name, self.mod = tape, z, bn, act, name, mod
+        self.want_f32, self.want_planes, self.chan_map = want_f32, want_planes, chan_map
+        self.c_valid = c_valid if c_valid is not None else (bn[0].numel() if bn else z.C)
+        self.out = T4(z.N, z.H, z.W, z.C)
+        self.stat = None
+        self.dgamma = self.dbeta = None
+
+    def forward(self):
+        t, z, out = self.tape, self.z, self.out
+        dev = z.f32.device
+        zm = z.mat(z.f32)
+        scale = shift = None
+        if self.bn is not None:
+            gamma, beta, rmean, rvar, nbt = self.bn
+            stats = _e((2 * z.C,), dev, torch.float64)
+            ops.bn_stats(zm, stats)
+            vec = _e((4, z.C), dev)
+            ops.bn_finalize(stats, z.rows, gamma.detach(), beta.detach(),
+                            rmean if t.training else None, rvar if t.training else None,
+                            self.chan_map, self.c_valid, vec[0], vec[1], vec[2], vec[3])
+            if t.training and nbt is not None:
+                nbt.add_(1)
+            self.stat = vec
+            scale, shift = vec[2], vec[3]
+        if self.want_f32:
+            out.f32 = _e((z.N, z.H, z.W, z.C), dev)
+        if self.want_planes:
+            out.hi = _e((z.N, z.H, z.W, z.C), dev, torch.bfloat16)
+            out.lo = _e((z.N, z.H, z.W, z.C), dev, torch.bfloat16) if t.planes == 2 else None
+        ops.bn_act_pack(zm, scale, shift, self.act, z.mat(self.mod.f32) if self.mod is not None else None,
+                        z.mat(out.f32) if out.f32 is not None else None,
+                        z.mat(out.hi) if out.hi is not None else None,
+                        z.mat(out.lo) if out.lo is not None else None)
+        if not t.need_grad:
+            z.f32 = None if self.mod is None and not self._keep_z() else z.f32
+
+    def _keep_z(self):
+        return False
+
+    def backward(self, need_param_grad=True):
+        z, out = self.z, self.out
+        dy = out.grad
+        assert dy is not None, self.name
+        dev = dy.device
+        zm, dym = z.mat(z.f32), z.mat(dy)
+        has_bn = self.bn is not None
+        modm = z.mat(self.mod.f32) if self.mod is not None else None
+        sums = None
+        if has_bn:
+            vec = self.stat
+            sums = _e((2 * z.C,), dev, torch.float64)
+            ops.bn_bwd_reduce(zm, dym, vec[2], vec[3], vec[0], vec[1], self.act, modm, sums)
+            if need_param_grad:
+                self.dgamma = torch.zeros_like(self.bn[0])
+                self.dbeta = torch.zeros_like(self.bn[1])
+        z.grad16 = _e((z.N, z.H, z.W, z.C), dev, torch.bfloat16)
+        dmod16 = None
+        if self.mod is not None:
+            dmod16 = _e((z.N, z.H, z.W, z.C), dev, torch.bfloat16)
+            self.mod.grad16 = dmod16
+        vec = self.stat if has_bn else (None, None, None, None)
+        ops.bn_bwd_apply(zm, dym, vec[2], vec[3], vec[0], vec[1], self.chan_map, self.c_valid, self.act,
+                         modm, sums, has_bn, dx=None, dx16=z.mat(z.grad16), dmod=None,
+                         dmod16=z.mat(dmod16) if dmod16 is not None else None,
+                         dgamma=self.dgamma, dbeta=self.dbeta)
+        out.grad = None
+
+
+class Tape:
+    def __init__(self, cache, training=True, need_grad=True, planes=2):
+        self.cache, self.training, self.need_grad, self.planes = cache, training, need_grad, planes
+        self.nodes = []
+
+    def add(self, node):
+        self.nodes.append(node)
+        node.forward()
+        return node.out if hasattr(node, "out") else None

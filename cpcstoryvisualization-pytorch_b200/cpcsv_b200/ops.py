@@ -215,10 +215,16 @@ def tanh_bwd_im2col(dy, y, col, dtype=BF16):
         col.stride(0), dtype, _stream()), "cpcsv_tanh_bwd_im2col")
 
 
-def pack_matrix(w, rows_out, cols_out, cols_valid, ld_r, ld_c, row_map, hi, lo, dtype=BF16):
+def pack_matrix(w, rows_out, cols_out, cols_valid, ld_r, ld_c, row_map, hi, lo, dtype=BF16, col_map=None):
     _lib.check(_lib.load().cpcsv_pack_matrix(
         _ptr(w, torch.float32), rows_out, cols_out, cols_valid, ld_r, ld_c, _ptr(row_map, torch.int32),
-        _ptr(hi), _ptr(lo), hi.stride(0), dtype, _stream()), "cpcsv_pack_matrix")
+        _ptr(col_map, torch.int32), _ptr(hi), _ptr(lo), hi.stride(0), dtype, _stream()), "cpcsv_pack_matrix")
+
+
+def scatter_rows_f32(src, row_map, dst, rows, cols):
+    _lib.check(_lib.load().cpcsv_scatter_rows_f32(
+        _ptr(src, torch.float32), src.stride(0), _ptr(row_map, torch.int32), _ptr(dst, torch.float32),
+        dst.stride(0), rows, cols, _stream()), "cpcsv_scatter_rows_f32")
 
 
 def pack_conv_weight(w, kind, rows_pad, cols_pad, hi, lo, dtype=BF16):

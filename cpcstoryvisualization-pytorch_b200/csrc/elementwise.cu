@@ -421,7 +421,8 @@ __global__ void tanh_bwd_im2col_kernel(const float* __restrict__ dy, int64_t sn,
 // ------------------------------------------------------------------------- weight packing
 __global__ void pack_matrix_kernel(const float* __restrict__ w, int64_t rows_out, int64_t cols_out,
                                    int64_t cols_valid, int64_t ld_r, int64_t ld_c,
-                                   const int32_t* __restrict__ row_map, uint16_t* __restrict__ hi,
+                                   const int32_t* __restrict__ row_map,
+                                   const int32_t* __restrict__ col_map, uint16_t* __restrict__ hi,
                                    uint16_t* __restrict__ lo, int64_t ldo, int dtype) {
   const int64_t total = rows_out * cols_out;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -430,12 +431,25 @@ __global__ void pack_matrix_kernel(const float* __restrict__ w, int64_t rows_out
     float v = 0.f;
     if (c < cols_valid) {
       const int64_t rs = row_map ? row_map[r] : r;
-      if (rs >= 0) v = w[rs * ld_r + c * ld_c];
+      const int64_t cs = col_map ? col_map[c] : c;
+      if (rs >= 0 && cs >= 0) v = w[rs * ld_r + cs * ld_c];
     }
     uint16_t hv, lv;
     split16(v, dtype, hv, lv);
     hi[r * ldo + c] = hv;
     if (lo) lo[r * ldo + c] = lv;
+  }
+}
+
+__global__ void scatter_rows_kernel(const float* __restrict__ src, int64_t ld_src,
+                                    const int32_t* __restrict__ row_map, float* __restrict__ dst,
+                                    int64_t ld_dst, int64_t rows, int64_t cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    const int64_t rd = row_map ? row_map[r] : r;
+    dst[rd * ld_dst + c] = src[r * ld_src + c];
   }
 }
 
@@ -663,13 +677,22 @@ extern "C" int cpcsv_tanh_bwd_im2col(const float* dy, int64_t sn, int64_t sc, in
 
 extern "C" int cpcsv_pack_matrix(const float* w, int64_t rows_out, int64_t cols_out,
                                  int64_t cols_valid, int64_t ld_r, int64_t ld_c,
-                                 const int32_t* row_map, void* hi, void* lo, int64_t ldo,
-                                 int32_t dtype, cpcsv_stream_t stream) {
+                                 const int32_t* row_map, const int32_t* col_map, void* hi, void* lo,
+                                 int64_t ldo, int32_t dtype, cpcsv_stream_t stream) {
   CPCSV_REQUIRE(w && hi && rows_out > 0 && cols_out > 0 && ldo >= cols_out, "pack_matrix: args");
   pack_matrix_kernel<<<grid_for(rows_out * cols_out, 256), 256, 0, STREAM(stream)>>>(
-      w, rows_out, cols_out, cols_valid, ld_r, ld_c, row_map, static_cast<uint16_t*>(hi),
+      w, rows_out, cols_out, cols_valid, ld_r, ld_c, row_map, col_map, static_cast<uint16_t*>(hi),
       static_cast<uint16_t*>(lo), ldo, dtype);
   return launched("pack_matrix");
+}
+
+extern "C" int cpcsv_scatter_rows_f32(const float* src, int64_t ld_src, const int32_t* row_map,
+                                      float* dst, int64_t ld_dst, int64_t rows, int64_t cols,
+                                      cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(src && dst && rows > 0 && cols > 0, "scatter_rows_f32: args");
+  scatter_rows_kernel<<<grid_for(rows * cols, 256), 256, 0, STREAM(stream)>>>(src, ld_src, row_map, dst,
+                                                                             ld_dst, rows, cols);
+  return launched("scatter_rows_f32");
 }
 
 extern "C" int cpcsv_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t kh,

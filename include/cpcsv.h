@@ -153,12 +153,17 @@ int cpcsv_tanh_to_nchw(const float* z, int64_t ldz, int32_t N, int32_t C, int32_
 int cpcsv_tanh_bwd_im2col(const float* dy, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
                           const float* y, int32_t N, int32_t C, int32_t H, int32_t W, void* col,
                           int32_t ldp, int32_t dtype, cpcsv_stream_t stream);
-/* fp32 [rows, cols] (pitch ld) -> 16-bit hi/lo with optional row gather, column padding and
- * transposition; the weight re-layout for the GEMM B operand. out[r, c] for r < rows_out,
- * c < cols_out;  src element = w[ridx(r) * ld_r + c * ld_c] */
+/* fp32 matrix -> 16-bit hi/lo with optional row / column gather, column padding and
+ * transposition; the weight re-layout for the GEMM B operand of the Linear layers.
+ * out[r, c] = w[rmap(r) * ld_r + cmap(c) * ld_c] for c < cols_valid, else 0 (a negative map
+ * entry also gives 0).  Used for fc / fc_seg (model.py:260-263,285-288), whose output
+ * features are re-ordered from (c, y, x) to NHWC (y, x, c) at pack time. */
 int cpcsv_pack_matrix(const float* w, int64_t rows_out, int64_t cols_out, int64_t cols_valid,
-                      int64_t ld_r, int64_t ld_c, const int32_t* row_map, void* hi, void* lo,
-                      int64_t ldo, int32_t dtype, cpcsv_stream_t stream);
+                      int64_t ld_r, int64_t ld_c, const int32_t* row_map, const int32_t* col_map,
+                      void* hi, void* lo, int64_t ldo, int32_t dtype, cpcsv_stream_t stream);
+/* dst[row_map[r], c] = src[r, c]  (fp32; undoes the row re-ordering for weight gradients) */
+int cpcsv_scatter_rows_f32(const float* src, int64_t ld_src, const int32_t* row_map, float* dst,
+                           int64_t ld_dst, int64_t rows, int64_t cols, cpcsv_stream_t stream);
 /* conv weight [Cout, Cin, kh, kw] fp32 -> tap-major GEMM operands.
  *  kind 0: plain taps          out[tap][co][ci]        (fprop B)
  *  kind 1: plain taps, transposed  out[tap][ci][co]    (dgrad B)

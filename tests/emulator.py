@@ -293,18 +293,25 @@ def tanh_bwd_im2col(dy, y, col, dtype=1):
     col.copy_(out.reshape(N * H * W, -1).to(TORCH16[dtype]))
 
 
-def pack_matrix(w, rows_out, cols_out, cols_valid, ld_r, ld_c, row_map, hi, lo, dtype=1):
+def pack_matrix(w, rows_out, cols_out, cols_valid, ld_r, ld_c, row_map, hi, lo, dtype=1, col_map=None):
     flat = w.reshape(-1)
     r = row_map.long() if row_map is not None else torch.arange(rows_out)
     full = torch.zeros(rows_out, cols_out)
     cidx = torch.arange(cols_valid)
+    csrc = col_map.long()[:cols_valid] if col_map is not None else cidx
     ok = r >= 0
-    idx = r[ok].view(-1, 1) * ld_r + cidx.view(1, -1) * ld_c
-    full[ok.nonzero().view(-1, 1), cidx.view(1, -1)] = flat[idx]
+    cok = csrc >= 0
+    idx = r[ok].view(-1, 1) * ld_r + csrc[cok].view(1, -1) * ld_c
+    full[ok.nonzero().view(-1, 1), cidx[cok].view(1, -1)] = flat[idx]
     h, l = _split16(full, dtype)
     hi[:rows_out, :cols_out].copy_(h)
     if lo is not None:
         lo[:rows_out, :cols_out].copy_(l)
+
+
+def scatter_rows_f32(src, row_map, dst, rows, cols):
+    r = row_map.long()[:rows] if row_map is not None else torch.arange(rows)
+    dst[r, :cols] = src[:rows, :cols]
 
 
 _MERGE = {(0, 0): (0, 0), (0, 1): (1, 2), (1, 0): (0, 1), (1, 1): (2, 2)}

@@ -1,0 +1,181 @@
+"""Every non-GEMM libcpcsv.so kernel against the CPU emulator of its contract (and thereby
+against the torch formulas the emulator is written in).  GPU only."""
+import pytest
+import torch
+
+import emulator as emu
+from cpcsv_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def both(fn_name, inputs, outputs, **kw):
+    """run ops.<fn> on cuda copies and emulator.<fn> on cpu copies; returns (gpu_outs, cpu_outs)"""
+    def to(x, dev):
+        return x.to(dev).clone() if torch.is_tensor(x) else x
+    res = []
+    for dev, mod in (("cuda", ops), ("cpu", emu)):
+        args = [to(a, dev) for a in inputs]
+        outs = {k: (to(v, dev) if v is not None else None) for k, v in outputs.items()}
+        getattr(mod, fn_name)(*args, **outs, **kw)
+        if dev == "cuda":
+            torch.cuda.synchronize()
+        res.append(({k: (v.cpu() if v is not None else None) for k, v in outs.items()},
+                    [a.cpu() if torch.is_tensor(a) else a for a in args]))
+    return res
+
+
+def close(a, b, tol=1e-5):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30)) < tol
+
+
+def test_bn_forward_chain():
+    rows, C = 1000, 192
+    x = rnd(rows, C, seed=1) * 2 + 0.5
+    stats_g = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    ops.bn_stats(x.cuda(), stats_g)
+    stats_c = torch.zeros(2 * C, dtype=torch.float64)
+    emu.bn_stats(x, stats_c)
+    assert close(stats_g.cpu(), stats_c, 1e-10)
+    gamma, beta = rnd(256, seed=2), rnd(256, seed=3)
+    cmap = torch.randperm(256, generator=torch.Generator().manual_seed(4))[:C].int()
+    outs = {}
+    for dev, mod in (("cuda", ops), ("cpu", emu)):
+        rm, rv = torch.zeros(256, device=dev), torch.ones(256, device=dev)
+        o = [torch.empty(C, device=dev) for _ in range(4)]
+        mod.bn_finalize(stats_c.to(dev), rows, gamma.to(dev), beta.to(dev), rm, rv, cmap.to(dev), C - 8, *o)
+        outs[dev] = [t.cpu() for t in o] + [rm.cpu(), rv.cpu()]
+    for a, b in zip(outs["cuda"], outs["cpu"]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    mean, invstd, scale, shift = outs["cpu"][:4]
+    mod_t = rnd(rows, C, seed=5, scale=0.3)
+    for act in (0, 1, 2):
+        for use_mod in (False, True):
+            (g, _), (c, _) = both("bn_act_pack", [x, scale, shift, act],
+                                  dict(mod=mod_t if use_mod else None, y=torch.empty(rows, C),
+                                       hi=torch.empty(rows, C, dtype=torch.bfloat16),
+                                       lo=torch.empty(rows, C, dtype=torch.bfloat16)))
+            assert close(g["y"], c["y"], 1e-6)
+            assert close(g["hi"].float() + g["lo"].float(), c["y"], 2e-5)
+            assert torch.equal(g["hi"], c["hi"]) or close(g["hi"].float(), c["hi"].float(), 1e-3)
+    # backward
+    dy = rnd(rows, C, seed=6)
+    for act, has_bn, use_mod in ((1, True, True), (2, True, False), (2, False, False), (0, True, False)):
+        sums = {}
+        for dev, mod in (("cuda", ops), ("cpu", emu)):
+            s = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+            mod.bn_bwd_reduce(x.to(dev), dy.to(dev), scale.to(dev) if has_bn else None,
+                              shift.to(dev) if has_bn else None, mean.to(dev), invstd.to(dev), act,
+                              mod_t.to(dev) if use_mod else None, s)
+            sums[dev] = s.cpu()
+        assert close(sums["cuda"], sums["cpu"], 1e-6)
+        (g, _), (c, _) = both(
+            "bn_bwd_apply",
+            [x, dy, scale if has_bn else None, shift if has_bn else None, mean, invstd, cmap, C - 8, act,
+             mod_t if use_mod else None, sums["cpu"], has_bn],
+            dict(dx=torch.empty(rows, C), dx16=torch.empty(rows, C, dtype=torch.bfloat16),
+                 dmod=torch.empty(rows, C) if use_mod else None,
+                 dmod16=torch.empty(rows, C, dtype=torch.bfloat16) if use_mod else None,
+                 dgamma=torch.zeros(256), dbeta=torch.zeros(256)))
+        for k in g:
+            if g[k] is not None:
+                assert close(g[k].float(), c[k].float(), 2e-3 if "16" in k else 1e-5), (k, act, has_bn)
+
+
+def test_layout_kernels():
+    x = rnd(5, 7, 4, 4, seed=7).permute(0, 1, 3, 2)       # non-contiguous NCHW
+    b = rnd(5, 9, seed=8)
+    (g, _), (c, _) = both("pack_nchw", [x, b],
+                          dict(hi=torch.empty(5 * 16, 64, dtype=torch.bfloat16),
+                               lo=torch.empty(5 * 16, 64, dtype=torch.bfloat16)), cpad=64)
+    assert torch.equal(g["hi"], c["hi"]) and torch.equal(g["lo"], c["lo"])
+    img = rnd(3, 3, 16, 16, seed=9)
+    (g, _), (c, _) = both("im2col_small", [img, 4, 2, 1],
+                          dict(hi=torch.empty(3 * 64, 64, dtype=torch.bfloat16),
+                               lo=torch.empty(3 * 64, 64, dtype=torch.bfloat16)), ldp=64)
+    assert torch.equal(g["hi"], c["hi"]) and torch.equal(g["lo"], c["lo"])
+    dcol = rnd(3 * 64, 64, seed=10)
+    (g, _), (c, _) = both("col2im_small", [dcol, 3, 3, 16, 16, 4, 2, 1], dict(dx=torch.empty(3, 3, 16, 16)))
+    assert close(g["dx"], c["dx"])
+    z = rnd(2 * 8 * 8, 16, seed=11)
+    (g, _), (c, _) = both("tanh_to_nchw", [z, 2, 3, 8, 8], dict(y=torch.empty(2, 3, 8, 8)))
+    assert close(g["y"], c["y"], 1e-6)
+    dy = rnd(2, 8, 3, 8, seed=12).permute(0, 2, 1, 3)     # strided
+    (g, _), (c, _) = both("tanh_bwd_im2col", [dy, c["y"]], dict(col=torch.empty(128, 64, dtype=torch.bfloat16)))
+    assert close(g["col"].float(), c["col"].float(), 2e-3)
+
+
+def test_weight_layout_kernels():
+    w = rnd(20, 12, 3, 3, seed=13, scale=0.05)
+    for kind in (0, 1, 2, 3):
+        rp, cp = (64, 64)
+        nt = 16 if kind >= 2 else 9
+        (g, _), (c, _) = both("pack_conv_weight", [w, kind, rp, cp],
+                              dict(hi=torch.empty(nt * rp, cp, dtype=torch.bfloat16),
+                                   lo=torch.empty(nt * rp, cp, dtype=torch.bfloat16)))
+        assert close(g["hi"].float() + g["lo"].float(), c["hi"].float() + c["lo"].float(), 1e-5), kind
+        dwt = rnd(nt, rp, cp, seed=14)
+        alpha = torch.tensor([0.7])
+        (g, _), (c, _) = both("unpack_conv_wgrad", [dwt, rp * cp, cp, kind, alpha], dict(dw=torch.empty(20, 12, 3, 3)))
+        assert close(g["dw"], c["dw"], 1e-6), kind
+    m = rnd(30, 17, seed=15)
+    rmap = torch.randint(0, 30, (40,), generator=torch.Generator().manual_seed(16)).int()
+    (g, _), (c, _) = both("pack_matrix", [m, 40, 64, 17, 17, 1, rmap],
+                          dict(hi=torch.empty(40, 64, dtype=torch.bfloat16),
+                               lo=torch.empty(40, 64, dtype=torch.bfloat16)))
+    assert torch.equal(g["hi"], c["hi"]) and torch.equal(g["lo"], c["lo"])
+
+
+def test_small_fp32_ops():
+    x, w, bias = rnd(37, 150, seed=17), rnd(70, 150, seed=18), rnd(70, seed=19)
+    (g, _), (c, _) = both("linear_f32", [x, w, bias], dict(y=torch.zeros(37, 70)))
+    assert close(g["y"], c["y"], 1e-5)
+    (g, _), (c, _) = both("linear_tn_f32", [rnd(37, 70, seed=20), x], dict(y=torch.ones(70, 150)), accumulate=True)
+    assert close(g["y"], c["y"], 1e-5)
+    (g, _), (c, _) = both("linear_nn_f32", [rnd(37, 70, seed=21), w], dict(y=torch.zeros(37, 150)))
+    assert close(g["y"], c["y"], 1e-5)
+    B, H = 9, 50
+    gi, gh, h = rnd(B, 3 * H, seed=22), rnd(B, 3 * H, seed=23), rnd(B, H, seed=24)
+    (g, _), (c, _) = both("gru_gates_fwd", [gi, gh, h], dict(hnew=torch.empty(B, H), save=torch.empty(B, 4 * H)))
+    assert close(g["hnew"], c["hnew"], 1e-5) and close(g["save"], c["save"], 1e-5)
+    (g2, _), (c2, _) = both("gru_gates_bwd", [rnd(B, H, seed=25), h, c["save"]],
+                            dict(dgi=torch.empty(B, 3 * H), dgh=torch.empty(B, 3 * H), dh=torch.empty(B, H)))
+    for k in g2:
+        assert close(g2[k], c2[k], 1e-5)
+    pre, eps = rnd(B, 24, seed=26), rnd(B, 12, seed=27)
+    (g, _), (c, _) = both("ca_fwd", [pre, eps], dict(mu=torch.empty(B, 12), logvar=torch.empty(B, 12), code=torch.empty(B, 12)))
+    for k in g:
+        assert close(g[k], c[k], 1e-5)
+    (g, _), (c, _) = both("ca_bwd", [pre, eps, rnd(B, 12, seed=28), rnd(B, 12, seed=29), rnd(B, 12, seed=30)],
+                          dict(dpre=torch.empty(B, 24)))
+    assert close(g["dpre"], c["dpre"], 1e-5)
+    img, filt = rnd(6, 3, 124, seed=31), rnd(6, 1, 3, 21, seed=32)
+    (g, _), (c, _) = both("dfn1d_fwd", [img, filt], dict(out=torch.empty(6, 1, 124)))
+    assert close(g["out"], c["out"], 1e-5)
+    (g, _), (c, _) = both("dfn1d_bwd", [img, filt, rnd(6, 1, 124, seed=33)],
+                          dict(dimg=torch.empty(6, 3, 124), dfilt=torch.empty(6, 1, 3, 21)))
+    assert close(g["dimg"], c["dimg"], 1e-5) and close(g["dfilt"], c["dfilt"], 1e-5)
+
+
+def test_spectral_norm_kernels():
+    R, Cc = 50, 333
+    w = rnd(R, Cc, seed=34, scale=0.02)
+    u = torch.nn.functional.normalize(rnd(R, seed=35), dim=0)
+    v = torch.nn.functional.normalize(rnd(Cc, seed=36), dim=0)
+    res = {}
+    for dev, mod in (("cuda", ops), ("cpu", emu)):
+        uu, vv = u.to(dev).clone(), v.to(dev).clone()
+        s, si = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+        mod.spectral_sigma(w.to(dev), uu, vv, True, s, si, torch.empty(R + Cc, device=dev))
+        g = rnd(R, Cc, seed=37).to(dev)
+        dw = torch.empty(R, Cc, device=dev)
+        mod.spectral_bwd(g, w.to(dev), uu, vv, s, dw, torch.zeros(4, device=dev))
+        res[dev] = [t.cpu() for t in (uu, vv, s, si, dw)]
+    for a, b in zip(res["cuda"], res["cpu"]):
+        assert close(a, b, 1e-5)
