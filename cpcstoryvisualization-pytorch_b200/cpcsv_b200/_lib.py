@@ -69,6 +69,8 @@ SIGNATURES = {
     "cpcsv_dfn1d_bwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p],
     "cpcsv_tanh_fwd": [_p, _p, _i64, _p],
     "cpcsv_tanh_bwd": [_p, _p, _p, _i64, _p],
+    "cpcsv_affine_sigmoid_fwd": [_p, _p, _p, _p, _i64, _p],
+    "cpcsv_affine_sigmoid_bwd": [_p, _p, _p, _p, _p, _i64, _p],
     "cpcsv_spectral_sigma": [_p, _i32, _i32, _p, _p, _i32, _f32, _p, _p, _p, _p],
     "cpcsv_spectral_bwd": [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p],
 }

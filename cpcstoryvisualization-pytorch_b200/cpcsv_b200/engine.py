@@ -184,11 +184,10 @@ class GemmNode:
     """out[rows, Npad] = x[rows, K] @ W^T for a Linear whose packed weight is supplied by
     ``pack(planes) -> [hi, lo]`` (row re-ordering / padding is the packer's business)."""
 
-    def __init__(self, tape, x, n_out_pad, pack_fwd, pack_bwd, name, out_shape=None):
+    def __init__(self, tape, x, n_out_pad, pack_fwd, pack_bwd, name):
         self.tape, self.x, self.name = tape, x, name
         self.pack_fwd, self.pack_bwd = pack_fwd, pack_bwd
-        N, H, W = out_shape if out_shape else (x.N, x.H, x.W)
-        self.out = T4(N, H, W, n_out_pad // (H * W) if out_shape else n_out_pad)
+        self.out = T4(x.N, x.H, x.W, n_out_pad)
         self.npad = n_out_pad
         self.dwt = None
 
@@ -254,11 +253,6 @@ class BnActNode:
                         z.mat(out.f32) if out.f32 is not None else None,
                         z.mat(out.hi) if out.hi is not None else None,
                         z.mat(out.lo) if out.lo is not None else None)
-        if not t.need_grad:
-            z.f32 = None if self.mod is None and not self._keep_z() else z.f32
-
-    def _keep_z(self):
-        return False
 
     def backward(self, need_param_grad=True):
         z, out = self.z, self.out
@@ -279,8 +273,9 @@ class BnActNode:
         z.grad16 = _e((z.N, z.H, z.W, z.C), dev, torch.bfloat16)
         dmod16 = None
         if self.mod is not None:
-            dmod16 = _e((z.N, z.H, z.W, z.C), dev, torch.bfloat16)
-            self.mod.grad16 = dmod16
+            m = self.mod
+            dmod16 = _e((m.N, m.H, m.W, m.C), dev, torch.bfloat16)
+            m.grad16 = dmod16
         vec = self.stat if has_bn else (None, None, None, None)
         ops.bn_bwd_apply(zm, dym, vec[2], vec[3], vec[0], vec[1], self.chan_map, self.c_valid, self.act,
                          modm, sums, has_bn, dx=None, dx16=z.mat(z.grad16), dmod=None,

@@ -1,0 +1,209 @@
+"""torch.autograd.Function wrappers of the fp32 conditioning-path kernels (CA_NET, GRU cells,
+Linear + BatchNorm1d, dynamic 1-D filter; reference model.py:37-65, 223-224, 250-257,
+302-346, layers.py:62-80).  These layers stay fp32.  Every
+forward/backward below is one or a few libcpcsv.so launches; torch only allocates.
+"""
+import torch
+
+from . import ops
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rowmat(t):
+    """2-D tensor with unit column stride (row pitch free)."""
+    if t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1) and t.stride(0) >= t.shape[1]:
+        return t
+    return t.contiguous()
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b  (fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w = _rowmat(x), _rowmat(w)
+        y = torch.empty(x.shape[0], w.shape[0], device=x.device)
+        ops.linear_f32(x, w, b, y)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _rowmat(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x, memory_format=torch.contiguous_format)
+            ops.linear_nn_f32(dy, w, dx)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(w.shape, device=w.device)
+            ops.linear_tn_f32(dy, x, dw)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            ones = torch.ones(dy.shape[0], 1, device=dy.device)
+            db = torch.empty(dy.shape[1], 1, device=dy.device)
+            ops.linear_tn_f32(dy, ones, db)
+            db = db.view(-1)
+        return dx, dw, db
+
+
+class BatchNorm1dFn(torch.autograd.Function):
+    """BatchNorm1d with batch statistics (+ optional tanh), running stats updated in place."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, rmean, rvar, nbt, training, act_tanh):
+        M, C = x.shape
+        Cp = (C + 3) // 4 * 4
+        dev = x.device
+        xp = torch.zeros(M, Cp, device=dev)
+        xp[:, :C].copy_(x)
+        stats = torch.empty(2 * Cp, device=dev, dtype=torch.float64)
+        ops.bn_stats(xp, stats)
+        vec = torch.empty(4, Cp, device=dev)
+        ops.bn_finalize(stats, M, gamma.detach(), beta.detach(), rmean if training else None,
+                        rvar if training else None, None, C, vec[0], vec[1], vec[2], vec[3])
+        if training and nbt is not None:
+            nbt.add_(1)
+        yp = torch.empty(M, Cp, device=dev)
+        ops.bn_act_pack(xp, vec[2], vec[3], ops.ACT_NONE, y=yp)
+        out = yp
+        if act_tanh:
+            out = torch.empty_like(yp)
+            ops.tanh_fwd(yp, out)
+        ctx.save_for_backward(xp, vec, out if act_tanh else None)
+        ctx.C, ctx.act_tanh = C, act_tanh
+        ctx.gshape = gamma.shape
+        return out[:, :C]
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, vec, tout = ctx.saved_tensors
+        M, Cp = xp.shape
+        C = ctx.C
+        dev = xp.device
+        dyp = torch.zeros(M, Cp, device=dev)
+        dyp[:, :C].copy_(dy)
+        if ctx.act_tanh:
+            d2 = torch.empty_like(dyp)
+            ops.tanh_bwd(tout, dyp, d2)
+            dyp = d2
+        sums = torch.empty(2 * Cp, device=dev, dtype=torch.float64)
+        ops.bn_bwd_reduce(xp, dyp, vec[2], vec[3], vec[0], vec[1], ops.ACT_NONE, None, sums)
+        dx = torch.empty(M, Cp, device=dev)
+        dgamma = torch.zeros(ctx.gshape, device=dev)
+        dbeta = torch.zeros(ctx.gshape, device=dev)
+        ops.bn_bwd_apply(xp, dyp, vec[2], vec[3], vec[0], vec[1], None, C, ops.ACT_NONE, None, sums, True,
+                         dx=dx, dgamma=dgamma, dbeta=dbeta)
+        return dx[:, :C], dgamma, dbeta, None, None, None, None, None
+
+
+class GRUCellFn(torch.autograd.Function):
+    """torch.nn.GRUCell semantics, gate order (r, z, n)."""
+
+    @staticmethod
+    def forward(ctx, x, h, w_ih, w_hh, b_ih, b_hh):
+        x, h = _rowmat(x), _c(h)
+        B, H = h.shape
+        dev = x.device
+        gi = torch.empty(B, 3 * H, device=dev)
+        gh = torch.empty(B, 3 * H, device=dev)
+        ops.linear_f32(x, w_ih, b_ih, gi)
+        ops.linear_f32(h, w_hh, b_hh, gh)
+        hnew = torch.empty(B, H, device=dev)
+        save = torch.empty(B, 4 * H, device=dev)
+        ops.gru_gates_fwd(gi, gh, h, hnew, save)
+        ctx.save_for_backward(x, h, w_ih, w_hh, save)
+        return hnew
+
+    @staticmethod
+    def backward(ctx, dhn):
+        x, h, w_ih, w_hh, save = ctx.saved_tensors
+        B, H = h.shape
+        dev = x.device
+        dhn = _c(dhn)
+        dgi = torch.empty(B, 3 * H, device=dev)
+        dgh = torch.empty(B, 3 * H, device=dev)
+        dh = torch.empty(B, H, device=dev)
+        ops.gru_gates_bwd(dhn, h, save, dgi, dgh, dh)
+        dx = dwi = dwh = dbi = dbh = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x.shape, device=dev)
+            ops.linear_nn_f32(dgi, w_ih, dx)
+        if ctx.needs_input_grad[1]:
+            ops.linear_nn_f32(dgh, w_hh, dh, accumulate=True)
+        else:
+            dh = None
+        if ctx.needs_input_grad[2]:
+            dwi = torch.empty(w_ih.shape, device=dev)
+            ops.linear_tn_f32(dgi, x, dwi)
+        if ctx.needs_input_grad[3]:
+            dwh = torch.empty(w_hh.shape, device=dev)
+            ops.linear_tn_f32(dgh, h, dwh)
+        ones = torch.ones(B, 1, device=dev)
+        if ctx.needs_input_grad[4]:
+            dbi = torch.empty(3 * H, 1, device=dev)
+            ops.linear_tn_f32(dgi, ones, dbi)
+            dbi = dbi.view(-1)
+        if ctx.needs_input_grad[5]:
+            dbh = torch.empty(3 * H, 1, device=dev)
+            ops.linear_tn_f32(dgh, ones, dbh)
+            dbh = dbh.view(-1)
+        return dx, dh, dwi, dwh, dbi, dbh
+
+
+class CondAugFn(torch.autograd.Function):
+    """CA_NET tail: relu, split into (mu, logvar), reparameterise with the given eps."""
+
+    @staticmethod
+    def forward(ctx, pre, eps):
+        pre, eps = _c(pre), _c(eps)
+        B, C = eps.shape
+        mu, logvar, code = (torch.empty(B, C, device=pre.device) for _ in range(3))
+        ops.ca_fwd(pre, eps, mu, logvar, code)
+        ctx.save_for_backward(pre, eps)
+        return mu, logvar, code
+
+    @staticmethod
+    def backward(ctx, dmu, dlogvar, dcode):
+        pre, eps = ctx.saved_tensors
+        dpre = torch.empty_like(pre)
+        ops.ca_bwd(pre, eps, _c(dmu) if dmu is not None else None,
+                   _c(dlogvar) if dlogvar is not None else None,
+                   _c(dcode) if dcode is not None else None, dpre)
+        return dpre, None
+
+
+class DynamicFilter1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, filt):
+        img, filt = _c(img), _c(filt)
+        N, C, L = img.shape
+        out = torch.empty(N, 1, L, device=img.device)
+        ops.dfn1d_fwd(img, filt, out)
+        ctx.save_for_backward(img, filt)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, filt = ctx.saved_tensors
+        dimg, dfilt = torch.empty_like(img), torch.empty_like(filt)
+        ops.dfn1d_bwd(img, filt, _c(dout), dimg, dfilt)
+        return dimg, dfilt
+
+
+def linear(x, w, b=None):
+    return LinearFn.apply(x, w, b)
+
+
+def batch_norm_1d(x, bn, act_tanh=False):
+    """bn: nn.BatchNorm1d holder module."""
+    return BatchNorm1dFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                               bn.num_batches_tracked, bn.training, act_tanh)
+
+
+def gru_cell(x, h, cell):
+    """cell: nn.GRUCell holder module."""
+    return GRUCellFn.apply(x, h, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)

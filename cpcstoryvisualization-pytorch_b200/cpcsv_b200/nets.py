@@ -1,0 +1,578 @@
+"""Network-level runners: build the kernel tape (engine.py) for one call of the generator
+trunk, a discriminator encoder or the conditional-logits head, and expose it to autograd as
+ONE ``torch.autograd.Function`` whose inputs are the activations plus every parameter.
+
+Reference call sites: generator trunk ``model.py:379-407 / 445-470``; encoders
+``model.py:498-514, 540-556, 582-598``; ``D_GET_LOGITS.forward`` ``model.py:86-97``.
+"""
+import torch
+
+from . import conv, engine, ops
+from .engine import T4, BnActNode, ConvNode, GemmNode, SpectralNorm, Tape, rup, _e
+
+_CACHE = engine.WeightCache()
+
+
+def weight_cache():
+    return _CACHE
+
+
+def invalidate_weight_cache():
+    """Call after an optimiser step if parameters were modified through paths that do not
+    bump ``Tensor._version`` (the cache also checks ``_version`` itself)."""
+    _CACHE.invalidate()
+
+
+class TapeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, *tensors):
+        ctx.runner = runner
+        outs = runner.run_forward(*tensors)
+        return outs if isinstance(outs, tuple) else (outs,)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        runner = ctx.runner
+        ctx.runner = None
+        return (None,) + tuple(runner.run_backward(grads, ctx.needs_input_grad[1:]))
+
+
+def _bn_tuple(bn):
+    return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked)
+
+
+def _eval_bn_unsupported(mod):
+    if not mod.training:
+        raise RuntimeError("cpcsv_b200: eval-mode BatchNorm (running statistics) is not part of the "
+                           "accelerated path; the reference never leaves train mode on this path "
+                           "(SURVEY.md section 3.3)")
+
+
+# =============================================================================== generator trunk
+class TrunkRunner:
+    """fc / fc_seg -> 4 up-blocks per branch with seg_c / seg_c1 modulation -> img / img_seg.
+
+    Inputs of the Function: zmc_all [N, ninput] and the parameters in ``self.names`` order.
+    Outputs: img [N,3,64,64], seg [N,1,64,64] (NCHW fp32, tanh range)."""
+
+    def __init__(self, G, need_grad, want_seg):
+        self.G, self.need_grad, self.want_seg = G, need_grad, want_seg
+        names = ["fc.0.weight", "fc.1.weight", "fc.1.bias"]
+        for i in range(1, 5):
+            names += ["upsample%d.1.weight" % i, "upsample%d.2.weight" % i, "upsample%d.2.bias" % i]
+        names += ["img.0.weight", "seg_c.weight", "seg_c1.weight",
+                  "fc_seg.0.weight", "fc_seg.1.weight", "fc_seg.1.bias"]
+        for i in range(1, 5):
+            names += ["upsample%d_seg.1.weight" % i, "upsample%d_seg.2.weight" % i,
+                      "upsample%d_seg.2.bias" % i]
+        names += ["img_seg.0.weight"]
+        self.names = names
+        self.params = dict(G.named_parameters())
+
+    def apply(self, zmc_all):
+        return TapeFn.apply(self, zmc_all, *[self.params[n] for n in self.names])
+
+    # ---------------------------------------------------------------- helpers
+    def _fc_maps(self, C, dev):
+        """fc emits feature j = c*16 + p (``view(-1, C, 4, 4)``, model.py:379); the trunk wants
+        NHWC order j' = p*Cp + c with Cp = C rounded up to 64.  perm[j'] = j, or -1 for the
+        padding channels (zero weight rows, zero BN scale)."""
+        key = ("fcperm", C, str(dev))
+        m = self.G._cpcsv_maps.get(key)
+        if m is None:
+            Cp = rup(C, 64)
+            jp = torch.arange(16 * Cp, device=dev)
+            c, p = jp % Cp, jp // Cp
+            m = torch.where(c < C, c * 16 + p, torch.full_like(jp, -1)).to(torch.int32)
+            self.G._cpcsv_maps[key] = m
+        return m
+
+    def _fc_node(self, tape, x0, lin, C, name):
+        w = lin.weight
+        K, Kp = w.shape[1], x0.C
+        Cp = rup(C, 64)
+        perm = self._fc_maps(C, w.device)
+        cache = tape.cache
+
+        def pack_fwd(planes):
+            def build():
+                hi = _e((16 * Cp, Kp), w.device, torch.bfloat16)
+                lo = _e((16 * Cp, Kp), w.device, torch.bfloat16) if planes == 2 else None
+                ops.pack_matrix(w.detach(), 16 * Cp, Kp, K, K, 1, perm, hi, lo)
+                return [hi, lo]
+            return cache.get((id(w), "fc_fwd", planes), w, build)
+
+        def pack_bwd():
+            def build():
+                hi = _e((Kp, 16 * Cp), w.device, torch.bfloat16)
+                # out[r = k, c = j'] = w[perm[j'], k]
+                ops.pack_matrix(w.detach(), Kp, 16 * Cp, 16 * Cp, 1, K, _row_pad_map(K, Kp, w.device), hi,
+                                None, col_map=perm)
+                return hi
+            return cache.get((id(w), "fc_bwd", 1), w, build)
+
+        node = GemmNode(tape, x0, 16 * Cp, pack_fwd, pack_bwd, name)
+        return node, perm
+
+    # ---------------------------------------------------------------- forward
+    def run_forward(self, zmc_all, *plist):
+        G = self.G
+        _eval_bn_unsupported(G)
+        dev = zmc_all.device
+        N, K = zmc_all.shape
+        tape = Tape(_CACHE, training=G.training, need_grad=self.need_grad, planes=2)
+        self.tape = tape
+        ngf, nseg = G.gf_dim, G.gf_dim_seg
+        Kp = rup(K, 64)
+        # latent -> operand planes (zero padded to a multiple of 64 columns)
+        x0 = T4(N, 1, 1, Kp)
+        x0.hi = torch.zeros(N, 1, 1, Kp, device=dev, dtype=torch.bfloat16)
+        x0.lo = torch.zeros(N, 1, 1, Kp, device=dev, dtype=torch.bfloat16)
+        zc = zmc_all.detach().contiguous()
+        ops.bn_act_pack(_pad4(zc), None, None, ops.ACT_NONE, hi=x0.hi.view(N, Kp)[:, :rup(K, 4)],
+                        lo=x0.lo.view(N, Kp)[:, :rup(K, 4)])
+        x0.needs_grad = self.need_grad
+        self.x0, self.K = x0, K
+
+        nodes = {}
+
+        def bn_of(seq_name, idx):
+            return _bn_tuple(getattr(G, seq_name)[idx])
+
+        # image branch head of the trunk
+        fc_img, perm_img = self._fc_node(tape, x0, G.fc[0], ngf, "fc")
+        z_fc = tape.add(fc_img)
+        fc_seg, perm_seg = self._fc_node(tape, x0, G.fc_seg[0], nseg, "fc_seg")
+        z_fs = tape.add(fc_seg)
+        nodes["fc"], nodes["fc_seg"] = fc_img, fc_seg
+        bn_fs = BnActNode(tape, z_fs, bn_of("fc_seg", 1), ops.ACT_RELU, "fc_seg.bn", chan_map=perm_seg,
+                          c_valid=z_fs.C)
+        a_seg = _alias(tape.add(bn_fs), N, 4, 4, rup(nseg, 64))
+        c_segc = ConvNode(tape, "s1", a_seg, G.seg_c.weight, "seg_c")
+        s0 = tape.add(c_segc)
+        bn_fc = BnActNode(tape, z_fc, bn_of("fc", 1), ops.ACT_RELU, "fc.bn", mod=s0, chan_map=perm_img,
+                          c_valid=z_fc.C)
+        a_img = _alias(tape.add(bn_fc), N, 4, 4, rup(ngf, 64))
+        self.alias = {"fc": a_img, "fc_seg": a_seg}
+        nodes.update({"fc_seg.bn": bn_fs, "seg_c": c_segc, "fc.bn": bn_fc})
+        for i in range(1, 5):
+            up_s = getattr(G, "upsample%d_seg" % i)
+            cs = ConvNode(tape, "up", a_seg, up_s[1].weight, "upsample%d_seg" % i)
+            z_s = tape.add(cs)
+            last_seg = (i == 4)
+            bs = BnActNode(tape, z_s, _bn_tuple(up_s[2]), ops.ACT_RELU, "upsample%d_seg.bn" % i,
+                           want_planes=True)
+            a_seg = tape.add(bs)
+            up_i = getattr(G, "upsample%d" % i)
+            ci = ConvNode(tape, "up", a_img, up_i[1].weight, "upsample%d" % i)
+            z_i = tape.add(ci)
+            mod = None
+            if i == 1:
+                c1 = ConvNode(tape, "s1", a_seg, G.seg_c1.weight, "seg_c1")
+                mod = tape.add(c1)
+                nodes["seg_c1"] = c1
+            bi = BnActNode(tape, z_i, _bn_tuple(up_i[2]), ops.ACT_RELU, "upsample%d.bn" % i, mod=mod)
+            a_img = tape.add(bi)
+            nodes.update({cs.name: cs, bs.name: bs, ci.name: ci, bi.name: bi})
+            del last_seg
+        self.nodes = nodes
+        self.a_img, self.a_seg = a_img, a_seg
+        img = self._head_fwd(a_img, G.img[0].weight, 3, "img")
+        seg = self._head_fwd(a_seg, G.img_seg[0].weight, 1, "img_seg")
+        self.img, self.seg = img, seg
+        return img, seg
+
+    def _head_pack(self, w, kind):
+        """3x3 head conv with 3 / 1 output channels.  kind 'fwd': [9 * 16, Ci] tap-major K-major;
+        kind 'bwd': [Ci, 64] with column tap*Co + co (the im2col'd-gradient GEMM)."""
+        Co, Ci = w.shape[0], w.shape[1]
+        Cip = rup(Ci, 64)
+
+        def build():
+            if kind == "fwd":
+                hi = _e((9 * 16, Cip), w.device, torch.bfloat16)
+                lo = _e((9 * 16, Cip), w.device, torch.bfloat16)
+                ops.pack_conv_weight(w.detach(), 0, 16, Cip, hi, lo)
+                return [hi, lo]
+            w2 = w.detach().permute(1, 2, 3, 0).reshape(Ci, 9 * Co).contiguous()   # [ci, tap*Co+co]
+            hi = _e((Cip, 64), w.device, torch.bfloat16)
+            rmap = None
+            ops.pack_matrix(w2, Cip, 64, 9 * Co, 9 * Co, 1, rmap, hi, None) if Cip == Ci else \
+                ops.pack_matrix(w2, Cip, 64, 9 * Co, 9 * Co, 1, _row_pad_map(Ci, Cip, w.device), hi, None)
+            return hi
+        return _CACHE.get((id(w), "head_" + kind, 2), w, build)
+
+    def _head_fwd(self, a, w, Co, name):
+        dev = a.hi.device
+        z = _e((a.N, a.H, a.W, 16), dev)
+        ops.conv_gemm(conv.conv_s1_fwd(a.planes(2), self._head_pack(w, "fwd"), z, 3))
+        y = _e((a.N, Co, a.H, a.W), dev)
+        ops.tanh_to_nchw(z.view(a.rows, 16), a.N, Co, a.H, a.W, y)
+        return y
+
+    def _head_bwd(self, a, w, y, dy, need_w):
+        """returns dW; accumulates d(a) into a.grad"""
+        dev = y.device
+        Co, Ci = w.shape[0], w.shape[1]
+        col = _e((a.rows, 64), dev, torch.bfloat16)
+        ops.tanh_bwd_im2col(dy, y, col)
+        dW = None
+        if need_w:
+            d = _e((a.C, 64), dev)
+            ops.conv_gemm(conv.gemm_tn(a.hi.view(a.rows, a.C), col, d))
+            dW = d[:Ci, :9 * Co].reshape(Ci, 3, 3, Co).permute(3, 0, 1, 2).contiguous()
+        acc = a.grad is not None
+        if not acc:
+            a.grad = _e((a.N, a.H, a.W, a.C), dev)
+        ops.conv_gemm(conv.gemm_nt([col, None], [self._head_pack(w, "bwd"), None], a.grad.view(a.rows, a.C),
+                                   accumulate=acc))
+        return dW
+
+    # ---------------------------------------------------------------- backward
+    def run_backward(self, grads, needs):
+        d_img, d_seg = grads
+        G, nodes = self.G, self.nodes
+        pg = {}
+        need_w = any(needs[1:])
+        for t in self._all_acts():
+            t.needs_grad = True
+        if d_img is not None:
+            pg["img.0.weight"] = self._head_bwd(self.a_img, G.img[0].weight, self.img, d_img, need_w)
+        seg_tail = d_seg is not None
+        if seg_tail:
+            pg["img_seg.0.weight"] = self._head_bwd(self.a_seg, G.img_seg[0].weight, self.seg, d_seg, need_w)
+
+        def bn_conv_bwd(bn_name, conv_name, prefix_bn, prefix_conv):
+            bn, cv = nodes[bn_name], nodes[conv_name]
+            if bn.out.grad is None:
+                return False
+            bn.backward(need_w)
+            pg[prefix_bn + ".weight"], pg[prefix_bn + ".bias"] = bn.dgamma, bn.dbeta
+            cv.backward(need_w)
+            pg[prefix_conv] = cv.dW
+            return True
+
+        # image branch, top down; level 1 also emits the seg_c1 gradient, level 0 seg_c's
+        for i in (4, 3, 2, 1):
+            bn_conv_bwd("upsample%d.bn" % i, "upsample%d" % i, "upsample%d.2" % i, "upsample%d.1.weight" % i)
+            if i == 1 and nodes["seg_c1"].out.grad16 is not None:
+                nodes["seg_c1"].backward(need_w)
+                pg["seg_c1.weight"] = nodes["seg_c1"].dW
+        self._fc_bwd("fc", need_w, pg)
+        if nodes["seg_c"].out.grad16 is not None:
+            nodes["seg_c"].backward(need_w)
+            pg["seg_c.weight"] = nodes["seg_c"].dW
+        for i in (4, 3, 2, 1):
+            bn_conv_bwd("upsample%d_seg.bn" % i, "upsample%d_seg" % i, "upsample%d_seg.2" % i,
+                        "upsample%d_seg.1.weight" % i)
+        self._fc_bwd("fc_seg", need_w, pg)
+        dz = None
+        if needs[0] and self.x0.grad is not None:
+            dz = self.x0.grad.view(self.x0.N, self.x0.C)[:, :self.K]
+        out = [dz]
+        for n, need in zip(self.names, needs[1:]):
+            out.append(pg.get(n) if need else None)
+        self.tape = self.nodes = None
+        return out
+
+    def _all_acts(self):
+        seen = []
+        for nd in self.tape.nodes:
+            if hasattr(nd, "x"):
+                seen.append(nd.x)
+        return seen
+
+    def _fc_bwd(self, name, need_w, pg):
+        bn, fc = self.nodes[name + ".bn"], self.nodes[name]
+        al = self.alias[name]
+        if al.grad is None:
+            return
+        bn.out.grad = al.grad.view(bn.out.N, 1, 1, bn.out.C)
+        bn.backward(need_w)
+        pg[name + ".1.weight"], pg[name + ".1.bias"] = bn.dgamma, bn.dbeta
+        fc.backward(need_w)
+        if need_w:
+            lin = getattr(self.G, name)[0]
+            C = lin.weight.shape[0] // 16
+            perm = self._fc_maps(C, lin.weight.device)
+            dw = torch.empty_like(lin.weight)
+            ops.scatter_rows_f32(fc.dwt, perm, dw, fc.npad, lin.weight.shape[1])
+            pg[name + ".0.weight"] = dw
+
+
+def _alias(t, N, H, W, C):
+    """the same buffers seen with another NHWC shape (fc output [N, 16C] -> [N, 4, 4, C])"""
+    a = T4(N, H, W, C)
+    for f in ("f32", "hi", "lo"):
+        v = getattr(t, f)
+        if v is not None:
+            setattr(a, f, v.view(N, H, W, C))
+    return a
+
+
+def _pad4(x):
+    """[M, K] fp32 -> same values with K padded to a multiple of 4 (zero columns)."""
+    M, K = x.shape
+    Kp = rup(K, 4)
+    if Kp == K:
+        return x
+    out = torch.zeros(M, Kp, device=x.device)
+    out[:, :K].copy_(x)
+    return out
+
+
+def _row_pad_map(rows, rows_pad, dev):
+    m = torch.full((rows_pad,), -1, dtype=torch.int32, device=dev)
+    m[:rows] = torch.arange(rows, dtype=torch.int32, device=dev)
+    return m
+
+
+# =============================================================================== D encoder
+class EncoderRunner:
+    """encode_img: conv4x4 s2 (im2col GEMM for the 1/3-channel image) -> LeakyReLU, then 3 x
+    [SN conv4x4 s2 -> BN -> LeakyReLU].  Input x [n, C, 64, 64] fp32 (any strides); output
+    features [n, 8*ndf, 4, 4] fp32 as a channels-last view."""
+
+    def __init__(self, D, need_grad):
+        self.D, self.need_grad = D, need_grad
+        enc = D.encode_img
+        self.sn0 = hasattr(enc[0], "weight_orig")
+        names = ["encode_img.0.weight_orig" if self.sn0 else "encode_img.0.weight"]
+        for idx in (2, 5, 8):
+            names += ["encode_img.%d.weight_orig" % idx, "encode_img.%d.weight" % (idx + 1),
+                      "encode_img.%d.bias" % (idx + 1)]
+        self.names = names
+        self.params = dict(D.named_parameters())
+
+    def apply(self, x):
+        return TapeFn.apply(self, x, *[self.params[n] for n in self.names])[0]
+
+    def _w0(self):
+        enc0 = self.D.encode_img[0]
+        return enc0.weight_orig if self.sn0 else enc0.weight
+
+    def _pack0(self, kind):
+        w = self._w0()
+        Co, Ci = w.shape[0], w.shape[1]
+        Cop = rup(Co, 64)
+        K = 16 * Ci
+        assert K <= 64
+
+        def build():
+            w2 = w.detach().permute(0, 2, 3, 1).reshape(Co, K).contiguous()     # [co, tap*Ci + c]
+            if kind == "fwd":
+                hi, lo = _e((Cop, 64), w.device, torch.bfloat16), _e((Cop, 64), w.device, torch.bfloat16)
+                ops.pack_matrix(w2, Cop, 64, K, K, 1, _row_pad_map(Co, Cop, w.device), hi, lo)
+                return [hi, lo]
+            hi = _e((64, Cop), w.device, torch.bfloat16)                         # [k, co]
+            ops.pack_matrix(w2, 64, Cop, Co, 1, K, _row_pad_map(K, 64, w.device), hi, None)
+            return hi
+        return _CACHE.get((id(w), "enc0_" + kind, 2), w, build)
+
+    def run_forward(self, x, *plist):
+        D = self.D
+        _eval_bn_unsupported(D)
+        enc = D.encode_img
+        dev = x.device
+        n, Cin, H, W = x.shape
+        tape = Tape(_CACHE, training=D.training, need_grad=self.need_grad, planes=2)
+        self.tape = tape
+        self.x_shape = (n, Cin, H, W)
+        xd = x.detach()
+        # layer 0: im2col + GEMM (+ SN alpha for the story discriminator)
+        Ho, Wo = H // 2, W // 2
+        col = T4(n, Ho, Wo, 64)
+        col.hi = _e((n, Ho, Wo, 64), dev, torch.bfloat16)
+        col.lo = _e((n, Ho, Wo, 64), dev, torch.bfloat16)
+        ops.im2col_small(xd, 4, 2, 1, col.hi, col.lo, 64)
+        self.col = col
+        w0 = self._w0()
+        Cop = rup(w0.shape[0], 64)
+        self.sn_first = None
+        alpha0 = None
+        if self.sn0:
+            self.sn_first = SpectralNorm(enc[0].weight_u, enc[0].weight_v)
+            alpha0 = self.sn_first.forward(w0, D.training, self.need_grad)
+        self.alpha0 = alpha0
+        z0 = T4(n, Ho, Wo, Cop)
+        z0.f32 = _e((n, Ho, Wo, Cop), dev)
+        ops.conv_gemm(conv.gemm_nt([col.hi.view(-1, 64), col.lo.view(-1, 64)], self._pack0("fwd"),
+                                   z0.f32.view(-1, Cop), alpha=alpha0))
+        self.z0 = z0
+        act0 = BnActNode(tape, z0, None, ops.ACT_LRELU, "enc0.act")
+        a = tape.add(act0)
+        self.act0 = act0
+        self.layers = []
+        for li, idx in enumerate((2, 5, 8)):
+            cmod, bmod = enc[idx], enc[idx + 1]
+            sn = SpectralNorm(cmod.weight_u, cmod.weight_v)
+            cn = ConvNode(tape, "s2", a, cmod.weight_orig, "enc%d" % idx, sn=sn)
+            z = tape.add(cn)
+            last = (li == 2)
+            bn = BnActNode(tape, z, _bn_tuple(bmod), ops.ACT_LRELU, "enc%d.bn" % idx, want_f32=last,
+                           want_planes=not last)
+            a = tape.add(bn)
+            self.layers.append((cn, bn, idx))
+        self.feat = a
+        Cf = enc[8].weight_orig.shape[0]
+        return a.f32.permute(0, 3, 1, 2)[:, :Cf]
+
+    def run_backward(self, grads, needs):
+        (dfeat,) = grads
+        D = self.D
+        pg = {}
+        need_w = any(needs[1:])
+        feat = self.feat
+        dev = dfeat.device
+        Cf = D.encode_img[8].weight_orig.shape[0]
+        g = torch.zeros(feat.N, feat.H, feat.W, feat.C, device=dev)
+        g[..., :Cf].copy_(dfeat.permute(0, 2, 3, 1))
+        feat.grad = g
+        for nd in self.tape.nodes:
+            if hasattr(nd, "x"):
+                nd.x.needs_grad = True
+        self.z0.needs_grad = True
+        for cn, bn, idx in reversed(self.layers):
+            bn.backward(need_w)
+            pg["encode_img.%d.weight" % (idx + 1)] = bn.dgamma
+            pg["encode_img.%d.bias" % (idx + 1)] = bn.dbeta
+            cn.backward(need_w)
+            pg["encode_img.%d.weight_orig" % idx] = cn.dW
+        # layer 0
+        self.act0.backward(False)
+        dz0 = self.z0.grad16                                    # [n, 32, 32, Cop] bf16
+        w0 = self._w0()
+        Co, Ci = w0.shape[0], w0.shape[1]
+        Cop = self.z0.C
+        K = 16 * Ci
+        dz0m = dz0.view(-1, Cop)
+        if need_w:
+            d = _e((Cop, 64), dev)
+            ops.conv_gemm(conv.gemm_tn(dz0m, self.col.hi.view(-1, 64), d))
+            gw = d[:Co, :K].reshape(Co, 4, 4, Ci).permute(0, 3, 1, 2).contiguous()
+            if self.sn_first is not None:
+                gw = self.sn_first.backward(gw, w0)
+            pg[self.names[0]] = gw
+        dx = None
+        if needs[0]:
+            n, Cin, H, W = self.x_shape
+            dcol = _e((dz0m.shape[0], 64), dev)
+            ops.conv_gemm(conv.gemm_nt([dz0m, None], [self._pack0("bwd"), None], dcol, alpha=self.alpha0))
+            dx = _e((n, Cin, H, W), dev)
+            ops.col2im_small(dcol, n, Cin, H, W, 4, 2, 1, dx)
+        out = [dx]
+        for nme, need in zip(self.names, needs[1:]):
+            out.append(pg.get(nme) if need else None)
+        self.tape = self.layers = None
+        return out
+
+
+# =============================================================================== logits head
+class LogitsRunner:
+    """D_GET_LOGITS: [h_code | c_code tiled 4x4] -> SN conv3x3 -> BN -> LeakyReLU ->
+    SN conv4x4 s4 (+bias) -> sigmoid -> [n]."""
+
+    def __init__(self, L, need_grad):
+        self.L, self.need_grad = L, need_grad
+        self.names = ["outlogits.0.weight_orig", "outlogits.1.weight", "outlogits.1.bias",
+                      "outlogits.3.weight_orig", "outlogits.3.bias"]
+        self.params = dict(L.named_parameters())
+
+    def apply(self, h_code, c_code):
+        return TapeFn.apply(self, h_code, c_code, *[self.params[n] for n in self.names])[0]
+
+    def _w3_perm(self, Cp):
+        """final 4x4 conv weight [1, C, 4, 4] -> row vector over the NHWC-flattened features
+        [(y*4+x)*Cp + c]."""
+        w = self.L.outlogits[3].weight_orig
+        C = w.shape[1]
+        out = torch.zeros(1, 16, Cp, device=w.device)
+        out[0, :, :C] = w.detach()[0].permute(1, 2, 0).reshape(16, C)
+        return out.view(1, 16 * Cp)
+
+    def run_forward(self, h_code, c_code, *plist):
+        L = self.L
+        _eval_bn_unsupported(L)
+        seq = L.outlogits
+        dev = h_code.device
+        n, Cf, H, W = h_code.shape
+        Ce = c_code.shape[1]
+        Cc = rup(Cf + Ce, 64)
+        tape = Tape(_CACHE, training=L.training, need_grad=self.need_grad, planes=2)
+        self.tape = tape
+        x = T4(n, H, W, Cc)
+        x.hi = _e((n, H, W, Cc), dev, torch.bfloat16)
+        x.lo = _e((n, H, W, Cc), dev, torch.bfloat16)
+        ops.pack_nchw(h_code.detach(), c_code.detach().contiguous().view(n, Ce), x.hi, x.lo, Cc)
+        self.x, self.Cf = x, Cf
+        sn = SpectralNorm(seq[0].weight_u, seq[0].weight_v)
+        cn = ConvNode(tape, "s1", x, seq[0].weight_orig, "logits.conv", sn=sn)
+        z = tape.add(cn)
+        bn = BnActNode(tape, z, _bn_tuple(seq[1]), ops.ACT_LRELU, "logits.bn", want_f32=True,
+                       want_planes=False)
+        a = tape.add(bn)
+        self.cn, self.bn, self.a = cn, bn, a
+        # final layer: dot product over the 4x4 x C features, spectral norm on a [1, 16C] matrix
+        w3 = seq[3].weight_orig
+        self.sn3 = SpectralNorm(seq[3].weight_u, seq[3].weight_v)
+        inv_sigma = self.sn3.forward(w3, L.training, self.need_grad)
+        feat = a.f32.view(n, H * W * a.C)
+        wrow = self._w3_perm(a.C)
+        t = _e((n, 1), dev)
+        ops.linear_f32(feat, wrow, None, t)
+        out = _e((n,), dev)
+        ops.affine_sigmoid_fwd(t.view(n), inv_sigma, seq[3].bias.detach(), out)
+        self.wrow, self.inv_sigma, self.out = wrow, inv_sigma, out
+        return out
+
+    def run_backward(self, grads, needs):
+        (dout,) = grads
+        L, a = self.L, self.a
+        seq = L.outlogits
+        dev = dout.device
+        n = a.N
+        need_w = any(needs[2:])
+        pg = {}
+        dout = dout.contiguous()
+        dt, dz = _e((n, 1), dev), _e((n, 1), dev)
+        ops.affine_sigmoid_bwd(dout, self.out, self.inv_sigma, dt.view(n), dz.view(n))
+        feat = a.f32.view(n, -1)
+        a.grad = _e((a.N, a.H, a.W, a.C), dev)
+        ops.linear_nn_f32(dt, self.wrow, a.grad.view(n, -1))          # d feat = dt (x) w_row
+        if need_w:
+            gw = _e((1, feat.shape[1]), dev)
+            ops.linear_tn_f32(dz, feat, gw)                           # dL/dW_eff (NHWC-flattened)
+            w3 = seq[3].weight_orig
+            C = w3.shape[1]
+            g4 = gw.view(16, a.C)[:, :C].reshape(4, 4, C).permute(2, 0, 1).reshape(1, C, 4, 4).contiguous()
+            pg["outlogits.3.weight_orig"] = self.sn3.backward(g4, w3)
+            ones = torch.ones(n, 1, device=dev)
+            db = _e((1, 1), dev)
+            ops.linear_tn_f32(dz, ones, db)
+            pg["outlogits.3.bias"] = db.view(1)
+        self.x.needs_grad = bool(needs[0])
+        self.bn.backward(need_w)
+        pg["outlogits.1.weight"], pg["outlogits.1.bias"] = self.bn.dgamma, self.bn.dbeta
+        self.cn.backward(need_w)
+        pg["outlogits.0.weight_orig"] = self.cn.dW
+        dh = None
+        if needs[0]:
+            dh = self.x.grad.permute(0, 3, 1, 2)[:, :self.Cf]
+        out = [dh, None]
+        for nme, need in zip(self.names, needs[2:]):
+            out.append(pg.get(nme) if need else None)
+        self.tape = None
+        return out
+
+
+# =============================================================================== cate_classify
+def cate_classify_weight_rows(w, Cp):
+    """conv(ndf*8 -> L, k4 s4 p1) on a 4x4 map = dot product with the kernel's lower-right 3x3
+    taps (padding rows/cols hit zeros).  Returns [L, 16*Cp] over NHWC-flattened features; built
+    with differentiable torch slicing so the weight gradient flows back through autograd."""
+    Lc, C = w.shape[0], w.shape[1]
+    k = torch.nn.functional.pad(w[:, :, 1:, 1:], (0, 1, 0, 1))          # [L, C, 4, 4] aligned to pixels
+    k = k.permute(0, 2, 3, 1)                                           # [L, 4, 4, C]
+    if Cp > C:
+        k = torch.nn.functional.pad(k, (0, Cp - C))
+    return k.reshape(Lc, 16 * Cp)

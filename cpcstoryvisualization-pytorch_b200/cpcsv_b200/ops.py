@@ -321,6 +321,16 @@ def tanh_bwd(y, dy, dx):
                "cpcsv_tanh_bwd")
 
 
+def affine_sigmoid_fwd(t, alpha, bias, out):
+    _lib.check(_lib.load().cpcsv_affine_sigmoid_fwd(_ptr(t), _ptr(alpha), _ptr(bias), _ptr(out), t.numel(),
+                                                    _stream()), "cpcsv_affine_sigmoid_fwd")
+
+
+def affine_sigmoid_bwd(dout, out, alpha, dt, dz):
+    _lib.check(_lib.load().cpcsv_affine_sigmoid_bwd(_ptr(dout), _ptr(out), _ptr(alpha), _ptr(dt), _ptr(dz),
+                                                    out.numel(), _stream()), "cpcsv_affine_sigmoid_bwd")
+
+
 # ------------------------------------------------------------------ spectral norm
 def spectral_sigma(w2d, u, v, power_iteration, sigma, inv_sigma, scratch, eps=1e-12):
     R, Cc = w2d.shape

@@ -90,7 +90,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t row
                                    float* shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (c >= C_valid) {
+  if (c >= C_valid || (chan_map && chan_map[c] < 0)) {  // padding channel
     mean[c] = 0.f; invstd[c] = 0.f; scale[c] = 0.f; shift[c] = 0.f;
     return;
   }
@@ -285,6 +285,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
       for (int j = 0; j < 4; ++j) {
         if (c + j < C_valid) {
           const int p = chan_map ? chan_map[c + j] : c + j;
+          if (p < 0) continue;
           dgamma[p] = static_cast<float>(sums[C + c + j]);
           dbeta[p] = static_cast<float>(sums[c + j]);
         }
@@ -449,7 +450,7 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, int64_t ld_sr
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / cols, c = i - r * cols;
     const int64_t rd = row_map ? row_map[r] : r;
-    dst[rd * ld_dst + c] = src[r * ld_src + c];
+    if (rd >= 0) dst[rd * ld_dst + c] = src[r * ld_src + c];
   }
 }
 

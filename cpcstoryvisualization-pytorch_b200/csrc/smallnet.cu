@@ -208,6 +208,28 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ y, const float* __rest
   if (i < n) dx[i] = dy[i] * (1.f - y[i] * y[i]);
 }
 
+// out = sigmoid(t * alpha + bias)   (final D_GET_LOGITS layer, reference model.py:79-80)
+__global__ void affine_sigmoid_fwd_kernel(const float* __restrict__ t, const float* __restrict__ alpha,
+                                          const float* __restrict__ bias, float* __restrict__ out,
+                                          int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = alpha ? *alpha : 1.f, b = bias ? *bias : 0.f;
+  out[i] = 1.f / (1.f + expf(-(t[i] * a + b)));
+}
+// dz = dout * out * (1 - out); dt = dz * alpha
+__global__ void affine_sigmoid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                          const float* __restrict__ alpha, float* __restrict__ dt,
+                                          float* __restrict__ dz, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = alpha ? *alpha : 1.f;
+  const float o = out[i];
+  const float g = dout[i] * o * (1.f - o);
+  dz[i] = g;
+  dt[i] = g * a;
+}
+
 // ------------------------------------------------------------------------- spectral norm
 // t[c] += sum_{r in chunk} W[r][c] * u[r]   (coalesced over c)
 __global__ void sn_wt_u_kernel(const float* __restrict__ W, int R, int C, const float* __restrict__ u,
@@ -383,6 +405,21 @@ extern "C" int cpcsv_tanh_bwd(const float* y, const float* dy, float* dx, int64_
   CPCSV_REQUIRE(y && dy && dx && n > 0, "tanh_bwd: args");
   tanh_bwd_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, STREAM(stream)>>>(y, dy, dx, n);
   return launched("tanh_bwd");
+}
+
+extern "C" int cpcsv_affine_sigmoid_fwd(const float* t, const float* alpha, const float* bias,
+                                        float* out, int64_t n, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(t && out && n > 0, "affine_sigmoid_fwd: args");
+  affine_sigmoid_fwd_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, STREAM(stream)>>>(
+      t, alpha, bias, out, n);
+  return launched("affine_sigmoid_fwd");
+}
+extern "C" int cpcsv_affine_sigmoid_bwd(const float* dout, const float* out, const float* alpha,
+                                        float* dt, float* dz, int64_t n, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(dout && out && dt && dz && n > 0, "affine_sigmoid_bwd: args");
+  affine_sigmoid_bwd_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, STREAM(stream)>>>(
+      dout, out, alpha, dt, dz, n);
+  return launched("affine_sigmoid_bwd");
 }
 
 extern "C" int cpcsv_spectral_sigma(const float* W, int32_t R, int32_t C, float* u, float* v,

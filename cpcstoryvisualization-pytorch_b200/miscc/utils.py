@@ -1,0 +1,116 @@
+"""Loss / bookkeeping helpers with the reference's names and call signatures
+(``miscc/utils.py`` of the reference: compute_discriminator_loss l.48-123,
+compute_generator_loss l.126-171, KL_loss l.184-188, weights_init l.191-201, get_multi_acc
+l.313-321, save_model l.323-338, count_param l.431-435).
+
+Differences that do not change results: the discriminators are called directly instead of
+through ``nn.parallel.data_parallel`` (one process drives one GPU here, where data_parallel
+degenerates to a plain call), and the classification accuracy is computed on the device and
+only converted to a Python float when ``cfg``-independent flag ``SYNC_ACCURACY`` is left on.
+"""
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from miscc.config import cfg  # noqa: F401
+
+SYNC_ACCURACY = True   # reference behaviour: .cpu().numpy() round trip per call (host sync)
+
+
+def _call(module, *inputs):
+    return module(*inputs)
+
+
+def get_multi_acc(predict, real):
+    """fraction of positive labels whose sigmoid score is >= 0.5 (reference l.313-321)."""
+    predict = torch.as_tensor(predict)
+    real = torch.as_tensor(real)
+    hit = ((torch.sigmoid(predict) >= 0.5) & (real == 1)).sum()
+    acc = hit.float() / real.sum()
+    return float(acc) if SYNC_ACCURACY else acc
+
+
+def compute_discriminator_loss(netD, real_imgs, fake_imgs, real_labels, fake_labels, real_catelabels,
+                               conditions, gpus):
+    """real / wrong / fake conditional BCE terms (+ character classification on the real
+    features).  Returns (errD, errD_real, errD_wrong, errD_fake, acc, consistency)."""
+    if conditions is None:
+        raise NotImplementedError("unconditional discriminators are unused by CP-CSV")
+    if netD.get_uncond_logits is not None or netD.seq_consisten_model:
+        raise NotImplementedError("uncond logits / sequence-consistency critic are disabled in cfg/final.yml")
+    batch_size = real_imgs.size(0)
+    cond = conditions.detach()
+    real_features = _call(netD, real_imgs)
+    fake_features = _call(netD, fake_imgs.detach())
+    head = netD.get_cond_logits
+    errD_real = F.binary_cross_entropy(_call(head, real_features, cond), real_labels)
+    errD_wrong = F.binary_cross_entropy(_call(head, real_features[:batch_size - 1], cond[1:]), fake_labels[1:])
+    errD_fake = F.binary_cross_entropy(_call(head, fake_features, cond), fake_labels)
+    errD = errD_real + (errD_fake + errD_wrong) * 0.5
+    acc = 0
+    if netD.cate_classify is not None:
+        cate_logits = _call(netD.cate_classify, real_features).squeeze()
+        errD = errD + 1.0 * F.multilabel_soft_margin_loss(cate_logits, real_catelabels)
+        acc = get_multi_acc(cate_logits.detach(), real_catelabels)
+    return errD, errD_real.detach(), errD_wrong.detach(), errD_fake.detach(), acc, 0
+
+
+def compute_generator_loss(netD, fake_imgs, real_imgs, real_labels, fake_catelabels, conditions, gpus):
+    """BCE of D(fake) against the real label (+ classification).  Returns (err, acc, consistency)."""
+    if conditions is None:
+        raise NotImplementedError("unconditional discriminators are unused by CP-CSV")
+    cond = conditions.detach()
+    fake_features = _call(netD, fake_imgs)
+    errD_fake = F.binary_cross_entropy(_call(netD.get_cond_logits, fake_features, cond), real_labels)
+    acc = 0
+    if netD.cate_classify is not None:
+        cate_logits = _call(netD.cate_classify, fake_features).squeeze()
+        errD_fake = errD_fake + 1.0 * F.multilabel_soft_margin_loss(cate_logits, fake_catelabels)
+        acc = get_multi_acc(cate_logits.detach(), fake_catelabels)
+    return errD_fake, acc, 0
+
+
+def KL_loss(mu, logvar):
+    """-0.5 * mean(1 + logvar - mu^2 - exp(logvar))"""
+    return -0.5 * torch.mean(1 + logvar - mu.pow(2) - logvar.exp())
+
+
+def weights_init(m):
+    """N(0, 0.02) for Conv / Linear weights, N(1, 0.02) for BatchNorm scale, zero biases;
+    dispatch on the class name like the reference."""
+    name = m.__class__.__name__
+    if "Conv" in name:
+        m.weight.data.normal_(0.0, 0.02)
+    elif "BatchNorm" in name:
+        m.weight.data.normal_(1.0, 0.02)
+        m.bias.data.fill_(0)
+    elif "Linear" in name:
+        m.weight.data.normal_(0.0, 0.02)
+        if m.bias is not None:
+            m.bias.data.fill_(0.0)
+
+
+def count_param(model):
+    return sum(p.numel() for p in model.parameters())
+
+
+def mkdir_p(path):
+    os.makedirs(path, exist_ok=True)
+
+
+def save_model(netG, netD_im, netD_st, netD_se, epoch, model_dir, whole=False):
+    """state_dict checkpoints with the reference's file names (l.323-338)."""
+    if whole:
+        torch.save(netG, "%s/netG.pkl" % model_dir)
+        torch.save(netD_im, "%s/netD_im.pkl" % model_dir)
+        torch.save(netD_st, "%s/netD_st.pkl" % model_dir)
+        if netD_se is not None:
+            torch.save(netD_se, "%s/netD_se.pkl" % model_dir)
+        return
+    torch.save(netG.state_dict(), "%s/netG_epoch_%d.pth" % (model_dir, epoch))
+    torch.save(netD_im.state_dict(), "%s/netD_im_epoch_last.pth" % model_dir)
+    torch.save(netD_st.state_dict(), "%s/netD_st_epoch_last.pth" % model_dir)
+    if netD_se is not None:
+        torch.save(netD_se.state_dict(), "%s/netD_se_epoch_last.pth" % model_dir)

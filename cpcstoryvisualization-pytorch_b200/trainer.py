@@ -1,0 +1,281 @@
+"""Drop-in for the reference's ``trainer.py``: ``GANTrainer(output_dir, args, ratio).train(
+imageloader, storyloader, testloader, stage)`` with the same batch-dict contract, optimiser
+settings, LR schedule, checkpoint files and step sequence (reference trainer.py:187-485), on
+top of the CUDA-kernel modules in ``model.py``.
+
+What is different from the reference, deliberately:
+  * the body of the hot loop lives in ``train_step`` (the reference has one monolithic
+    ``train``); ``train`` calls it once per story batch;
+  * one process drives one GPU.  Multi-GPU = one process per GPU (torchrun), each with its own
+    ``cfg.TRAIN.*_BATCH_SIZE`` shard (weak scaling, like the reference's batch x num_gpus);
+    gradients are averaged with one NCCL all-reduce per optimiser step (``GradSync``);
+  * the never-stepped ReduceLROnPlateau schedulers (reference l.224-228, broken on torch>=2.7)
+    are not created; tensorboard logging is optional and lazy (no per-step host sync unless a
+    logger is attached);
+  * while the generator is updated the discriminators' parameters have requires_grad off, so the
+    weight gradients the reference computes and then discards (zeroed by the next
+    ``zero_grad``) are not computed.
+"""
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.optim as optim
+
+from miscc.config import cfg
+from miscc.utils import (KL_loss, compute_discriminator_loss, compute_generator_loss, count_param,
+                         mkdir_p, save_model, weights_init)
+
+
+class GradSync:
+    """Average gradients across ranks: one flat NCCL all-reduce per network per step."""
+
+    def __init__(self, enabled=None):
+        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
+            if enabled is None else enabled
+        self.world = dist.get_world_size() if self.enabled else 1
+
+    def __call__(self, params):
+        if not self.enabled:
+            return
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads:
+            return
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat)
+        flat.div_(self.world)
+        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+            g.copy_(f)
+
+
+def build_networks(video_len=None):
+    """StoryGAN + the three discriminators, initialised like reference trainer.py:87-97."""
+    from model import StoryGAN, STAGE1_D_IMG, STAGE1_D_STY_V2, STAGE1_D_SEG
+    if cfg.CASCADE_MODEL:
+        raise NotImplementedError("CASCADE_MODEL=True (cascade_model.py) is outside the accelerated path; "
+                                  "cfg/final.yml:17 sets it to False")
+    nets = {"G": StoryGAN(video_len if video_len is not None else cfg.VIDEO_LEN),
+            "D_im": STAGE1_D_IMG(), "D_st": STAGE1_D_STY_V2(), "D_se": STAGE1_D_SEG()}
+    for n in nets.values():
+        n.apply(weights_init)
+    return nets
+
+
+def build_optimizers(nets, fused=None):
+    """Adam(betas=(0.5, 0.999)); lr from cfg (reference trainer.py:212-220)."""
+    fused = torch.cuda.is_available() if fused is None else fused
+    kw = dict(betas=(0.5, 0.999))
+    if fused:
+        kw["fused"] = True
+    opts = {}
+    for k, net in nets.items():
+        lr = cfg.TRAIN.GENERATOR_LR if k == "G" else cfg.TRAIN.DISCRIMINATOR_LR
+        opts[k] = optim.Adam([p for p in net.parameters() if p.requires_grad], lr=lr, **kw)
+    return opts
+
+
+def _set_requires_grad(net, flag):
+    for p in net.parameters():
+        p.requires_grad_(flag)
+
+
+def prepare_inputs(st_batch, im_batch):
+    """reference trainer.py:252-288: slice text to cfg.TEXT.DIMENSION, append labels."""
+    T = cfg.TEXT.DIMENSION
+    im_labels, st_labels = im_batch["labels"], st_batch["labels"]
+    return dict(
+        st_real=st_batch["images"], im_real=im_batch["images"], se_real=im_batch["images_seg"],
+        st_labels=st_labels, im_labels=im_labels,
+        im_motion=torch.cat((im_batch["description"][:, :T], im_labels), 1),
+        im_content=im_batch["content"][:, :, :T],
+        st_motion=torch.cat((st_batch["description"][:, :, :T], st_labels), 2),
+        st_content=st_batch["description"][:, :, :T])
+
+
+def _cond_vectors(x, c_mu, cim_mu):
+    """reference trainer.py:303-307 / 386-389 (without the FloatTensor host round trip)."""
+    T = cfg.TEXT.DIMENSION
+    chars = (x["st_labels"].mean(1) > 0).to(c_mu.dtype)
+    st_mu = torch.cat((c_mu, x["st_motion"][:, :, :T].mean(1).squeeze(), chars), 1)
+    im_mu = torch.cat((x["im_motion"], cim_mu), 1)
+    return st_mu, im_mu
+
+
+def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=True, skip_d_wgrad=True):
+    """One iteration of the reference's hot loop (trainer.py:290-416).  ``x`` from
+    ``prepare_inputs`` (device tensors), ``labels`` = (im_ones, im_zeros, st_ones, st_zeros).
+    Returns a dict of loss tensors (no host sync)."""
+    netG, netD_im, netD_st, netD_se = nets["G"], nets["D_im"], nets["D_st"], nets["D_se"]
+    im_ones, im_zeros, st_ones, st_zeros = labels
+    gpus = None
+    out = {}
+    # (2) fakes for the discriminator update
+    with torch.no_grad():
+        _, st_fake, _, _, c_mu, _, _ = netG.sample_videos(x["st_motion"], x["st_content"])
+        _, im_fake, _, _, cim_mu, _, se_fake = netG.sample_images(x["im_motion"], x["im_content"], seg=True)
+    st_mu, im_mu = _cond_vectors(x, c_mu, cim_mu)
+    out["p1_st_fake"], out["p1_im_fake"], out["p1_se_fake"] = st_fake, im_fake, se_fake
+    # (3) discriminators
+    for k in ("D_im", "D_st", "D_se"):
+        nets[k].zero_grad(set_to_none=True)
+    se_errD, *_rest = compute_discriminator_loss(netD_se, x["se_real"], se_fake, im_ones, im_zeros,
+                                                 x["im_labels"], im_mu, gpus)
+    im_errD, *_rest = compute_discriminator_loss(netD_im, x["im_real"], im_fake, im_ones, im_zeros,
+                                                 x["im_labels"], im_mu, gpus)
+    st_errD, *_rest = compute_discriminator_loss(netD_st, x["st_real"], st_fake, st_ones, st_zeros,
+                                                 x["st_labels"], st_mu, gpus)
+    se_errD.backward()
+    if grad_sync:
+        grad_sync(list(netD_se.parameters()))
+    if apply_optim:
+        opts["D_se"].step()
+    im_errD.backward()
+    st_errD.backward()
+    if grad_sync:
+        grad_sync(list(netD_im.parameters()))
+        grad_sync(list(netD_st.parameters()))
+    if apply_optim:
+        opts["D_im"].step()
+        opts["D_st"].step()
+    out.update(se_errD=se_errD.detach(), im_errD=im_errD.detach(), st_errD=st_errD.detach())
+    # (4) generator
+    netG.zero_grad(set_to_none=True)
+    if skip_d_wgrad:
+        for k in ("D_im", "D_st", "D_se"):
+            _set_requires_grad(nets[k], False)
+    try:
+        _, st_fake, _, _, c_mu, c_logvar, _ = netG.sample_videos(x["st_motion"], x["st_content"])
+        _, im_fake, _, _, cim_mu, cim_logvar, se_fake = netG.sample_images(x["im_motion"], x["im_content"],
+                                                                         seg=True)
+        st_mu, im_mu = _cond_vectors(x, c_mu, cim_mu)
+        se_errG, _, _ = compute_generator_loss(netD_se, se_fake, x["se_real"], im_ones, x["im_labels"], im_mu, gpus)
+        im_errG, _, _ = compute_generator_loss(netD_im, im_fake, x["im_real"], im_ones, x["im_labels"], im_mu, gpus)
+        st_errG, _, _ = compute_generator_loss(netD_st, st_fake, x["st_real"], st_ones, x["st_labels"], st_mu, gpus)
+        im_kl = KL_loss(cim_mu, cim_logvar)
+        st_kl = KL_loss(c_mu, c_logvar)
+        kl_w = cfg.TRAIN.COEFF.KL
+        total = im_errG + im_kl * kl_w + ratio * (se_errG * cfg.SEGMENT_RATIO + st_errG * cfg.IMAGE_RATIO
+                                                  + st_kl * kl_w)
+        total.backward()
+    finally:
+        if skip_d_wgrad:
+            for k in ("D_im", "D_st", "D_se"):
+                _set_requires_grad(nets[k], True)
+    if grad_sync:
+        grad_sync(list(netG.parameters()))
+    if apply_optim:
+        opts["G"].step()
+    out.update(se_errG=se_errG.detach(), im_errG=im_errG.detach(), st_errG=st_errG.detach(),
+               im_kl=im_kl.detach(), st_kl=st_kl.detach(), errG_total=total.detach())
+    out["p3_st_fake"], out["p3_im_fake"], out["p3_se_fake"] = st_fake.detach(), im_fake.detach(), se_fake.detach()
+    return out
+
+
+class GANTrainer(object):
+    def __init__(self, output_dir, args, ratio=1.0):
+        if cfg.TRAIN.FLAG:
+            output_dir = "{}/".format(output_dir)
+            self.model_dir = os.path.join(output_dir, "Model")
+            self.image_dir = os.path.join(output_dir, "Image")
+            self.log_dir = os.path.join(output_dir, "log")
+            self.test_dir = os.path.join(output_dir, "Test")
+            for d in (self.model_dir, self.image_dir, self.log_dir, self.test_dir):
+                mkdir_p(d)
+        self.video_len = cfg.VIDEO_LEN
+        self.max_epoch = cfg.TRAIN.MAX_EPOCH
+        self.snapshot_interval = cfg.TRAIN.SNAPSHOT_INTERVAL
+        self.gpus = [int(ix) for ix in str(cfg.GPU_ID).split(",")]
+        if len(self.gpus) != 1:
+            raise RuntimeError("this trainer drives ONE GPU per process; launch one process per GPU with "
+                               "torchrun instead of listing several ids in cfg.GPU_ID")
+        self.num_gpus = 1
+        self.imbatch_size = cfg.TRAIN.IM_BATCH_SIZE
+        self.stbatch_size = cfg.TRAIN.ST_BATCH_SIZE
+        self.ratio = ratio
+        self.con_ckpt = getattr(args, "continue_ckpt", None)
+        local_rank = int(os.environ.get("LOCAL_RANK", self.gpus[0]))
+        torch.cuda.set_device(local_rank)
+        self.device = torch.device("cuda", local_rank)
+        self._logger = None
+        try:
+            from tensorboardX import SummaryWriter
+            self._logger = SummaryWriter(self.log_dir)
+        except Exception:
+            pass
+
+    def load_network_stageI(self):
+        nets = build_networks(self.video_len)
+        print("The total parameter is : {}M".format(sum(count_param(n) for n in nets.values()) // 1e6))
+        if cfg.NET_G != "":
+            nets["G"].load_state_dict(torch.load(cfg.NET_G, map_location="cpu"))
+        if self.con_ckpt:
+            nets["G"].load_state_dict(torch.load("{}/netG_epoch_{}.pth".format(self.model_dir, self.con_ckpt)))
+            for k, tag in (("D_im", "im"), ("D_st", "st"), ("D_se", "se")):
+                nets[k].load_state_dict(torch.load("{}/netD_{}_epoch_last.pth".format(self.model_dir, tag)))
+        for n in nets.values():
+            n.to(self.device)
+        return nets["G"], nets["D_im"], nets["D_st"], nets["D_se"]
+
+    def sample_real_image_batch(self):
+        if self.imagedataset is None:
+            self.imagedataset = enumerate(self.imageloader)
+        batch_idx, batch = next(self.imagedataset)
+        batch = {k: (v if k == "text" else v.to(self.device, non_blocking=True)) for k, v in batch.items()}
+        if batch_idx == len(self.imageloader) - 1:
+            self.imagedataset = enumerate(self.imageloader)
+        return batch
+
+    def train(self, imageloader, storyloader, testloader, stage=1):
+        self.imageloader, self.imagedataset = imageloader, None
+        netG, netD_im, netD_st, netD_se = self.load_network_stageI()
+        nets = {"G": netG, "D_im": netD_im, "D_st": netD_st, "D_se": netD_se}
+        opts = build_optimizers(nets)
+        dev = self.device
+        labels = (torch.ones(self.imbatch_size, device=dev), torch.zeros(self.imbatch_size, device=dev),
+                  torch.ones(self.stbatch_size, device=dev), torch.zeros(self.stbatch_size, device=dev))
+        grad_sync = GradSync()
+        generator_lr, discriminator_lr = cfg.TRAIN.GENERATOR_LR, cfg.TRAIN.DISCRIMINATOR_LR
+        lr_decay_step = cfg.TRAIN.LR_DECAY_EPOCH
+        start_epoch = int(self.con_ckpt) if self.con_ckpt else 0
+        c_time = time.time()
+        for epoch in range(start_epoch, self.max_epoch):
+            start_t = time.time()
+            num_step = len(storyloader)
+            for i, data in enumerate(storyloader):
+                im_batch = self.sample_real_image_batch()
+                st_batch = {k: (v if k == "text" else v.to(dev, non_blocking=True)) for k, v in data.items()}
+                x = prepare_inputs(st_batch, im_batch)
+                stats = train_step(nets, opts, x, labels, self.ratio, grad_sync)
+                if self._logger is not None and i % 20 == 0:
+                    step = i + num_step * epoch
+                    for key in ("se_errD", "im_errD", "st_errD", "se_errG", "im_errG", "st_errG", "im_kl",
+                                "st_kl", "errG_total"):
+                        self._logger.add_scalar(key, float(stats[key]), step)
+            # learning-rate halving, reference trainer.py:447-456
+            if epoch % lr_decay_step == 0 and epoch > 0:
+                generator_lr *= 0.5
+                discriminator_lr *= 0.5
+                for g in opts["G"].param_groups:
+                    g["lr"] = generator_lr
+                for k in ("D_st", "D_im"):
+                    for g in opts[k].param_groups:
+                        g["lr"] = discriminator_lr
+                lr_decay_step *= 2
+            print("----[{}/{}] epoch {:.1f} min, total {:.1f} h----".format(
+                epoch, self.max_epoch, (time.time() - start_t) / 60, (time.time() - c_time) / 3600))
+            if epoch % self.snapshot_interval == 0 and int(os.environ.get("RANK", "0")) == 0:
+                save_model(netG, netD_im, netD_st, netD_se, epoch, self.model_dir)
+        if int(os.environ.get("RANK", "0")) == 0:
+            save_model(netG, netD_im, netD_st, netD_se, self.max_epoch, self.model_dir)
+        return nets
+
+
+def story_rate(ms_per_step, n_gpus=1):
+    """stories / s for a measured step time (BASELINE.json metric)."""
+    return cfg.TRAIN.ST_BATCH_SIZE * n_gpus / (ms_per_step * 1e-3)
+
+
+__all__ = ["GANTrainer", "train_step", "build_networks", "build_optimizers", "prepare_inputs", "GradSync",
+           "story_rate", "np"]

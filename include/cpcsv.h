@@ -218,6 +218,14 @@ int cpcsv_dfn1d_bwd(const float* img, const float* filt, const float* dout, int3
 int cpcsv_tanh_fwd(const float* x, float* y, int64_t n, cpcsv_stream_t stream);
 int cpcsv_tanh_bwd(const float* y, const float* dy, float* dx, int64_t n, cpcsv_stream_t stream);
 
+/* final layer of D_GET_LOGITS (model.py:79-80): out = sigmoid(t * alpha + bias) where
+ * t = features . weight_orig, alpha = 1/sigma (device scalars); and its backward
+ * dz = dout * out * (1 - out), dt = dz * alpha. */
+int cpcsv_affine_sigmoid_fwd(const float* t, const float* alpha, const float* bias, float* out,
+                             int64_t n, cpcsv_stream_t stream);
+int cpcsv_affine_sigmoid_bwd(const float* dout, const float* out, const float* alpha, float* dt,
+                             float* dz, int64_t n, cpcsv_stream_t stream);
+
 /* ---------------------------------------------------------------- spectral norm (legacy hook)
  * torch.nn.utils.spectral_norm, 1 power iteration, eps 1e-12 (model.py:5,19,79,502-510;
  * SURVEY.md Appendix A).  W is [R, C] row-major fp32 (= weight_orig.reshape(Cout, -1)).

@@ -166,7 +166,7 @@ def bn_finalize(stats, rows, gamma, beta, running_mean, running_var, chan_map, c
     var = (stats[Cc:] / rows - m * m).clamp_min(0)
     inv = 1.0 / torch.sqrt(var + eps)
     idx = chan_map.long() if chan_map is not None else torch.arange(Cc)
-    valid = torch.arange(Cc) < c_valid
+    valid = (torch.arange(Cc) < c_valid) & (idx >= 0)
     pv = idx[valid]
     g = torch.zeros(Cc, dtype=torch.float64)
     b = torch.zeros(Cc, dtype=torch.float64)
@@ -238,8 +238,9 @@ def bn_bwd_apply(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod,
         dmod16.copy_((dy * a).to(torch.bfloat16))
     if dgamma is not None:
         idx = chan_map.long()[:c_valid] if chan_map is not None else torch.arange(c_valid)
-        dgamma[idx] = sums[Cc:Cc + c_valid].float()
-        dbeta[idx] = sums[:c_valid].float()
+        ok = idx >= 0
+        dgamma[idx[ok]] = sums[Cc:Cc + c_valid].float()[ok]
+        dbeta[idx[ok]] = sums[:c_valid].float()[ok]
 
 
 # ------------------------------------------------------------------------------ layout kernels
@@ -311,7 +312,8 @@ def pack_matrix(w, rows_out, cols_out, cols_valid, ld_r, ld_c, row_map, hi, lo, 
 
 def scatter_rows_f32(src, row_map, dst, rows, cols):
     r = row_map.long()[:rows] if row_map is not None else torch.arange(rows)
-    dst[r, :cols] = src[:rows, :cols]
+    ok = r >= 0
+    dst[r[ok], :cols] = src[:rows, :cols][ok]
 
 
 _MERGE = {(0, 0): (0, 0), (0, 1): (1, 2), (1, 0): (0, 1), (1, 1): (2, 2)}
@@ -440,10 +442,11 @@ def dfn1d_fwd(img, filt, out):
 def dfn1d_bwd(img, filt, dout, dimg, dfilt):
     N, Cc, L = img.shape
     K = filt.shape[-1]
-    i2 = img.detach().clone().requires_grad_(True)
-    f2 = filt.detach().clone().reshape(N, Cc, K).requires_grad_(True)
-    r = torch.nn.functional.conv1d(i2.reshape(1, N * Cc, L), f2, padding=K // 2, groups=N)
-    gi, gf = torch.autograd.grad(r, (i2, f2), dout.reshape(r.shape))
+    with torch.enable_grad():
+        i2 = img.detach().clone().requires_grad_(True)
+        f2 = filt.detach().clone().reshape(N, Cc, K).requires_grad_(True)
+        r = torch.nn.functional.conv1d(i2.reshape(1, N * Cc, L), f2, padding=K // 2, groups=N)
+        gi, gf = torch.autograd.grad(r, (i2, f2), dout.reshape(r.shape))
     dimg.copy_(gi)
     dfilt.copy_(gf.reshape(dfilt.shape))
 
@@ -454,6 +457,19 @@ def tanh_fwd(x, y):
 
 def tanh_bwd(y, dy, dx):
     dx.copy_(dy * (1 - y * y))
+
+
+def affine_sigmoid_fwd(t, alpha, bias, out):
+    a = float(alpha) if alpha is not None else 1.0
+    b = float(bias) if bias is not None else 0.0
+    out.copy_(torch.sigmoid(t * a + b))
+
+
+def affine_sigmoid_bwd(dout, out, alpha, dt, dz):
+    a = float(alpha) if alpha is not None else 1.0
+    g = dout * out * (1 - out)
+    dz.copy_(g)
+    dt.copy_(g * a)
 
 
 def spectral_sigma(w2d, u, v, power_iteration, sigma, inv_sigma, scratch, eps=1e-12):
