@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Contract benchmark: CP-CSV GAN training step (BASELINE.json metric: stories/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host CPU cores
+
+A "step" is one iteration of the reference's hot loop (trainer.py:290-416) at the
+cfg/final.yml batch (18 stories x 5 frames + 90 images, 64x64): no-grad generator passes,
+the three discriminator updates and the generator update, including the four Adam steps.
+With N > 1 every rank runs that batch on its own GPU (weak scaling, as the reference's
+batch x num_gpus) and gradients are averaged with NCCL; ``value`` is the whole-job rate.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "cpcstoryvisualization-pytorch_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+NOMINAL_GFLOP_PER_STEP = 11874.8   # necessary algorithmic work, SURVEY.md section 8(d)
+WORKLOAD = ("pororo cfg/final.yml: 18 stories x 5 frames + 90 images, 64x64; G + D_im + D_st + D_se "
+            "fwd/bwd + 4 Adam steps")
+
+
+def preset_dict(st_batch=18, im_batch=90):
+    return dict(CUDA=True, USE_SEQ_CONSISTENCY=False, SEGMENT_LEARNING=True, CASCADE_MODEL=False,
+                SEGMENT_RATIO=1.0, IMAGE_RATIO=5.0, KL=1.0, DISCRIMINATOR_LR=4e-4, GENERATOR_LR=1e-4,
+                VIDEO_LEN=5, TEXT_DIM=356, LABEL_NUM=9, ST_BATCH=st_batch, IM_BATCH=im_batch,
+                CONDITION_DIM=124, Z_DIM=100, DF_DIM=124, GF_DIM=256, GF_SEG_DIM=1024, name="pororo")
+
+
+def apply_cfg(cfg, p):
+    cfg.CUDA = p["CUDA"]; cfg.VIDEO_LEN = p["VIDEO_LEN"]; cfg.LABEL_NUM = p["LABEL_NUM"]
+    cfg.USE_SEQ_CONSISTENCY = False; cfg.SEGMENT_LEARNING = True; cfg.CASCADE_MODEL = False
+    cfg.SEGMENT_RATIO = p["SEGMENT_RATIO"]; cfg.IMAGE_RATIO = p["IMAGE_RATIO"]; cfg.Z_DIM = p["Z_DIM"]
+    cfg.TRAIN.IM_BATCH_SIZE = p["IM_BATCH"]; cfg.TRAIN.ST_BATCH_SIZE = p["ST_BATCH"]
+    cfg.TRAIN.DISCRIMINATOR_LR = p["DISCRIMINATOR_LR"]; cfg.TRAIN.GENERATOR_LR = p["GENERATOR_LR"]
+    cfg.TRAIN.COEFF.KL = p["KL"]
+    cfg.GAN.CONDITION_DIM = p["CONDITION_DIM"]; cfg.GAN.Z_DIM = p["Z_DIM"]; cfg.GAN.DF_DIM = p["DF_DIM"]
+    cfg.GAN.GF_DIM = p["GF_DIM"]; cfg.GAN.GF_SEG_DIM = p["GF_SEG_DIM"]; cfg.TEXT.DIMENSION = p["TEXT_DIM"]
+
+
+def synthetic_host_batch(p, seed, pin):
+    """the two loader dicts of reference trainer.py:252-274 with synthetic contents (host memory)"""
+    g = torch.Generator().manual_seed(seed)
+    B, N, V, T, L = p["ST_BATCH"], p["IM_BATCH"], p["VIDEO_LEN"], p["TEXT_DIM"], p["LABEL_NUM"]
+    st = {"images": torch.rand(B, 3, V, 64, 64, generator=g) * 2 - 1,
+          "description": torch.randn(B, V, T, generator=g),
+          "labels": (torch.rand(B, V, L, generator=g) < 0.3).float()}
+    im = {"images": torch.rand(N, 3, 64, 64, generator=g) * 2 - 1,
+          "description": torch.randn(N, T, generator=g),
+          "content": torch.randn(N, V, T, generator=g),
+          "labels": (torch.rand(N, L, generator=g) < 0.3).float(),
+          "images_seg": torch.rand(N, 1, 64, 64, generator=g) * 2 - 1}
+    if pin:
+        st = {k: v.pin_memory() for k, v in st.items()}
+        im = {k: v.pin_memory() for k, v in im.items()}
+    return st, im
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        # median over the samples taken under load (upper half: idle samples sit at the floor clock)
+        load = [v for v in sm if mx and v > 0.3 * mx] or sm
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_reference_rate(steps, warmup, st_batch=2, im_batch=10, threads=None):
+    """The reference algorithm (oracle port, fp32, torch CPU ops) on the host cores, on a bounded
+    sample of the workload: the cfg/final.yml model at `st_batch` stories + `im_batch` images per
+    step instead of 18 + 90.  Returns (stories/s, seconds/step, cores)."""
+    from oracle import functional as Fn
+    from oracle import params, synth
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    p = preset_dict(st_batch, im_batch)
+    p["CUDA"] = False
+    model = Fn.OracleModel(params.init_all(p, 0), p, device="cpu")
+    batch = synth.make_batch(p, 1)
+    times = []
+    for i in range(warmup + steps):
+        feed = synth.NoiseFeed(synth.make_noise(p, 2 + i))
+        t0 = time.perf_counter()
+        Fn.train_step(model, batch, feed)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return st_batch / sec, sec, threads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    rate, sec, cores = cpu_reference_rate(steps, warm)
+    sample = ("oracle port of the reference step (fp32, torch CPU ops, %d threads); cfg/final.yml model, "
+              "bounded sample of 2 stories + 10 images per step (1/9 of the batch); %d timed steps" % (cores, steps))
+    line = {"impl": "reference", "metric": "train stories/s", "value": rate, "unit": "stories/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "stories/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "stories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- product arm
+class StepEngine:
+    """The public train_step API around static device buffers, optionally as one CUDA graph."""
+
+    def __init__(self, p, device, use_graph, grad_sync):
+        from miscc.config import cfg
+        apply_cfg(cfg, p)
+        import miscc.utils as mu
+        import trainer
+        from cpcsv_b200 import nets as knets
+        mu.SYNC_ACCURACY = False            # no host round trip inside the step
+        self.trainer, self.knets = trainer, knets
+        self.p, self.device = p, device
+        torch.manual_seed(1234 + int(os.environ.get("RANK", "0")))
+        self.nets = trainer.build_networks(p["VIDEO_LEN"])
+        for n in self.nets.values():
+            n.to(device).train()
+        self.opts = {}
+        for k, net in self.nets.items():
+            lr = p["GENERATOR_LR"] if k == "G" else p["DISCRIMINATOR_LR"]
+            self.opts[k] = torch.optim.Adam(net.parameters(), lr=lr, betas=(0.5, 0.999), fused=True,
+                                            capturable=use_graph)
+        N, B = p["IM_BATCH"], p["ST_BATCH"]
+        self.labels = (torch.ones(N, device=device), torch.zeros(N, device=device),
+                       torch.ones(B, device=device), torch.zeros(B, device=device))
+        st, im = synthetic_host_batch(p, 7, pin=True)
+        self.host_st, self.host_im = st, im
+        self.dev_st = {k: v.to(device) for k, v in st.items()}
+        self.dev_im = {k: v.to(device) for k, v in im.items()}
+        self.h2d_bytes = sum(v.numel() * v.element_size() for d in (st, im) for v in d.values())
+        self.grad_sync = grad_sync
+        self.use_graph = use_graph
+        self.graph = None
+        self.loss_keys = ("se_errD", "im_errD", "st_errD", "se_errG", "im_errG", "st_errG", "im_kl", "st_kl",
+                          "errG_total")
+        self.loss_dev = torch.zeros(len(self.loss_keys), device=device)
+        self.loss_host = torch.zeros(len(self.loss_keys)).pin_memory()
+
+    def _step_body(self):
+        x = self.trainer.prepare_inputs(self.dev_st, self.dev_im)
+        out = self.trainer.train_step(self.nets, self.opts, x, self.labels, 1.0, self.grad_sync)
+        self.loss_dev.copy_(torch.stack([out[k].reshape(()) for k in self.loss_keys]))
+
+    def capture(self):
+        self.knets.invalidate_weight_cache()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step_body()
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+
+    def upload(self):
+        for k, v in self.host_st.items():
+            self.dev_st[k].copy_(v, non_blocking=True)
+        for k, v in self.host_im.items():
+            self.dev_im[k].copy_(v, non_blocking=True)
+
+    def download(self):
+        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+
+
+def job_flops(job):
+    """executed tensor-core FLOPs of one conv_gemm launch (padded channels and split planes counted)"""
+    n, h, w = job.grid
+    pix = n * h * w
+    if job.mode == 0:
+        mmas = 3 if job.planes == 2 else 1
+        return 2.0 * pix * job.groups * job.taps_per_group * job.k_blocks * 64 * job.n_valid * mmas
+    return 2.0 * pix * job.groups * job.m_valid * job.n_valid
+
+
+def profile_gemm_launches(engine, steps):
+    """per-launch CUDA-event timing of every tcgen05 GEMM launch over `steps` eager steps"""
+    from cpcsv_b200 import ops
+    orig = ops.conv_gemm
+    recs = []
+
+    def timed(job):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(job)
+        e1.record()
+        recs.append((e0, e1, job_flops(job)))
+
+    ops.conv_gemm = timed
+    try:
+        for _ in range(steps):
+            engine._step_body()
+        torch.cuda.synchronize()
+    finally:
+        ops.conv_gemm = orig
+    ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+    fl = sum(f for _, _, f in recs)
+    return {"launches_per_step": len(recs) / steps, "gemm_ms_per_step": ms / steps,
+            "executed_gflop_per_step": fl / steps / 1e9, "achieved_tflops": fl / (ms * 1e-3) / 1e12}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cpcsv_b200")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from cpcsv_b200 import _lib
+    _lib.load()
+
+    p = preset_dict()
+    import trainer
+    grad_sync = trainer.GradSync() if world > 1 else None
+    eng = StepEngine(p, device, use_graph=not args.no_graph, grad_sync=grad_sync)
+
+    # warm-up (eager: builds caches, sets kernel attributes), then capture
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(args.warmup):
+            eng.step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    if not args.no_graph:
+        eng.capture()
+        torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - launches0 if not args.no_graph else None
+    for _ in range(2):
+        eng.step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(with_io):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            if with_io:
+                eng.upload()
+            eng.step()
+            if with_io:
+                eng.download()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    c0 = _lib.launch_count()
+    ms_dev = timed_loop(False)
+    c1 = _lib.launch_count()
+    ms_e2e = timed_loop(True)
+    clocks = sampler.stop() if rank == 0 else None
+    if launches_per_step is None:
+        launches_per_step = (c1 - c0) / args.steps
+
+    prof = profile_gemm_launches(eng, 2)
+    stories = p["ST_BATCH"] * world
+    ms_step = ms_dev / args.steps
+    ms_step_e2e = ms_e2e / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
+
+    line = {
+        "metric": "train stories/s", "value": stories / (ms_step * 1e-3), "unit": "stories/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cuda_graph": not args.no_graph,
+                   "precision": "fwd convs: bf16 hi/lo split operands (3 MMAs), fp32 accumulate; bwd GEMMs "
+                                "single-pass bf16; BN/conditioning/grads fp32",
+                   "l2": "per-step working set (activations + 158 M params + Adam state) is ~4 GB >> 126 MB L2; "
+                         "no explicit flush",
+                   "nominal_gflop_per_step": NOMINAL_GFLOP_PER_STEP,
+                   "nominal_tflops": NOMINAL_GFLOP_PER_STEP / ms_step / 1e3,
+                   "nominal_frac_of_peak": NOMINAL_GFLOP_PER_STEP / ms_step / 1e3 / peak},
+        "e2e": {"value": stories / (ms_step_e2e * 1e-3), "unit": "stories/s",
+                "h2d_bytes_per_step": eng.h2d_bytes, "d2h_bytes_per_step": eng.loss_host.numel() * 4,
+                "ms_per_step": ms_step_e2e},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": {"bound": "tensor", "achieved": prof["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
+                     "frac": prof["achieved_tflops"] / peak, "traffic": None,
+                     "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM)", "peak_source": peak_src,
+                     "executed_gflop_per_step": prof["executed_gflop_per_step"],
+                     "gemm_launches_per_step": prof["launches_per_step"],
+                     "gemm_ms_per_step_eager_events": prof["gemm_ms_per_step"]},
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, sec, cores = cpu_reference_rate(2, 1)
+        line["cpu_baseline"] = {
+            "value": rate, "unit": "stories/s", "cores": cores, "kind": "port",
+            "sample": "oracle port of the reference step (fp32 torch CPU ops, %d threads) on the cfg/final.yml "
+                      "model with 2 stories + 10 images per step (1/9 of the batch), 2 timed steps, %.1f s/step"
+                      % (cores, sec)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

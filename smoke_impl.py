@@ -1,0 +1,38 @@
+"""__graft_entry__.smoke(): one tiny CP-CSV train step (generator + 3 discriminators, forward and
+backward) through libcpcsv.so on cuda:0, checked against the oracle on the same inputs."""
+import functools
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "cpcstoryvisualization-pytorch_b200"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+
+def run():
+    import torch
+    assert torch.cuda.is_available(), "smoke() needs a CUDA device"
+    import harness
+    import trainer
+    from cpcsv_b200 import _lib
+    from oracle import functional as Fn
+    from oracle import presets
+    p = presets.get("small")
+    dev = torch.device("cuda", 0)
+    before = _lib.launch_count()
+    orig_p, orig_o = trainer.train_step, Fn.train_step
+    trainer.train_step = functools.partial(orig_p, apply_optim=False)
+    Fn.train_step = functools.partial(orig_o, apply_optim=False)
+    try:
+        _, out, grads = harness.run_product_step(p, dev)
+        _, ref_out, ref_grads = harness.run_oracle_step(p, dev, torch.float64)
+    finally:
+        trainer.train_step, Fn.train_step = orig_p, orig_o
+    torch.cuda.synchronize()
+    res = harness.compare(out, grads, ref_out, ref_grads)
+    launches = _lib.launch_count() - before
+    print("smoke: %d libcpcsv kernel launches; loss rel %.2e, image relL2 %.2e, min grad cosine %.6f (%s)" % (
+        launches, res["loss_rel"], res["img_rel"], res["cos_min"], res["cos_min_name"]))
+    assert launches > 100
+    assert res["loss_rel"] <= 1e-3 and res["img_rel"] <= 2e-2 and res["cos_min"] >= 0.999, res
