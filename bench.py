@@ -368,8 +368,8 @@ def main():
                    "l2": "per-step working set (activations + 158 M params + Adam state) is ~4 GB >> 126 MB L2; "
                          "no explicit flush",
                    "nominal_gflop_per_step": NOMINAL_GFLOP_PER_STEP,
-                   "nominal_tflops": NOMINAL_GFLOP_PER_STEP / ms_step / 1e3,
-                   "nominal_frac_of_peak": NOMINAL_GFLOP_PER_STEP / ms_step / 1e3 / peak},
+                   "nominal_tflops": NOMINAL_GFLOP_PER_STEP / ms_step,
+                   "nominal_frac_of_peak": NOMINAL_GFLOP_PER_STEP / ms_step / peak},
         "e2e": {"value": stories / (ms_step_e2e * 1e-3), "unit": "stories/s",
                 "h2d_bytes_per_step": eng.h2d_bytes, "d2h_bytes_per_step": eng.loss_host.numel() * 4,
                 "ms_per_step": ms_step_e2e},

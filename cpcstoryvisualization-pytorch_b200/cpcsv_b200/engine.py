@@ -48,6 +48,11 @@ class WeightCache:
     def invalidate(self):
         self.epoch += 1
 
+    def invalidate_params(self, param_ids):
+        """drop the entries of the given parameters (keys are (id(param), kind, planes))"""
+        for key in [k for k in self.d if k[0] in param_ids]:
+            del self.d[key]
+
     def get(self, key, param, build):
         tag = (param._version, param.data_ptr(), self.epoch)
         ent = self.d.get(key)

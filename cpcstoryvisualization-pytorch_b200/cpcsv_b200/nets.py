@@ -18,9 +18,27 @@ def weight_cache():
 
 
 def invalidate_weight_cache():
-    """Call after an optimiser step if parameters were modified through paths that do not
-    bump ``Tensor._version`` (the cache also checks ``_version`` itself)."""
+    """Drop every packed operand plane.  The cache validates entries against
+    ``Tensor._version``, but fused optimisers (``Adam(fused=True)``) update parameters without
+    bumping it, so every ``torch.optim`` step also invalidates the cache through the global
+    post-step hook registered below.  Call this by hand after modifying parameters through
+    any other path that bypasses the version counter."""
     _CACHE.invalidate()
+
+
+def _install_optimizer_hook():
+    try:
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+    except ImportError as e:  # pragma: no cover - every supported torch has it
+        raise RuntimeError("cpcsv_b200 needs torch.optim global step hooks (torch >= 2.0)") from e
+    def hook(opt, args, kwargs):
+        ids = {id(p) for g in opt.param_groups for p in g["params"]}
+        _CACHE.invalidate_params(ids)
+
+    register_optimizer_step_post_hook(hook)
+
+
+_install_optimizer_hook()
 
 
 class TapeFn(torch.autograd.Function):

@@ -497,6 +497,54 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
   }
 }
 
+// Coalesced variant for the untransposed layouts dwt[tap][co][ci]: one block = one `co` and 128
+// consecutive `ci`; reads are contiguous in ci, the T = kh*kw values of every (co, ci) are
+// transposed through shared memory so the writes to dw[co][ci][t] are contiguous too.
+__global__ void __launch_bounds__(128)
+unpack_conv_wgrad_rows_kernel(const float* __restrict__ dwt, int64_t mat_stride, int64_t ldc, int Cout,
+                              int Cin, int T, int kind, const float* __restrict__ alpha,
+                              float* __restrict__ dw) {
+  __shared__ float s[128 * 16];
+  const int co = blockIdx.y;
+  const int ci0 = blockIdx.x * 128;
+  const int ci = ci0 + threadIdx.x;
+  const float a_ = alpha ? *alpha : 1.f;
+  const int tin = kind == 2 ? 16 : T;
+  float v[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t)
+    v[t] = (t < tin && ci < Cin) ? dwt[t * mat_stride + static_cast<int64_t>(co) * ldc + ci] : 0.f;
+  if (kind == 2) {
+    // tap index = a*8 + b*4 + i*2 + j; 3x3 tap (ky,kx) collects the phases that merged it
+    float o[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float acc = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 16; ++tap) {
+          const int a = tap >> 3, b = (tap >> 2) & 1, ti = (tap >> 1) & 1, tj = tap & 1;
+          int y0, y1, x0, x1;
+          merged_range(a, ti, y0, y1);
+          merged_range(b, tj, x0, x1);
+          if (ky >= y0 && ky <= y1 && kx >= x0 && kx <= x1) acc += v[tap];
+        }
+        o[ky * 3 + kx] = acc;
+      }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s[threadIdx.x * T + t] = o[t] * a_;
+  } else {
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      if (t < T) s[threadIdx.x * T + t] = v[t] * a_;
+  }
+  __syncthreads();
+  const int nvalid = min(128, Cin - ci0);
+  float* dst = dw + (static_cast<int64_t>(co) * Cin + ci0) * T;
+  for (int j = threadIdx.x; j < nvalid * T; j += 128) dst[j] = s[j];
+}
+
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwt, int64_t mat_stride,
                                          int64_t ldc, int Cout, int Cin, int kh, int kw, int kind,
                                          const float* __restrict__ alpha, float* __restrict__ dw) {
@@ -719,6 +767,12 @@ extern "C" int cpcsv_unpack_conv_wgrad(const float* dwt, int64_t mat_stride, int
   CPCSV_REQUIRE(dwt && dw && kind >= 0 && kind <= 3, "unpack_conv_wgrad: args");
   CPCSV_REQUIRE(kind < 2 || (kh == 3 && kw == 3), "unpack_conv_wgrad: sub-pixel merge needs 3x3");
   const int64_t work = static_cast<int64_t>(Cout) * Cin * kh * kw;
+  if ((kind == 0 || kind == 2) && kh * kw <= 16) {
+    dim3 grid(static_cast<unsigned>(ceil_div(Cin, 128)), static_cast<unsigned>(Cout));
+    unpack_conv_wgrad_rows_kernel<<<grid, 128, 0, STREAM(stream)>>>(dwt, mat_stride, ldc, Cout, Cin,
+                                                                   kh * kw, kind, alpha, dw);
+    return launched("unpack_conv_wgrad");
+  }
   unpack_conv_wgrad_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
       dwt, mat_stride, ldc, Cout, Cin, kh, kw, kind, alpha, dw);
   return launched("unpack_conv_wgrad");

@@ -70,6 +70,44 @@ static int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64
   return launched(what);
 }
 
+// Skinny case Y[M, N<=16] = X[M,K] W[N,K]^T with K in the thousands (D_GET_LOGITS' final 4x4
+// conv and cate_classify are dot products over the 16k-element feature map): split K over
+// the grid, reduce in the block, one atomicAdd per (row, output, split).  Y is pre-zeroed.
+__global__ void __launch_bounds__(256)
+linear_skinny_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, int64_t ldw,
+                     const float* __restrict__ bias, float* __restrict__ Y, int64_t ldy, int N, int K,
+                     int kchunk) {
+  const int m = blockIdx.y;
+  const int k0 = blockIdx.x * kchunk;
+  const int k1 = min(K, k0 + kchunk);
+  float acc[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+  const float* x = X + static_cast<int64_t>(m) * ldx;
+  for (int k = k0 + threadIdx.x; k < k1; k += 256) {
+    const float xv = x[k];
+#pragma unroll
+    for (int n = 0; n < 16; ++n)
+      if (n < N) acc[n] = fmaf(xv, W[static_cast<int64_t>(n) * ldw + k], acc[n]);
+  }
+  __shared__ float sh[8][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    float v = acc[n];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp][n] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x];
+    if (bias && blockIdx.x == 0) v += bias[threadIdx.x];
+    atomicAdd(Y + static_cast<int64_t>(m) * ldy + threadIdx.x, v);
+  }
+}
+
 // ------------------------------------------------------------------------- GRU gates
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -332,6 +370,13 @@ using namespace cpcsv;
 extern "C" int cpcsv_linear_f32(const float* X, int64_t ldx, const float* W, int64_t ldw,
                                 const float* bias, float* Y, int64_t ldy, int32_t M, int32_t N,
                                 int32_t K, int32_t accumulate, cpcsv_stream_t stream) {
+  if (N <= 16 && K >= 2048 && ldy == N && X && W && Y && M > 0) {
+    if (!accumulate) cudaMemsetAsync(Y, 0, sizeof(float) * M * N, STREAM(stream));
+    const int kchunk = 2048;
+    dim3 grid(static_cast<unsigned>(ceil_div(K, kchunk)), static_cast<unsigned>(M));
+    linear_skinny_kernel<<<grid, 256, 0, STREAM(stream)>>>(X, ldx, W, ldw, bias, Y, ldy, N, K, kchunk);
+    return launched("linear_f32/skinny");
+  }
   return sgemm(X, ldx, 1, W, ldw, 1, bias, Y, ldy, M, N, K, accumulate, STREAM(stream), "linear_f32");
 }
 extern "C" int cpcsv_linear_tn_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* Y,

@@ -179,3 +179,51 @@ def test_spectral_norm_kernels():
         res[dev] = [t.cpu() for t in (uu, vv, s, si, dw)]
     for a, b in zip(res["cuda"], res["cpu"]):
         assert close(a, b, 1e-5)
+
+
+def test_skinny_linear_and_big_unpack():
+    x, w, bias = rnd(90, 5000, seed=40), rnd(9, 5000, seed=41), rnd(9, seed=42)
+    (g, _), (c, _) = both("linear_f32", [x, w, bias], dict(y=torch.zeros(90, 9)))
+    assert close(g["y"], c["y"], 1e-5)
+    (g, _), (c, _) = both("linear_f32", [x, w[:1], None], dict(y=torch.ones(90, 1)), accumulate=True)
+    assert close(g["y"], c["y"], 1e-5)
+    for kind, k in ((0, 4), (0, 3), (2, 3)):
+        nt = 16 if kind == 2 else k * k
+        dwt = rnd(nt, 192, 320, seed=43)
+        (g, _), (c, _) = both("unpack_conv_wgrad", [dwt, 192 * 320, 320, kind, None],
+                              dict(dw=torch.empty(150, 300, k, k)))
+        assert close(g["dw"], c["dw"], 1e-6), kind
+
+
+def test_weight_cache_sees_fused_optimizer_updates():
+    """Adam(fused=True) does not bump Tensor._version; the packed-operand cache must still be
+    refreshed (global optimizer post-step hook in cpcsv_b200.nets)."""
+    import harness
+    from oracle import functional as Fn
+    from oracle import params, presets, synth
+    p = presets.get("small")
+    dev = torch.device("cuda")
+    nets = harness.build_product(p, params.init_all(p, 0), dev)
+    G = nets["G"]
+    batch = synth.make_batch(p, 1, device=dev)
+    x = harness.product_inputs(batch)
+
+    def run():
+        feed = synth.NoiseFeed(synth.make_noise(p, 2, device=dev, calls=("images",)))
+        harness.inject_noise(G, feed)
+        with torch.no_grad():
+            return G.sample_images(x["im_motion"], x["im_content"], seg=True)[1]
+    img0 = run()
+    opt = torch.optim.Adam(G.parameters(), lr=2e-2, betas=(0.5, 0.999), fused=True)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for q in G.parameters():
+        q.grad = torch.randn(q.shape, device=dev, generator=gen)
+    opt.step()
+    img1 = run()
+    sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    # the product forward above already advanced the BN buffers once more than the oracle will
+    feed = synth.NoiseFeed(synth.make_noise(p, 2, device=dev, calls=("images",)))
+    with torch.no_grad():
+        ref = Fn.sample_images(sd, x["im_motion"], x["im_content"], feed, seg=True)[1]
+    assert harness.rel_l2(img1, ref) < 1e-3, harness.rel_l2(img1, ref)
+    assert harness.rel_l2(img0, ref) > 1e-2      # the update really changed the output
