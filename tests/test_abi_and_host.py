@@ -1,0 +1,50 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/cpcsv.h declares
+(no compute calls), argument errors are reported without a GPU, and the product refuses to
+run on CPU tensors (no fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+from cpcsv_b200 import _lib, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    header = open(os.path.join(ROOT, "include", "cpcsv.h")).read()
+    declared = set(re.findall(r"\b(cpcsv_[a-z0-9_]+)\s*\(", header))
+    declared -= {"cpcsv_stream_t"}
+    lib = _lib.load()
+    bound = set(_lib.SIGNATURES) | set(_lib.OTHER_SYMBOLS)
+    assert declared == bound, (declared - bound, bound - declared)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.cpcsv_version() >= 100
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _lib.load()
+    rc = lib.cpcsv_bn_stats(None, 0, 0, 0, None, None)
+    assert rc < 0 and b"bn_stats" in lib.cpcsv_last_error_string()
+    g = _lib.Gemm()
+    g.mode = 7
+    assert lib.cpcsv_conv_gemm(g, None) < 0
+    assert b"mode" in lib.cpcsv_last_error_string()
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.bn_stats(x, torch.zeros(16, dtype=torch.float64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.tanh_fwd(x, x)
+
+
+def test_gemm_struct_layout_matches_header():
+    # sizeof(cpcsv_gemm_t): 18 int32, 4 int64, 2 pointers, 4 views (88 B), 16 taps (40 B)
+    import ctypes as C
+    assert C.sizeof(_lib.View5) == 8 + 5 * 8 + 5 * 8
+    assert C.sizeof(_lib.Tap) == 40
+    assert C.sizeof(_lib.Gemm) == 18 * 4 + 4 * 8 + 2 * 8 + 4 * 88 + 16 * 40
