@@ -34,11 +34,20 @@ def pick_block_n(npad):
 
 
 def pick_splits(tiles, iters):
-    """Split-K factor for small-M layers so the persistent grid fills the 148 SMs."""
-    if tiles >= NUM_SMS or iters < 8:
+    """Split-K factor that fills the last wave of the persistent grid: with `tiles` work items on
+    148 SMs the efficiency is tiles / (ceil(tiles / 148) * 148); splitting the reduction s ways
+    multiplies the tile count.  Each extra split costs a red.add pass over the output, so a
+    split is only taken when it buys > 4 % per step of s."""
+    if iters < 8:
         return 1
-    want = -(-NUM_SMS // tiles)
-    return max(1, min(want, iters // 4))
+    best, best_score = 1, -1.0
+    for s in range(1, min(8, iters // 4) + 1):
+        n = tiles * s
+        eff = n / (-(-n // NUM_SMS) * NUM_SMS)
+        score = eff - 0.04 * (s - 1)
+        if score > best_score + 1e-9:
+            best, best_score = s, score
+    return best
 
 
 def _m_tiles(grid, tile):

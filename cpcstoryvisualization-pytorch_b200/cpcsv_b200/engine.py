@@ -95,32 +95,33 @@ class ConvNode:
         self.alpha = None
         self.dW = None
 
-    def _pack(self, kindcode, rows_pad, cols_pad, planes):
+    def _pack(self, kindcode, rows_pad, cols_pad, planes, dtype=BF16):
         w = self.w
         ntap = CONV_GEOM[self.kind][3]
 
         def build():
             dev = w.device
-            hi = _e((ntap * rows_pad, cols_pad), dev, torch.bfloat16)
-            lo = _e((ntap * rows_pad, cols_pad), dev, torch.bfloat16) if planes == 2 else None
-            ops.pack_conv_weight(w.detach(), kindcode, rows_pad, cols_pad, hi, lo)
+            t16 = ops.TORCH16[dtype]
+            hi = _e((ntap * rows_pad, cols_pad), dev, t16)
+            lo = _e((ntap * rows_pad, cols_pad), dev, t16) if planes == 2 else None
+            ops.pack_conv_weight(w.detach(), kindcode, rows_pad, cols_pad, hi, lo, dtype)
             return [hi, lo]
-        return self.tape.cache.get((id(w), kindcode, planes), w, build)
+        return self.tape.cache.get((id(w), kindcode, planes, dtype), w, build)
 
     def forward(self):
         t, x, out = self.tape, self.x, self.out
         dev = x.hi.device
         if self.sn is not None:
             self.alpha = self.sn.forward(self.w, t.training, t.need_grad)
-        wp = self._pack(CONV_GEOM[self.kind][1], self.Co_pad, self.Ci_pad, t.planes)
+        wp = self._pack(CONV_GEOM[self.kind][1], self.Co_pad, self.Ci_pad, t.planes, t.dtype)
         out.f32 = _e((out.N, out.H, out.W, out.C), dev)
         xp = x.planes(t.planes)
         if self.kind == "s1":
-            job = conv.conv_s1_fwd(xp, wp, out.f32, 3, self.alpha)
+            job = conv.conv_s1_fwd(xp, wp, out.f32, 3, self.alpha, dtype=t.dtype)
         elif self.kind == "up":
-            job = conv.upconv_fwd(xp, wp, out.f32)
+            job = conv.upconv_fwd(xp, wp, out.f32, dtype=t.dtype)
         else:
-            job = conv.conv_s2_fwd(xp, wp, out.f32, self.alpha)
+            job = conv.conv_s2_fwd(xp, wp, out.f32, self.alpha, dtype=t.dtype)
         ops.conv_gemm(job)
 
     def backward(self, need_wgrad=True):
@@ -201,7 +202,8 @@ class GemmNode:
         dev = x.hi.device
         out.f32 = _e((out.N, out.H, out.W, out.C), dev)
         a = [p.view(x.rows, x.C) if p is not None else None for p in x.planes(t.planes)]
-        ops.conv_gemm(conv.gemm_nt(a, self.pack_fwd(t.planes), out.f32.view(x.rows, self.npad)))
+        ops.conv_gemm(conv.gemm_nt(a, self.pack_fwd(t.planes, t.dtype), out.f32.view(x.rows, self.npad),
+                                   dtype=t.dtype))
 
     def backward(self, need_wgrad=True):
         x, out = self.x, self.out
@@ -246,18 +248,21 @@ class BnActNode:
                             rmean if t.training else None, rvar if t.training else None,
                             self.chan_map, self.c_valid, vec[0], vec[1], vec[2], vec[3])
             if t.training and nbt is not None:
-                nbt.add_(1)
+                t.counters.append(nbt)
             self.stat = vec
             scale, shift = vec[2], vec[3]
         if self.want_f32:
             out.f32 = _e((z.N, z.H, z.W, z.C), dev)
         if self.want_planes:
-            out.hi = _e((z.N, z.H, z.W, z.C), dev, torch.bfloat16)
-            out.lo = _e((z.N, z.H, z.W, z.C), dev, torch.bfloat16) if t.planes == 2 else None
+            t16 = ops.TORCH16[t.dtype]
+            out.hi = _e((z.N, z.H, z.W, z.C), dev, t16)
+            out.lo = _e((z.N, z.H, z.W, z.C), dev, t16) if t.planes == 2 else None
         ops.bn_act_pack(zm, scale, shift, self.act, z.mat(self.mod.f32) if self.mod is not None else None,
                         z.mat(out.f32) if out.f32 is not None else None,
                         z.mat(out.hi) if out.hi is not None else None,
-                        z.mat(out.lo) if out.lo is not None else None)
+                        z.mat(out.lo) if out.lo is not None else None, t.dtype)
+        if not t.need_grad and self.mod is None:
+            z.f32 = None        # nothing reads the raw conv output again: release it early
 
     def backward(self, need_param_grad=True):
         z, out = self.z, self.out
@@ -273,8 +278,9 @@ class BnActNode:
             sums = _e((2 * z.C,), dev, torch.float64)
             ops.bn_bwd_reduce(zm, dym, vec[2], vec[3], vec[0], vec[1], self.act, modm, sums)
             if need_param_grad:
-                self.dgamma = torch.zeros_like(self.bn[0])
-                self.dbeta = torch.zeros_like(self.bn[1])
+                # every entry is written by bn_bwd_apply (all real channels are mapped)
+                self.dgamma = torch.empty_like(self.bn[0])
+                self.dbeta = torch.empty_like(self.bn[1])
         z.grad16 = _e((z.N, z.H, z.W, z.C), dev, torch.bfloat16)
         dmod16 = None
         if self.mod is not None:
@@ -290,9 +296,23 @@ class BnActNode:
 
 
 class Tape:
-    def __init__(self, cache, training=True, need_grad=True, planes=2):
-        self.cache, self.training, self.need_grad, self.planes = cache, training, need_grad, planes
+    """One network call.  With ``need_grad`` the forward GEMMs use bf16 hi/lo split operands
+    (3 MMAs); a no-grad call (the fakes for the discriminator update, inference) uses single-pass
+    fp16 operands -- SURVEY.md Appendix E: fp16, not bf16, keeps the discriminator gradients that
+    are computed on those fakes within tolerance."""
+
+    def __init__(self, cache, training=True, need_grad=True, planes=None, dtype=None):
+        self.cache, self.training, self.need_grad = cache, training, need_grad
+        self.planes = planes if planes is not None else (2 if need_grad else 1)
+        self.dtype = dtype if dtype is not None else (ops.BF16 if need_grad else ops.FP16)
         self.nodes = []
+        self.counters = []      # num_batches_tracked buffers to bump once the forward is done
+
+    def finish_forward(self):
+        """one multi-tensor launch for all `num_batches_tracked += 1` of this call"""
+        if self.counters:
+            torch._foreach_add_(self.counters, 1)
+            self.counters = []
 
     def add(self, node):
         self.nodes.append(node)

@@ -112,13 +112,14 @@ class TrunkRunner:
         perm = self._fc_maps(C, w.device)
         cache = tape.cache
 
-        def pack_fwd(planes):
+        def pack_fwd(planes, dtype):
             def build():
-                hi = _e((16 * Cp, Kp), w.device, torch.bfloat16)
-                lo = _e((16 * Cp, Kp), w.device, torch.bfloat16) if planes == 2 else None
-                ops.pack_matrix(w.detach(), 16 * Cp, Kp, K, K, 1, perm, hi, lo)
+                t16 = ops.TORCH16[dtype]
+                hi = _e((16 * Cp, Kp), w.device, t16)
+                lo = _e((16 * Cp, Kp), w.device, t16) if planes == 2 else None
+                ops.pack_matrix(w.detach(), 16 * Cp, Kp, K, K, 1, perm, hi, lo, dtype)
                 return [hi, lo]
-            return cache.get((id(w), "fc_fwd", planes), w, build)
+            return cache.get((id(w), "fc_fwd", planes, dtype), w, build)
 
         def pack_bwd():
             def build():
@@ -138,17 +139,19 @@ class TrunkRunner:
         _eval_bn_unsupported(G)
         dev = zmc_all.device
         N, K = zmc_all.shape
-        tape = Tape(_CACHE, training=G.training, need_grad=self.need_grad, planes=2)
+        tape = Tape(_CACHE, training=G.training, need_grad=self.need_grad)
         self.tape = tape
         ngf, nseg = G.gf_dim, G.gf_dim_seg
         Kp = rup(K, 64)
+        t16 = ops.TORCH16[tape.dtype]
         # latent -> operand planes (zero padded to a multiple of 64 columns)
         x0 = T4(N, 1, 1, Kp)
-        x0.hi = torch.zeros(N, 1, 1, Kp, device=dev, dtype=torch.bfloat16)
-        x0.lo = torch.zeros(N, 1, 1, Kp, device=dev, dtype=torch.bfloat16)
+        x0.hi = torch.zeros(N, 1, 1, Kp, device=dev, dtype=t16)
+        x0.lo = torch.zeros(N, 1, 1, Kp, device=dev, dtype=t16) if tape.planes == 2 else None
         zc = zmc_all.detach().contiguous()
         ops.bn_act_pack(_pad4(zc), None, None, ops.ACT_NONE, hi=x0.hi.view(N, Kp)[:, :rup(K, 4)],
-                        lo=x0.lo.view(N, Kp)[:, :rup(K, 4)])
+                        lo=x0.lo.view(N, Kp)[:, :rup(K, 4)] if x0.lo is not None else None,
+                        dtype=tape.dtype)
         x0.needs_grad = self.need_grad
         self.x0, self.K = x0, K
 
@@ -198,9 +201,10 @@ class TrunkRunner:
         img = self._head_fwd(a_img, G.img[0].weight, 3, "img")
         seg = self._head_fwd(a_seg, G.img_seg[0].weight, 1, "img_seg")
         self.img, self.seg = img, seg
+        tape.finish_forward()
         return img, seg
 
-    def _head_pack(self, w, kind):
+    def _head_pack(self, w, kind, planes=2, dtype=ops.BF16):
         """3x3 head conv with 3 / 1 output channels.  kind 'fwd': [9 * 16, Ci] tap-major K-major;
         kind 'bwd': [Ci, 64] with column tap*Co + co (the im2col'd-gradient GEMM)."""
         Co, Ci = w.shape[0], w.shape[1]
@@ -208,9 +212,10 @@ class TrunkRunner:
 
         def build():
             if kind == "fwd":
-                hi = _e((9 * 16, Cip), w.device, torch.bfloat16)
-                lo = _e((9 * 16, Cip), w.device, torch.bfloat16)
-                ops.pack_conv_weight(w.detach(), 0, 16, Cip, hi, lo)
+                t16 = ops.TORCH16[dtype]
+                hi = _e((9 * 16, Cip), w.device, t16)
+                lo = _e((9 * 16, Cip), w.device, t16) if planes == 2 else None
+                ops.pack_conv_weight(w.detach(), 0, 16, Cip, hi, lo, dtype)
                 return [hi, lo]
             w2 = w.detach().permute(1, 2, 3, 0).reshape(Ci, 9 * Co).contiguous()   # [ci, tap*Co+co]
             hi = _e((Cip, 64), w.device, torch.bfloat16)
@@ -218,12 +223,14 @@ class TrunkRunner:
             ops.pack_matrix(w2, Cip, 64, 9 * Co, 9 * Co, 1, rmap, hi, None) if Cip == Ci else \
                 ops.pack_matrix(w2, Cip, 64, 9 * Co, 9 * Co, 1, _row_pad_map(Ci, Cip, w.device), hi, None)
             return hi
-        return _CACHE.get((id(w), "head_" + kind, 2), w, build)
+        return _CACHE.get((id(w), "head_" + kind, planes, dtype), w, build)
 
     def _head_fwd(self, a, w, Co, name):
         dev = a.hi.device
         z = _e((a.N, a.H, a.W, 16), dev)
-        ops.conv_gemm(conv.conv_s1_fwd(a.planes(2), self._head_pack(w, "fwd"), z, 3))
+        tp = self.tape
+        ops.conv_gemm(conv.conv_s1_fwd(a.planes(tp.planes), self._head_pack(w, "fwd", tp.planes, tp.dtype), z, 3,
+                                       dtype=tp.dtype))
         y = _e((a.N, Co, a.H, a.W), dev)
         ops.tanh_to_nchw(z.view(a.rows, 16), a.N, Co, a.H, a.W, y)
         return y
@@ -393,7 +400,7 @@ class EncoderRunner:
         enc = D.encode_img
         dev = x.device
         n, Cin, H, W = x.shape
-        tape = Tape(_CACHE, training=D.training, need_grad=self.need_grad, planes=2)
+        tape = Tape(_CACHE, training=D.training, need_grad=self.need_grad, planes=2, dtype=ops.BF16)
         self.tape = tape
         self.x_shape = (n, Cin, H, W)
         xd = x.detach()
@@ -433,6 +440,7 @@ class EncoderRunner:
             self.layers.append((cn, bn, idx))
         self.feat = a
         Cf = enc[8].weight_orig.shape[0]
+        tape.finish_forward()
         return a.f32.permute(0, 3, 1, 2)[:, :Cf]
 
     def run_backward(self, grads, needs):
@@ -516,7 +524,7 @@ class LogitsRunner:
         n, Cf, H, W = h_code.shape
         Ce = c_code.shape[1]
         Cc = rup(Cf + Ce, 64)
-        tape = Tape(_CACHE, training=L.training, need_grad=self.need_grad, planes=2)
+        tape = Tape(_CACHE, training=L.training, need_grad=self.need_grad, planes=2, dtype=ops.BF16)
         self.tape = tape
         x = T4(n, H, W, Cc)
         x.hi = _e((n, H, W, Cc), dev, torch.bfloat16)
@@ -541,6 +549,7 @@ class LogitsRunner:
         out = _e((n,), dev)
         ops.affine_sigmoid_fwd(t.view(n), inv_sigma, seq[3].bias.detach(), out)
         self.wrow, self.inv_sigma, self.out = wrow, inv_sigma, out
+        tape.finish_forward()
         return out
 
     def run_backward(self, grads, needs):

@@ -461,6 +461,55 @@ __device__ __forceinline__ void merged_range(int a, int i, int& lo, int& hi) {
   else        { lo = i == 0 ? 0 : 2; hi = i == 0 ? 1 : 2; }
 }
 
+// Tiled variant: a block owns a 16 (co) x 32 (ci) tile of the weight for ALL taps.  The source
+// w[co][ci][t] is read as contiguous runs of 32*T floats per co, staged in shared memory, and
+// written out per tap with the threads running along the destination's contiguous dimension.
+__global__ void __launch_bounds__(256)
+pack_conv_weight_tiled_kernel(const float* __restrict__ w, int Cout, int Cin, int T, int kind,
+                              int rows_pad, int cols_pad, uint16_t* __restrict__ hi,
+                              uint16_t* __restrict__ lo, int dtype) {
+  __shared__ float s[16][32 * 16 + 1];
+  const int co0 = blockIdx.y * 16, ci0 = blockIdx.x * 32;
+  const bool transposed = (kind == 1 || kind == 3);
+  const int ntap = kind >= 2 ? 16 : T;
+  // load: 16 rows (co) of 32*T contiguous floats
+  const int run = 32 * T;
+  for (int i = threadIdx.x; i < 16 * run; i += 256) {
+    const int r = i / run, j = i - r * run;
+    const int co = co0 + r, ci = ci0 + j / T;
+    s[r][j] = (co < Cout && ci < Cin) ? w[(static_cast<int64_t>(co) * Cin + ci0) * T + j] : 0.f;
+  }
+  __syncthreads();
+  // store: one (tap, co, ci) element per iteration; fastest thread index follows the output's
+  // contiguous dimension (ci for [tap][co][ci], co for [tap][ci][co])
+  for (int i = threadIdx.x; i < ntap * 16 * 32; i += 256) {
+    int tap, r, c;   // r: co index in tile, c: ci index in tile
+    if (!transposed) { c = i & 31; r = (i >> 5) & 15; tap = i >> 9; }
+    else             { r = i & 15; c = (i >> 4) & 31; tap = i >> 9; }
+    float v;
+    if (kind < 2) {
+      v = s[r][c * T + tap];
+    } else {
+      const int a = tap >> 3, b = (tap >> 2) & 1, ti = (tap >> 1) & 1, tj = tap & 1;
+      int y0, y1, x0, x1;
+      merged_range(a, ti, y0, y1);
+      merged_range(b, tj, x0, x1);
+      v = 0.f;
+      for (int ky = y0; ky <= y1; ++ky)
+        for (int kx = x0; kx <= x1; ++kx) v += s[r][c * 9 + ky * 3 + kx];
+    }
+    const int row = transposed ? ci0 + c : co0 + r;
+    const int col = transposed ? co0 + r : ci0 + c;
+    if (row < rows_pad && col < cols_pad) {
+      uint16_t hv, lv;
+      split16(v, dtype, hv, lv);
+      const int64_t o = (static_cast<int64_t>(tap) * rows_pad + row) * cols_pad + col;
+      hi[o] = hv;
+      if (lo) lo[o] = lv;
+    }
+  }
+}
+
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw,
                                         int kind, int rows_pad, int cols_pad,
                                         uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
@@ -754,6 +803,15 @@ extern "C" int cpcsv_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin,
                 "pack_conv_weight: padding smaller than the matrix");
   const int ntap = kind >= 2 ? 16 : kh * kw;
   const int64_t work = static_cast<int64_t>(ntap) * rows_pad * cols_pad;
+  if (kh * kw <= 16) {
+    // tiles cover the PADDED index space so the zero padding is written too
+    const int co_ext = tr ? cols_pad : rows_pad, ci_ext = tr ? rows_pad : cols_pad;
+    dim3 grid(static_cast<unsigned>(ceil_div(ci_ext, 32)), static_cast<unsigned>(ceil_div(co_ext, 16)));
+    pack_conv_weight_tiled_kernel<<<grid, 256, 0, STREAM(stream)>>>(
+        w, Cout, Cin, kh * kw, kind, rows_pad, cols_pad, static_cast<uint16_t*>(hi),
+        static_cast<uint16_t*>(lo), dtype);
+    return launched("pack_conv_weight");
+  }
   pack_conv_weight_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
       w, Cout, Cin, kh, kw, kind, rows_pad, cols_pad, static_cast<uint16_t*>(hi),
       static_cast<uint16_t*>(lo), dtype);

@@ -280,18 +280,32 @@ __global__ void sn_wt_u_kernel(const float* __restrict__ W, int R, int C, const 
   for (int r = r0; r < r1; ++r) acc = fmaf(W[static_cast<int64_t>(r) * C + c], u[r], acc);
   atomicAdd(&t[c], acc);
 }
-// t[r] = dot(W[r], v): one warp per row
-__global__ void sn_w_v_kernel(const float* __restrict__ W, int R, int C, const float* __restrict__ v,
-                              float* __restrict__ t) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= R) return;
-  const float* w = W + static_cast<int64_t>(warp) * C;
-  float acc = 0.f;
-  for (int c = lane; c < C; c += 32) acc = fmaf(w[c], v[c], acc);
+// t[r] = dot(W[r], v): one 256-thread block per row, 4 independent loads in flight per thread
+__global__ void __launch_bounds__(256)
+sn_w_v_kernel(const float* __restrict__ W, int R, int C, const float* __restrict__ v,
+              float* __restrict__ t) {
+  const int r = blockIdx.x;
+  const float* w = W + static_cast<int64_t>(r) * C;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int c = threadIdx.x;
+  for (; c + 768 < C; c += 1024) {
+    a0 = fmaf(w[c], v[c], a0);
+    a1 = fmaf(w[c + 256], v[c + 256], a1);
+    a2 = fmaf(w[c + 512], v[c + 512], a2);
+    a3 = fmaf(w[c + 768], v[c + 768], a3);
+  }
+  for (; c < C; c += 256) a0 = fmaf(w[c], v[c], a0);
+  float acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) t[warp] = acc;
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += sh[i];
+    t[r] = s;
+  }
 }
 __device__ float block_sum(float v, float* sh) {
 #pragma unroll
@@ -484,8 +498,7 @@ extern "C" int cpcsv_spectral_sigma(const float* W, int32_t R, int32_t C, float*
     rc = launched("spectral_sigma/normalize_v");
     if (rc) return rc;
   }
-  sn_w_v_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(R) * 32, 256)), 256, 0, stream>>>(
-      W, R, C, v, tr);
+  sn_w_v_kernel<<<static_cast<unsigned>(R), 256, 0, stream>>>(W, R, C, v, tr);
   int rc = launched("spectral_sigma/W_v");
   if (rc) return rc;
   sn_finish_kernel<<<1, 1024, 0, stream>>>(tr, R, eps, do_power_iteration, u, sigma, inv_sigma);
