@@ -33,18 +33,22 @@ def pick_block_n(npad):
     raise AssertionError(npad)
 
 
-def pick_splits(tiles, iters):
+def pick_splits(tiles, iters, penalty=0.04):
     """Split-K factor that fills the last wave of the persistent grid: with `tiles` work items on
     148 SMs the efficiency is tiles / (ceil(tiles / 148) * 148); splitting the reduction s ways
     multiplies the tile count.  Each extra split costs a red.add pass over the output, so a
     split is only taken when it buys > 4 % per step of s."""
     if iters < 8:
         return 1
+    if tiles * 8 < NUM_SMS:
+        # a handful of output tiles with a very long reduction (first-layer / head weight
+        # gradients: K = all pixels): one split per SM
+        return max(1, min(-(-NUM_SMS // tiles), iters // 4))
     best, best_score = 1, -1.0
     for s in range(1, min(8, iters // 4) + 1):
         n = tiles * s
         eff = n / (-(-n // NUM_SMS) * NUM_SMS)
-        score = eff - 0.04 * (s - 1)
+        score = eff - penalty * (s - 1)
         if score > best_score + 1e-9:
             best, best_score = s, score
     return best
@@ -78,7 +82,7 @@ def _wgrad_job(a_view, b_view, grid, taps, m_valid, npad, out, ldc, dtype=BF16, 
     n_tiles = npad // block_n
     iters = _m_tiles(grid, tile)
     if splits is None:
-        splits = pick_splits(len(taps) * (-(-m_valid // 128)) * n_tiles, iters)
+        splits = pick_splits(len(taps) * (-(-m_valid // 128)) * n_tiles, iters, penalty=0.10)
     return GemmJob(mode=1, planes=1, grid=grid, tile=tile, groups=len(taps), taps_per_group=1,
                    k_blocks=0, taps=taps, a=[a_view], b=[b_view], out=out, n_valid=npad,
                    block_n=block_n, n_tiles=n_tiles, m_valid=m_valid, splits=splits, ldc=ldc,
