@@ -55,8 +55,23 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C
   const int c = (blockIdx.x * 32 + cq) * 4;
   double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
   if (c < C) {
-    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + rl; r < rows;
-         r += static_cast<int64_t>(gridDim.y) * 8) {
+    // 4 independent 16-byte loads in flight per thread; fp64 accumulation keeps the
+    // E[x^2] - mean^2 cancellation exact
+    const int64_t step = static_cast<int64_t>(gridDim.y) * 8;
+    int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + rl;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(x + (r + u * step) * ldx + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[0] += v[u].x; ss[0] += static_cast<double>(v[u].x) * v[u].x;
+        s[1] += v[u].y; ss[1] += static_cast<double>(v[u].y) * v[u].y;
+        s[2] += v[u].z; ss[2] += static_cast<double>(v[u].z) * v[u].z;
+        s[3] += v[u].w; ss[3] += static_cast<double>(v[u].w) * v[u].w;
+      }
+    }
+    for (; r < rows; r += step) {
       const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
       s[0] += v.x; ss[0] += static_cast<double>(v.x) * v.x;
       s[1] += v.y; ss[1] += static_cast<double>(v.y) * v.y;
@@ -201,8 +216,18 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
   const int c = (blockIdx.x * 32 + cq) * 4;
   double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
   if (c < C) {
-    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + rl; r < rows;
-         r += static_cast<int64_t>(gridDim.y) * 8) {
+    const int64_t step = static_cast<int64_t>(gridDim.y) * 8;
+    int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + rl;
+    for (; r + step < rows; r += 2 * step) {   // two rows in flight
+      const BwdElem e0 = bwd_elem(x, dy, r, c, ldx, lddy, scale, shift, mean, invstd, act, mod, ldmod);
+      const BwdElem e1 = bwd_elem(x, dy, r + step, c, ldx, lddy, scale, shift, mean, invstd, act, mod, ldmod);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] += static_cast<double>(e0.g[j]) + e1.g[j];
+        sx[j] += static_cast<double>(e0.g[j]) * e0.xhat[j] + static_cast<double>(e1.g[j]) * e1.xhat[j];
+      }
+    }
+    for (; r < rows; r += step) {
       const BwdElem e = bwd_elem(x, dy, r, c, ldx, lddy, scale, shift, mean, invstd, act, mod, ldmod);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -419,6 +444,43 @@ __global__ void tanh_bwd_im2col_kernel(const float* __restrict__ dy, int64_t sn,
   }
 }
 
+// Row-staged variant (C <= 4, W <= 128): one block per image row.  dz = dy * (1 - y^2) of the
+// three source rows is computed once into shared memory with coalesced NCHW reads; the 64-wide
+// im2col rows are then written contiguously.
+__global__ void __launch_bounds__(256)
+tanh_bwd_im2col_rows_kernel(const float* __restrict__ dy, int64_t sn, int64_t sc, int64_t sh,
+                            int64_t sw, const float* __restrict__ y, int C, int H, int W,
+                            uint16_t* __restrict__ col, int ldp, int dtype) {
+  __shared__ float dz[3][4][130];   // [source row h-1..h+1][channel][w + 1], zero borders
+  const int h = blockIdx.x % H;
+  const int n = blockIdx.x / H;
+  for (int i = threadIdx.x; i < 3 * C * (W + 2); i += 256) {
+    const int wq = i % (W + 2);
+    const int c = (i / (W + 2)) % C;
+    const int rr = i / ((W + 2) * C);
+    const int ih = h - 1 + rr, iw = wq - 1;
+    float v = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      const float yy = y[((static_cast<int64_t>(n) * C + c) * H + ih) * W + iw];
+      v = dy[n * sn + c * sc + ih * sh + iw * sw] * (1.f - yy * yy);
+    }
+    dz[rr][c][wq] = v;
+  }
+  __syncthreads();
+  uint16_t* out = col + (static_cast<int64_t>(n) * H + h) * W * ldp;
+  for (int i = threadIdx.x; i < W * ldp; i += 256) {
+    const int j = i % ldp, w = i / ldp;
+    float v = 0.f;
+    if (j < 9 * C) {
+      const int tap = j / C, c = j - tap * C;
+      const int ky = tap / 3, kx = tap - ky * 3;
+      // source pixel (h - (ky-1), w - (kx-1)) -> staged row 2 - ky, column w - kx + 2
+      v = dz[2 - ky][c][w - kx + 2];
+    }
+    out[i] = to16(v, dtype);
+  }
+}
+
 // ------------------------------------------------------------------------- weight packing
 __global__ void pack_matrix_kernel(const float* __restrict__ w, int64_t rows_out, int64_t cols_out,
                                    int64_t cols_valid, int64_t ld_r, int64_t ld_c,
@@ -480,32 +542,46 @@ pack_conv_weight_tiled_kernel(const float* __restrict__ w, int Cout, int Cin, in
     s[r][j] = (co < Cout && ci < Cin) ? w[(static_cast<int64_t>(co) * Cin + ci0) * T + j] : 0.f;
   }
   __syncthreads();
-  // store: one (tap, co, ci) element per iteration; fastest thread index follows the output's
-  // contiguous dimension (ci for [tap][co][ci], co for [tap][ci][co])
-  for (int i = threadIdx.x; i < ntap * 16 * 32; i += 256) {
-    int tap, r, c;   // r: co index in tile, c: ci index in tile
-    if (!transposed) { c = i & 31; r = (i >> 5) & 15; tap = i >> 9; }
-    else             { r = i & 15; c = (i >> 4) & 31; tap = i >> 9; }
-    float v;
-    if (kind < 2) {
-      v = s[r][c * T + tap];
-    } else {
+  // store: every thread emits 8 consecutive elements (one 16-byte store per plane) along the
+  // output's contiguous dimension: ci for [tap][co][ci], co for [tap][ci][co]
+  for (int i = threadIdx.x; i < ntap * 64; i += 256) {
+    const int tap = i >> 6;
+    int r0, c0, dr, dc;      // first (co, ci) element inside the tile and the step along the vector
+    if (!transposed) { c0 = (i & 3) * 8; r0 = (i >> 2) & 15; dr = 0; dc = 1; }
+    else             { r0 = (i & 1) * 8; c0 = (i >> 1) & 31; dr = 1; dc = 0; }
+    int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
+    if (kind >= 2) {
       const int a = tap >> 3, b = (tap >> 2) & 1, ti = (tap >> 1) & 1, tj = tap & 1;
-      int y0, y1, x0, x1;
       merged_range(a, ti, y0, y1);
       merged_range(b, tj, x0, x1);
-      v = 0.f;
-      for (int ky = y0; ky <= y1; ++ky)
-        for (int kx = x0; kx <= x1; ++kx) v += s[r][c * 9 + ky * 3 + kx];
     }
-    const int row = transposed ? ci0 + c : co0 + r;
-    const int col = transposed ? co0 + r : ci0 + c;
+    uint16_t hv[8], lv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int r = r0 + e * dr, c = c0 + e * dc;
+      float v;
+      if (kind < 2) {
+        v = s[r][c * T + tap];
+      } else {
+        v = 0.f;
+        for (int ky = y0; ky <= y1; ++ky)
+          for (int kx = x0; kx <= x1; ++kx) v += s[r][c * 9 + ky * 3 + kx];
+      }
+      split16(v, dtype, hv[e], lv[e]);
+    }
+    const int row = transposed ? ci0 + c0 : co0 + r0;
+    const int col = transposed ? co0 + r0 : ci0 + c0;
     if (row < rows_pad && col < cols_pad) {
-      uint16_t hv, lv;
-      split16(v, dtype, hv, lv);
       const int64_t o = (static_cast<int64_t>(tap) * rows_pad + row) * cols_pad + col;
-      hi[o] = hv;
-      if (lo) lo[o] = lv;
+      uint4 hq, lq;
+      hq.x = hv[0] | (static_cast<uint32_t>(hv[1]) << 16); hq.y = hv[2] | (static_cast<uint32_t>(hv[3]) << 16);
+      hq.z = hv[4] | (static_cast<uint32_t>(hv[5]) << 16); hq.w = hv[6] | (static_cast<uint32_t>(hv[7]) << 16);
+      *reinterpret_cast<uint4*>(hi + o) = hq;
+      if (lo) {
+        lq.x = lv[0] | (static_cast<uint32_t>(lv[1]) << 16); lq.y = lv[2] | (static_cast<uint32_t>(lv[3]) << 16);
+        lq.z = lv[4] | (static_cast<uint32_t>(lv[5]) << 16); lq.w = lv[6] | (static_cast<uint32_t>(lv[7]) << 16);
+        *reinterpret_cast<uint4*>(lo + o) = lq;
+      }
     }
   }
 }
@@ -643,7 +719,7 @@ extern "C" int cpcsv_bn_stats(const float* x, int64_t rows, int32_t C, int64_t l
   CPCSV_REQUIRE(x && stats && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_stats: args");
   cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, STREAM(stream));
   dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), 1);
-  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 4, grid.x);
+  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 8, grid.x);
   const int64_t max_gy = ceil_div(rows, 8);
   if (gy > max_gy) gy = max_gy;
   grid.y = static_cast<unsigned>(gy < 1 ? 1 : gy);
@@ -690,7 +766,7 @@ extern "C" int cpcsv_bn_bwd_reduce(const float* x, const float* dy, int64_t rows
                 "bn_bwd_reduce: args");
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, STREAM(stream));
   dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), 1);
-  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 4, grid.x);
+  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 8, grid.x);
   const int64_t max_gy = ceil_div(rows, 8);
   if (gy > max_gy) gy = max_gy;
   grid.y = static_cast<unsigned>(gy < 1 ? 1 : gy);
@@ -768,6 +844,11 @@ extern "C" int cpcsv_tanh_bwd_im2col(const float* dy, int64_t sn, int64_t sc, in
                                      void* col, int32_t ldp, int32_t dtype, cpcsv_stream_t stream) {
   CPCSV_REQUIRE(dy && y && col && 9 * C <= ldp, "tanh_bwd_im2col: args");
   const int64_t work = static_cast<int64_t>(N) * H * W * ldp;
+  if (C <= 4 && W <= 128) {
+    tanh_bwd_im2col_rows_kernel<<<static_cast<unsigned>(N * H), 256, 0, STREAM(stream)>>>(
+        dy, sn, sc, sh, sw, y, C, H, W, static_cast<uint16_t*>(col), ldp, dtype);
+    return launched("tanh_bwd_im2col");
+  }
   tanh_bwd_im2col_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
       dy, sn, sc, sh, sw, y, N, C, H, W, static_cast<uint16_t*>(col), ldp, dtype);
   return launched("tanh_bwd_im2col");
@@ -803,7 +884,7 @@ extern "C" int cpcsv_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin,
                 "pack_conv_weight: padding smaller than the matrix");
   const int ntap = kind >= 2 ? 16 : kh * kw;
   const int64_t work = static_cast<int64_t>(ntap) * rows_pad * cols_pad;
-  if (kh * kw <= 16) {
+  if (kh * kw <= 16 && cols_pad % 8 == 0) {
     // tiles cover the PADDED index space so the zero padding is written too
     const int co_ext = tr ? cols_pad : rows_pad, ci_ext = tr ? rows_pad : cols_pad;
     dim3 grid(static_cast<unsigned>(ceil_div(ci_ext, 32)), static_cast<unsigned>(ceil_div(co_ext, 16)));
