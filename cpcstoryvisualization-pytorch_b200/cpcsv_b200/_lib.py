@@ -74,7 +74,8 @@ SIGNATURES = {
     "cpcsv_spectral_sigma": [_p, _i32, _i32, _p, _p, _i32, _f32, _p, _p, _p, _p],
     "cpcsv_spectral_bwd": [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p],
 }
-OTHER_SYMBOLS = ("cpcsv_version", "cpcsv_last_error_string", "cpcsv_launch_count")
+OTHER_SYMBOLS = ("cpcsv_version", "cpcsv_last_error_string", "cpcsv_launch_count",
+                 "cpcsv_bn_workspace_doubles")
 
 _lib = None
 
@@ -96,6 +97,8 @@ def load():
     lib.cpcsv_version.restype = C.c_int
     lib.cpcsv_last_error_string.restype = C.c_char_p
     lib.cpcsv_launch_count.restype = C.c_int64
+    lib.cpcsv_bn_workspace_doubles.argtypes = [C.c_int64, C.c_int32]
+    lib.cpcsv_bn_workspace_doubles.restype = C.c_int64
     _lib = lib
     return lib
 

@@ -241,7 +241,7 @@ class BnActNode:
         scale = shift = None
         if self.bn is not None:
             gamma, beta, rmean, rvar, nbt = self.bn
-            stats = _e((2 * z.C,), dev, torch.float64)
+            stats = ops.bn_workspace(z.rows, z.C, dev)
             ops.bn_stats(zm, stats)
             vec = _e((4, z.C), dev)
             ops.bn_finalize(stats, z.rows, gamma.detach(), beta.detach(),
@@ -275,7 +275,7 @@ class BnActNode:
         sums = None
         if has_bn:
             vec = self.stat
-            sums = _e((2 * z.C,), dev, torch.float64)
+            sums = ops.bn_workspace(z.rows, z.C, dev)
             ops.bn_bwd_reduce(zm, dym, vec[2], vec[3], vec[0], vec[1], self.act, modm, sums)
             if need_param_grad:
                 # every entry is written by bn_bwd_apply (all real channels are mapped)

@@ -60,7 +60,7 @@ class BatchNorm1dFn(torch.autograd.Function):
         dev = x.device
         xp = torch.zeros(M, Cp, device=dev)
         xp[:, :C].copy_(x)
-        stats = torch.empty(2 * Cp, device=dev, dtype=torch.float64)
+        stats = ops.bn_workspace(M, Cp, dev)
         ops.bn_stats(xp, stats)
         vec = torch.empty(4, Cp, device=dev)
         ops.bn_finalize(stats, M, gamma.detach(), beta.detach(), rmean if training else None,
@@ -90,7 +90,7 @@ class BatchNorm1dFn(torch.autograd.Function):
             d2 = torch.empty_like(dyp)
             ops.tanh_bwd(tout, dyp, d2)
             dyp = d2
-        sums = torch.empty(2 * Cp, device=dev, dtype=torch.float64)
+        sums = ops.bn_workspace(M, Cp, dev)
         ops.bn_bwd_reduce(xp, dyp, vec[2], vec[3], vec[0], vec[1], ops.ACT_NONE, None, sums)
         dx = torch.empty(M, Cp, device=dev)
         dgamma = torch.zeros(ctx.gshape, device=dev)

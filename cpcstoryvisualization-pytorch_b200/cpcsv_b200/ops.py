@@ -123,9 +123,15 @@ def conv_gemm(job):
 
 
 # ------------------------------------------------------------------ BatchNorm / packing
+def bn_workspace(rows, channels, device):
+    """fp64 buffer for bn_stats / bn_bwd_reduce: [0, 2C) results, then per-block partials."""
+    n = _lib.load().cpcsv_bn_workspace_doubles(rows, channels)
+    return torch.empty(n, device=device, dtype=torch.float64)
+
+
 def bn_stats(x, stats):
     rows, Cc, ld = _rows2d(x)
-    assert stats.numel() == 2 * Cc
+    assert stats.numel() >= 2 * Cc
     _lib.check(_lib.load().cpcsv_bn_stats(_ptr(x, torch.float32), rows, Cc, ld,
                                           _ptr(stats, torch.float64), _stream()), "cpcsv_bn_stats")
 

@@ -91,10 +91,30 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C
     for (int j = 0; j < 8; ++j) {
       double t = 0;
       for (int k = 0; k < 8; ++k) t += sh[k][cq][j];
-      if (j < 4) atomicAdd(&stats[c + j], t);
-      else atomicAdd(&stats[C + c + (j - 4)], t);
+      // per-block partial (no atomics: hundreds of blocks hitting 2C addresses serialise in L2)
+      double* part = stats + static_cast<int64_t>(2 * C) * (1 + blockIdx.y);
+      if (j < 4) part[c + j] = t;
+      else part[C + c + (j - 4)] = t;
     }
   }
+}
+
+// out[i] = sum_p part[p][i] for i < n; partials start at out + n
+__global__ void sum_partials_kernel(double* __restrict__ out, int n, int parts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double t = 0;
+  for (int p = 0; p < parts; ++p) t += out[static_cast<int64_t>(n) * (1 + p) + i];
+  out[i] = t;
+}
+
+// number of row-blocks (= partial slots) the reduction kernels use for a [rows, C] problem
+static inline int reduction_parts(int64_t rows, int C) {
+  const int64_t gx = ceil_div(C, 128);
+  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 4, gx);
+  const int64_t max_gy = ceil_div(rows, 8);
+  if (gy > max_gy) gy = max_gy;
+  return static_cast<int>(gy < 1 ? 1 : gy);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t rows, int C,
@@ -248,8 +268,9 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
     for (int j = 0; j < 8; ++j) {
       double t = 0;
       for (int k = 0; k < 8; ++k) t += sh[k][cq][j];
-      if (j < 4) atomicAdd(&sums[c + j], t);
-      else atomicAdd(&sums[C + c + (j - 4)], t);
+      double* part = sums + static_cast<int64_t>(2 * C) * (1 + blockIdx.y);
+      if (j < 4) part[c + j] = t;
+      else part[C + c + (j - 4)] = t;
     }
   }
 }
@@ -717,14 +738,18 @@ using namespace cpcsv;
 extern "C" int cpcsv_bn_stats(const float* x, int64_t rows, int32_t C, int64_t ldx, double* stats,
                               cpcsv_stream_t stream) {
   CPCSV_REQUIRE(x && stats && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_stats: args");
-  cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, STREAM(stream));
-  dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), 1);
-  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 8, grid.x);
-  const int64_t max_gy = ceil_div(rows, 8);
-  if (gy > max_gy) gy = max_gy;
-  grid.y = static_cast<unsigned>(gy < 1 ? 1 : gy);
+  const int parts = reduction_parts(rows, C);
+  dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), static_cast<unsigned>(parts));
   bn_stats_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, rows, C, ldx, stats);
-  return launched("bn_stats");
+  int rc = launched("bn_stats");
+  if (rc) return rc;
+  sum_partials_kernel<<<static_cast<unsigned>(ceil_div(2 * C, 256)), 256, 0, STREAM(stream)>>>(stats, 2 * C,
+                                                                                             parts);
+  return launched("bn_stats/sum");
+}
+
+extern "C" int64_t cpcsv_bn_workspace_doubles(int64_t rows, int32_t C) {
+  return static_cast<int64_t>(2 * C) * (1 + reduction_parts(rows, C));
 }
 
 extern "C" int cpcsv_bn_finalize(const double* stats, int64_t rows, int32_t C, const float* gamma,
@@ -764,15 +789,15 @@ extern "C" int cpcsv_bn_bwd_reduce(const float* x, const float* dy, int64_t rows
   CPCSV_REQUIRE(x && dy && sums && mean && invstd && rows > 0 && C > 0 && C % 4 == 0 &&
                     ldx % 4 == 0 && lddy % 4 == 0,
                 "bn_bwd_reduce: args");
-  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, STREAM(stream));
-  dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), 1);
-  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 8, grid.x);
-  const int64_t max_gy = ceil_div(rows, 8);
-  if (gy > max_gy) gy = max_gy;
-  grid.y = static_cast<unsigned>(gy < 1 ? 1 : gy);
+  const int parts = reduction_parts(rows, C);
+  dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), static_cast<unsigned>(parts));
   bn_bwd_reduce_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, dy, rows, C, ldx, lddy, scale, shift, mean,
                                                          invstd, act, mod, ldmod, sums);
-  return launched("bn_bwd_reduce");
+  int rc = launched("bn_bwd_reduce");
+  if (rc) return rc;
+  sum_partials_kernel<<<static_cast<unsigned>(ceil_div(2 * C, 256)), 256, 0, STREAM(stream)>>>(sums, 2 * C,
+                                                                                             parts);
+  return launched("bn_bwd_reduce/sum");
 }
 
 extern "C" int cpcsv_bn_bwd_apply(const float* x, const float* dy, int64_t rows, int32_t C,

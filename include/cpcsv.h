@@ -94,7 +94,11 @@ int cpcsv_conv_gemm(const cpcsv_gemm_t* job, cpcsv_stream_t stream);
  * 252-263, 503-513; semantics SURVEY.md Appendix A) on fp32 [rows, C] conv outputs, fused
  * with the split into bf16 hi/lo operand planes for the next tcgen05 GEMM.
  */
-/* per-channel sum and sum of squares: stats[0..C) += sum, stats[C..2C) += sumsq (fp64) */
+/* per-channel sum and sum of squares (fp64): stats[0..C) = sum, stats[C..2C) = sumsq.
+ * `stats` (and `sums` of cpcsv_bn_bwd_reduce) must hold cpcsv_bn_workspace_doubles(rows, C)
+ * doubles: the first 2C are the result, the rest per-block partials (two-stage reduction, no
+ * atomics). */
+int64_t cpcsv_bn_workspace_doubles(int64_t rows, int32_t C);
 int cpcsv_bn_stats(const float* x, int64_t rows, int32_t C, int64_t ldx, double* stats,
                    cpcsv_stream_t stream);
 /* mean/invstd, running-stat update (momentum 0.1, unbiased var), scale/shift.

@@ -152,6 +152,10 @@ def _split16(v, dtype):
     return hi, lo
 
 
+def bn_workspace(rows, channels, device):
+    return torch.empty(2 * channels, device=device, dtype=torch.float64)
+
+
 def bn_stats(x, stats):
     Cc = x.shape[1]
     xd = x.double()
