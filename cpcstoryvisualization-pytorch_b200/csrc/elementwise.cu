@@ -735,6 +735,7 @@ using namespace cpcsv;
 
 #define STREAM(s) static_cast<cudaStream_t>(s)
 
+#if 0  // the BatchNorm entry points moved to bn.cu (register-resident per-channel constants)
 extern "C" int cpcsv_bn_stats(const float* x, int64_t rows, int32_t C, int64_t ldx, double* stats,
                               cpcsv_stream_t stream) {
   CPCSV_REQUIRE(x && stats && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_stats: args");
@@ -819,6 +820,8 @@ extern "C" int cpcsv_bn_bwd_apply(const float* x, const float* dy, int64_t rows,
       static_cast<uint16_t*>(dmod16), lddmod16, dgamma, dbeta);
   return launched("bn_bwd_apply");
 }
+
+#endif
 
 extern "C" int cpcsv_pack_nchw(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t sn,
                                int64_t sc, int64_t sh, int64_t sw, const float* bcast, int32_t Cb,
