@@ -240,7 +240,7 @@ def bn_bwd_apply(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod,
         dmod.copy_(dy * a)
     if dmod16 is not None:
         dmod16.copy_((dy * a).to(torch.bfloat16))
-    if dgamma is not None:
+    if dgamma is not None and has_bn:
         idx = chan_map.long()[:c_valid] if chan_map is not None else torch.arange(c_valid)
         ok = idx >= 0
         dgamma[idx[ok]] = sums[Cc:Cc + c_valid].float()[ok]
