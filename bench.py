@@ -206,17 +206,50 @@ class StepEngine:
         out = self.trainer.train_step(self.nets, self.opts, x, self.labels, 1.0, self.grad_sync)
         self.loss_dev.copy_(torch.stack([out[k].reshape(()) for k in self.loss_keys]))
 
+    # --- the step in three segments, with the NCCL gradient exchange between them ------------
+    def _seg_d(self):
+        self._x = self.trainer.prepare_inputs(self.dev_st, self.dev_im)
+        self._out = self.trainer.stage_discriminators(self.nets, self._x, self.labels)
+
+    def _seg_g(self):
+        for k in self.trainer.D_NETS:
+            self.opts[k].step()
+        self._out.update(self.trainer.stage_generator(self.nets, self._x, self.labels, 1.0))
+
+    def _seg_opt(self):
+        self.opts["G"].step()
+        self.loss_dev.copy_(torch.stack([self._out[k].reshape(()) for k in self.loss_keys]))
+
     def capture(self):
+        """Single-GPU: the whole step is ONE CUDA graph.  Multi-GPU: three graphs with the two
+        NCCL all-reduces issued eagerly between them (collectives are kept out of the capture)."""
         self.knets.invalidate_weight_cache()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._step_body()
+        if self.grad_sync is None:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step_body()
+            return
+        self.graphs = []
+        pool = None
+        for seg in (self._seg_d, self._seg_g, self._seg_opt):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                seg()
+            pool = g.pool()
+            self.graphs.append(g)
+        self.graph = True
 
     def step(self):
-        if self.graph is not None:
+        if self.graph is None:
+            self._step_body()
+        elif self.grad_sync is None:
             self.graph.replay()
         else:
-            self._step_body()
+            self.graphs[0].replay()
+            self.trainer.sync_grads(self.nets, self.trainer.D_NETS, self.grad_sync)
+            self.graphs[1].replay()
+            self.trainer.sync_grads(self.nets, ("G",), self.grad_sync)
+            self.graphs[2].replay()
 
     def upload(self):
         for k, v in self.host_st.items():
@@ -272,6 +305,8 @@ def main():
     ap.add_argument("--impl", default="cpcsv_b200")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--segmented", action="store_true",
+                    help="single GPU: use the three-graph multi-GPU step structure (for testing)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -291,6 +326,8 @@ def main():
     p = preset_dict()
     import trainer
     grad_sync = trainer.GradSync() if world > 1 else None
+    if args.segmented and world == 1:
+        grad_sync = trainer.GradSync(enabled=False)
     eng = StepEngine(p, device, use_graph=not args.no_graph, grad_sync=grad_sync)
 
     # warm-up (eager: builds caches, sets kernel attributes), then capture

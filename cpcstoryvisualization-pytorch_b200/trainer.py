@@ -103,10 +103,14 @@ def _cond_vectors(x, c_mu, cim_mu):
     return st_mu, im_mu
 
 
-def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=True, skip_d_wgrad=True):
-    """One iteration of the reference's hot loop (trainer.py:290-416).  ``x`` from
-    ``prepare_inputs`` (device tensors), ``labels`` = (im_ones, im_zeros, st_ones, st_zeros).
-    Returns a dict of loss tensors (no host sync)."""
+D_NETS = ("D_se", "D_im", "D_st")
+
+
+def stage_discriminators(nets, x, labels):
+    """reference trainer.py:290-343 minus the optimiser steps: no-grad fakes, the three
+    discriminator losses and their backward passes.  The three discriminators are independent
+    networks, so running all backward passes before any of their Adam steps (instead of the
+    reference's se.step() between se.backward() and im.backward()) gives identical results."""
     netG, netD_im, netD_st, netD_se = nets["G"], nets["D_im"], nets["D_st"], nets["D_se"]
     im_ones, im_zeros, st_ones, st_zeros = labels
     gpus = None
@@ -127,20 +131,19 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
     st_errD, *_rest = compute_discriminator_loss(netD_st, x["st_real"], st_fake, st_ones, st_zeros,
                                                  x["st_labels"], st_mu, gpus)
     se_errD.backward()
-    if grad_sync:
-        grad_sync(list(netD_se.parameters()))
-    if apply_optim:
-        opts["D_se"].step()
     im_errD.backward()
     st_errD.backward()
-    if grad_sync:
-        grad_sync(list(netD_im.parameters()))
-        grad_sync(list(netD_st.parameters()))
-    if apply_optim:
-        opts["D_im"].step()
-        opts["D_st"].step()
     out.update(se_errD=se_errD.detach(), im_errD=im_errD.detach(), st_errD=st_errD.detach())
-    # (4) generator
+    return out
+
+
+def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True):
+    """reference trainer.py:365-415: generator forward with fresh noise, the three adversarial
+    losses + KL terms, backward."""
+    netG, netD_im, netD_st, netD_se = nets["G"], nets["D_im"], nets["D_st"], nets["D_se"]
+    im_ones, im_zeros, st_ones, st_zeros = labels
+    gpus = None
+    out = {}
     netG.zero_grad(set_to_none=True)
     if skip_d_wgrad:
         for k in ("D_im", "D_st", "D_se"):
@@ -163,13 +166,32 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
         if skip_d_wgrad:
             for k in ("D_im", "D_st", "D_se"):
                 _set_requires_grad(nets[k], True)
-    if grad_sync:
-        grad_sync(list(netG.parameters()))
-    if apply_optim:
-        opts["G"].step()
     out.update(se_errG=se_errG.detach(), im_errG=im_errG.detach(), st_errG=st_errG.detach(),
                im_kl=im_kl.detach(), st_kl=st_kl.detach(), errG_total=total.detach())
     out["p3_st_fake"], out["p3_im_fake"], out["p3_se_fake"] = st_fake.detach(), im_fake.detach(), se_fake.detach()
+    return out
+
+
+def sync_grads(nets, names, grad_sync):
+    """the one exchange step of the data-parallel job: average gradients across ranks"""
+    if grad_sync:
+        for k in names:
+            grad_sync(list(nets[k].parameters()))
+
+
+def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=True, skip_d_wgrad=True):
+    """One iteration of the reference's hot loop (trainer.py:290-416).  ``x`` from
+    ``prepare_inputs`` (device tensors), ``labels`` = (im_ones, im_zeros, st_ones, st_zeros).
+    Returns a dict of loss tensors (no host sync)."""
+    out = stage_discriminators(nets, x, labels)
+    sync_grads(nets, D_NETS, grad_sync)
+    if apply_optim:
+        for k in D_NETS:
+            opts[k].step()
+    out.update(stage_generator(nets, x, labels, ratio, skip_d_wgrad))
+    sync_grads(nets, ("G",), grad_sync)
+    if apply_optim:
+        opts["G"].step()
     return out
 
 
