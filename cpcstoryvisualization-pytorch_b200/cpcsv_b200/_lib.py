@@ -47,6 +47,10 @@ SIGNATURES = {
     "cpcsv_bn_bwd_reduce": [_p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _i32, _p, _i64, _p, _p],
     "cpcsv_bn_bwd_apply": [_p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _i64,
                            _p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p],
+    "cpcsv_bn_fwd_fused": [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _i32, _f32, _f32, _i32, _p, _i64, _p, _i64,
+                           _p, _p, _i64, _i32, _p, _p, _p],
+    "cpcsv_bn_bwd_fused": [_p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p, _p,
+                           _i64, _p, _i64, _p, _p, _p],
     "cpcsv_pack_nchw": [_p, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _p, _i32, _i64, _p, _p,
                         _i32, _i32, _p],
     "cpcsv_im2col_small": [_p, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p,

@@ -238,29 +238,36 @@ class BnActNode:
         t, z, out = self.tape, self.z, self.out
         dev = z.f32.device
         zm = z.mat(z.f32)
-        scale = shift = None
-        if self.bn is not None:
-            gamma, beta, rmean, rvar, nbt = self.bn
-            stats = ops.bn_workspace(z.rows, z.C, dev)
-            ops.bn_stats(zm, stats)
-            vec = _e((4, z.C), dev)
-            ops.bn_finalize(stats, z.rows, gamma.detach(), beta.detach(),
-                            rmean if t.training else None, rvar if t.training else None,
-                            self.chan_map, self.c_valid, vec[0], vec[1], vec[2], vec[3])
-            if t.training and nbt is not None:
-                t.counters.append(nbt)
-            self.stat = vec
-            scale, shift = vec[2], vec[3]
         if self.want_f32:
             out.f32 = _e((z.N, z.H, z.W, z.C), dev)
         if self.want_planes:
             t16 = ops.TORCH16[t.dtype]
             out.hi = _e((z.N, z.H, z.W, z.C), dev, t16)
             out.lo = _e((z.N, z.H, z.W, z.C), dev, t16) if t.planes == 2 else None
-        ops.bn_act_pack(zm, scale, shift, self.act, z.mat(self.mod.f32) if self.mod is not None else None,
-                        z.mat(out.f32) if out.f32 is not None else None,
-                        z.mat(out.hi) if out.hi is not None else None,
-                        z.mat(out.lo) if out.lo is not None else None, t.dtype)
+        modm = z.mat(self.mod.f32) if self.mod is not None else None
+        ym = z.mat(out.f32) if out.f32 is not None else None
+        him = z.mat(out.hi) if out.hi is not None else None
+        lom = z.mat(out.lo) if out.lo is not None else None
+        scale = shift = None
+        if self.bn is not None:
+            gamma, beta, rmean, rvar, nbt = self.bn
+            if t.training and nbt is not None:
+                t.counters.append(nbt)
+            ws = ops.bn_workspace(z.rows, z.C, dev)
+            vec = _e((4, z.C), dev)
+            self.stat = vec
+            rm, rv = (rmean, rvar) if t.training else (None, None)
+            # one cooperative launch; multi-launch path when the grid cannot be co-resident
+            if ops.bn_fwd_fused(zm, gamma.detach(), beta.detach(), rm, rv, self.chan_map, self.c_valid,
+                                self.act, modm, ym, him, lom, t.dtype, ws, vec):
+                if not t.need_grad and self.mod is None:
+                    z.f32 = None
+                return
+            ops.bn_stats(zm, ws)
+            ops.bn_finalize(ws, z.rows, gamma.detach(), beta.detach(), rm, rv, self.chan_map, self.c_valid,
+                            vec[0], vec[1], vec[2], vec[3])
+            scale, shift = vec[2], vec[3]
+        ops.bn_act_pack(zm, scale, shift, self.act, modm, ym, him, lom, t.dtype)
         if not t.need_grad and self.mod is None:
             z.f32 = None        # nothing reads the raw conv output again: release it early
 
@@ -272,25 +279,29 @@ class BnActNode:
         zm, dym = z.mat(z.f32), z.mat(dy)
         has_bn = self.bn is not None
         modm = z.mat(self.mod.f32) if self.mod is not None else None
-        sums = None
-        if has_bn:
-            vec = self.stat
-            sums = ops.bn_workspace(z.rows, z.C, dev)
-            ops.bn_bwd_reduce(zm, dym, vec[2], vec[3], vec[0], vec[1], self.act, modm, sums)
-            if need_param_grad:
-                # every entry is written by bn_bwd_apply (all real channels are mapped)
-                self.dgamma = torch.empty_like(self.bn[0])
-                self.dbeta = torch.empty_like(self.bn[1])
         z.grad16 = _e((z.N, z.H, z.W, z.C), dev, torch.bfloat16)
         dmod16 = None
         if self.mod is not None:
             m = self.mod
             dmod16 = _e((m.N, m.H, m.W, m.C), dev, torch.bfloat16)
             m.grad16 = dmod16
+        dmod16m = z.mat(dmod16) if dmod16 is not None else None
+        sums = None
+        if has_bn:
+            vec = self.stat
+            sums = ops.bn_workspace(z.rows, z.C, dev)
+            if need_param_grad:
+                # every entry is written by the apply stage (all real channels are mapped)
+                self.dgamma = torch.empty_like(self.bn[0])
+                self.dbeta = torch.empty_like(self.bn[1])
+            if ops.bn_bwd_fused(zm, dym, vec[2], vec[3], vec[0], vec[1], self.chan_map, self.c_valid,
+                                self.act, modm, sums, z.mat(z.grad16), dmod16m, self.dgamma, self.dbeta):
+                out.grad = None
+                return
+            ops.bn_bwd_reduce(zm, dym, vec[2], vec[3], vec[0], vec[1], self.act, modm, sums)
         vec = self.stat if has_bn else (None, None, None, None)
         ops.bn_bwd_apply(zm, dym, vec[2], vec[3], vec[0], vec[1], self.chan_map, self.c_valid, self.act,
-                         modm, sums, has_bn, dx=None, dx16=z.mat(z.grad16), dmod=None,
-                         dmod16=z.mat(dmod16) if dmod16 is not None else None,
+                         modm, sums, has_bn, dx=None, dx16=z.mat(z.grad16), dmod=None, dmod16=dmod16m,
                          dgamma=self.dgamma, dbeta=self.dbeta)
         out.grad = None
 

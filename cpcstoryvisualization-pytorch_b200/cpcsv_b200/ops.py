@@ -180,6 +180,37 @@ def bn_bwd_apply(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod,
         _ptr(dgamma), _ptr(dbeta), _stream()), "cpcsv_bn_bwd_apply")
 
 
+def bn_fwd_fused(x, gamma, beta, running_mean, running_var, chan_map, c_valid, act, mod, y, hi, lo, dtype,
+                 ws, vec, eps=1e-5, momentum=0.1):
+    """stats + finalize + apply in one cooperative launch; False if the grid cannot be co-resident
+    (caller falls back to bn_stats / bn_finalize / bn_act_pack)."""
+    rows, Cc, ld = _rows2d(x)
+    rc = _lib.load().cpcsv_bn_fwd_fused(
+        _ptr(x, torch.float32), rows, Cc, ld, _ptr(gamma, torch.float32), _ptr(beta, torch.float32),
+        _ptr(running_mean), _ptr(running_var), _ptr(chan_map, torch.int32), c_valid, eps, momentum, act,
+        _ptr(mod), mod.stride(0) if mod is not None else 0, _ptr(y), y.stride(0) if y is not None else 0,
+        _ptr(hi), _ptr(lo), hi.stride(0) if hi is not None else 0, dtype, _ptr(ws, torch.float64),
+        _ptr(vec, torch.float32), _stream())
+    if rc == -4:
+        return False
+    _lib.check(rc, "cpcsv_bn_fwd_fused")
+    return True
+
+
+def bn_bwd_fused(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod, ws, dx16, dmod16, dgamma,
+                 dbeta):
+    rows, Cc, ld = _rows2d(x)
+    rc = _lib.load().cpcsv_bn_bwd_fused(
+        _ptr(x, torch.float32), _ptr(dy, torch.float32), rows, Cc, ld, dy.stride(0), _ptr(scale), _ptr(shift),
+        _ptr(mean), _ptr(invstd), _ptr(chan_map, torch.int32), c_valid, act, _ptr(mod),
+        mod.stride(0) if mod is not None else 0, _ptr(ws, torch.float64), _ptr(dx16), dx16.stride(0),
+        _ptr(dmod16), dmod16.stride(0) if dmod16 is not None else 0, _ptr(dgamma), _ptr(dbeta), _stream())
+    if rc == -4:
+        return False
+    _lib.check(rc, "cpcsv_bn_bwd_fused")
+    return True
+
+
 # ------------------------------------------------------------------ layout kernels
 def pack_nchw(x, bcast, hi, lo, cpad, dtype=BF16):
     N, Cc, H, W = x.shape

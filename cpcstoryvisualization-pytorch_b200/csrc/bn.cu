@@ -7,6 +7,7 @@
 // stores.  Thread block = `qpb` quads x (256 / qpb) row lanes; grid.x walks the channel quads,
 // grid.y the rows.  Reductions are two-stage (per-block partials, then a small tree kernel):
 // hundreds of blocks doing fp64 atomics on 2C addresses serialise in L2.
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -357,6 +358,262 @@ bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, int6
   }
 }
 
+// ------------------------------------------------------------------------- fused (cooperative)
+// One launch per BatchNorm layer instead of four / three: partial sums -> grid.sync -> tree sum by
+// the first row of blocks -> grid.sync -> per-channel constants -> streaming apply.  At the
+// cfg/final.yml batch most layers are a few MB, so the launch count (not bytes) is what costs.
+__device__ __forceinline__ void grid_sync() { cooperative_groups::this_grid().sync(); }
+
+// every block of channel-block blockIdx.x sums the per-row-block partials of its quads: only the
+// blocks with blockIdx.y == 0 do it and publish the totals in ws[0 .. 2C)
+__device__ __forceinline__ void sum_partials_block(double* __restrict__ ws, int C, int c, int ql, int rl,
+                                                   int qpb, int rpb, int parts, double (*sh)[8]) {
+  double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < C) {
+    for (int p = rl; p < parts; p += rpb) {
+      const double* part = ws + static_cast<int64_t>(2 * C) * (1 + p);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        t[j] += part[c + j];
+        t[4 + j] += part[C + c + j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = t[j];
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double a = 0;
+      for (int k = 0; k < rpb; ++k) a += sh[k * qpb + ql][j];
+      if (j < 4) ws[c + j] = a;
+      else ws[C + c + (j - 4)] = a;
+    }
+  }
+}
+
+template <bool kMod, bool kY, bool kHi, bool kLo>
+__global__ void __launch_bounds__(256)
+bn_fwd_fused_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* running_mean, float* running_var, const int32_t* __restrict__ chan_map,
+                    int C_valid, float eps, float momentum, int act, const float* __restrict__ mod,
+                    int64_t ldmod, float* __restrict__ y, int64_t ldy, uint16_t* __restrict__ hi,
+                    uint16_t* __restrict__ lo, int64_t ldp, int dtype, double* __restrict__ ws,
+                    float* __restrict__ vec, int qpb, int rpb) {
+  const int ql = threadIdx.x % qpb, rl = threadIdx.x / qpb;
+  const int c = (blockIdx.x * qpb + ql) * 4;
+  const int64_t step = static_cast<int64_t>(gridDim.y) * rpb;
+  __shared__ double sh[256][8];
+  // --- phase A: per-block partial sums
+  {
+    double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    if (c < C) {
+      int64_t r = static_cast<int64_t>(blockIdx.y) * rpb + rl;
+      for (; r + step < rows; r += 2 * step) {
+        const float4 v0 = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        const float4 v1 = *reinterpret_cast<const float4*>(x + (r + step) * ldx + c);
+        s[0] += static_cast<double>(v0.x) + v1.x; ss[0] += static_cast<double>(v0.x) * v0.x + static_cast<double>(v1.x) * v1.x;
+        s[1] += static_cast<double>(v0.y) + v1.y; ss[1] += static_cast<double>(v0.y) * v0.y + static_cast<double>(v1.y) * v1.y;
+        s[2] += static_cast<double>(v0.z) + v1.z; ss[2] += static_cast<double>(v0.z) * v0.z + static_cast<double>(v1.z) * v1.z;
+        s[3] += static_cast<double>(v0.w) + v1.w; ss[3] += static_cast<double>(v0.w) * v0.w + static_cast<double>(v1.w) * v1.w;
+      }
+      for (; r < rows; r += step) {
+        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        s[0] += v.x; ss[0] += static_cast<double>(v.x) * v.x;
+        s[1] += v.y; ss[1] += static_cast<double>(v.y) * v.y;
+        s[2] += v.z; ss[2] += static_cast<double>(v.z) * v.z;
+        s[3] += v.w; ss[3] += static_cast<double>(v.w) * v.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sh[threadIdx.x][j] = s[j];
+      sh[threadIdx.x][4 + j] = ss[j];
+    }
+    __syncthreads();
+    if (rl == 0 && c < C) {
+      double* part = ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double t = 0;
+        for (int k = 0; k < rpb; ++k) t += sh[k * qpb + ql][j];
+        if (j < 4) part[c + j] = t;
+        else part[C + c + (j - 4)] = t;
+      }
+    }
+  }
+  __threadfence();
+  grid_sync();
+  // --- phase B: tree sum + finalize by the first row of blocks
+  if (blockIdx.y == 0) {
+    __syncthreads();
+    sum_partials_block(ws, C, c, ql, rl, qpb, rpb, static_cast<int>(gridDim.y), sh);
+    if (rl == 0 && c < C) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cc = c + j;
+        float m_ = 0.f, is_ = 0.f, sc_ = 0.f, sf_ = 0.f;
+        const int p = chan_map ? chan_map[cc] : cc;
+        if (cc < C_valid && p >= 0) {
+          const double n = static_cast<double>(rows);
+          const double m = ws[cc] / n;
+          double var = ws[C + cc] / n - m * m;
+          if (var < 0) var = 0;
+          is_ = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+          m_ = static_cast<float>(m);
+          sc_ = gamma[p] * is_;
+          sf_ = beta[p] - m_ * sc_;
+          if (running_mean) {
+            const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+            running_mean[p] = (1.f - momentum) * running_mean[p] + momentum * m_;
+            running_var[p] = (1.f - momentum) * running_var[p] + momentum * static_cast<float>(unbiased);
+          }
+        }
+        vec[cc] = m_; vec[C + cc] = is_; vec[2 * C + cc] = sc_; vec[3 * C + cc] = sf_;
+      }
+    }
+  }
+  __threadfence();
+  grid_sync();
+  // --- phase C: apply + activation (+ modulation) + operand split
+  if (c >= C) return;
+  float sc[4], sf[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sc[j] = __ldcg(vec + 2 * C + c + j); sf[j] = __ldcg(vec + 3 * C + c + j); }
+  for (int64_t r = static_cast<int64_t>(blockIdx.y) * rpb + rl; r < rows; r += step) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    float v[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = apply_act(fmaf(v[j], sc[j], sf[j]), act);
+    if (kMod) {
+      const float4 mv = *reinterpret_cast<const float4*>(mod + r * ldmod + c);
+      v[0] *= 1.f + mv.x; v[1] *= 1.f + mv.y; v[2] *= 1.f + mv.z; v[3] *= 1.f + mv.w;
+    }
+    if (kY) *reinterpret_cast<float4*>(y + r * ldy + c) = make_float4(v[0], v[1], v[2], v[3]);
+    if (kHi) {
+      uint2 hv;
+      hv.x = pack2(v[0], v[1], dtype);
+      hv.y = pack2(v[2], v[3], dtype);
+      *reinterpret_cast<uint2*>(hi + r * ldp + c) = hv;
+      if (kLo) {
+        uint2 lv;
+        lv.x = pack2(v[0] - round16(v[0], dtype), v[1] - round16(v[1], dtype), dtype);
+        lv.y = pack2(v[2] - round16(v[2], dtype), v[3] - round16(v[3], dtype), dtype);
+        *reinterpret_cast<uint2*>(lo + r * ldp + c) = lv;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t rows, int C,
+                    int64_t ldx, int64_t lddy, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const int32_t* __restrict__ chan_map, int C_valid,
+                    int act, const float* __restrict__ mod, int64_t ldmod, double* __restrict__ ws,
+                    uint16_t* __restrict__ dx16, int64_t ld16, uint16_t* __restrict__ dmod16,
+                    int64_t lddmod16, float* __restrict__ dgamma, float* __restrict__ dbeta, int qpb,
+                    int rpb) {
+  const int ql = threadIdx.x % qpb, rl = threadIdx.x / qpb;
+  const int c = (blockIdx.x * qpb + ql) * 4;
+  const int64_t step = static_cast<int64_t>(gridDim.y) * rpb;
+  __shared__ double sh[256][8];
+  ChanConst k;
+  if (c < C) k = load_const(scale, shift, mean, invstd, c);
+  {
+    double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
+    if (c < C) {
+      for (int64_t r = static_cast<int64_t>(blockIdx.y) * rpb + rl; r < rows; r += step) {
+        float g0[4], h0[4], a0[4], d0[4];
+        bwd_row(x, dy, mod, r, c, ldx, lddy, ldmod, k, act, g0, h0, a0, d0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[j] += g0[j];
+          sx[j] += static_cast<double>(g0[j]) * h0[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sh[threadIdx.x][j] = s[j];
+      sh[threadIdx.x][4 + j] = sx[j];
+    }
+    __syncthreads();
+    if (rl == 0 && c < C) {
+      double* part = ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double t = 0;
+        for (int kk = 0; kk < rpb; ++kk) t += sh[kk * qpb + ql][j];
+        if (j < 4) part[c + j] = t;
+        else part[C + c + (j - 4)] = t;
+      }
+    }
+  }
+  __threadfence();
+  grid_sync();
+  if (blockIdx.y == 0) {
+    __syncthreads();
+    sum_partials_block(ws, C, c, ql, rl, qpb, rpb, static_cast<int>(gridDim.y), sh);
+  }
+  __threadfence();
+  grid_sync();
+  if (c >= C) return;
+  float mg[4], mgx[4];
+  const float inv_rows = 1.f / static_cast<float>(rows);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mg[j] = static_cast<float>(__ldcg(ws + c + j)) * inv_rows;
+    mgx[j] = static_cast<float>(__ldcg(ws + C + c + j)) * inv_rows;
+  }
+  if (dgamma && blockIdx.y == 0 && rl == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (c + j < C_valid) {
+        const int p = chan_map ? chan_map[c + j] : c + j;
+        if (p >= 0) {
+          dgamma[p] = static_cast<float>(__ldcg(ws + C + c + j));
+          dbeta[p] = static_cast<float>(__ldcg(ws + c + j));
+        }
+      }
+    }
+  }
+  for (int64_t r = static_cast<int64_t>(blockIdx.y) * rpb + rl; r < rows; r += step) {
+    float g[4], xhat[4], a[4], dv[4];
+    bwd_row(x, dy, mod, r, c, ldx, lddy, ldmod, k, act, g, xhat, a, dv);
+    uint2 v;
+    v.x = pack2(k.sc[0] * (g[0] - mg[0] - xhat[0] * mgx[0]), k.sc[1] * (g[1] - mg[1] - xhat[1] * mgx[1]), 1);
+    v.y = pack2(k.sc[2] * (g[2] - mg[2] - xhat[2] * mgx[2]), k.sc[3] * (g[3] - mg[3] - xhat[3] * mgx[3]), 1);
+    *reinterpret_cast<uint2*>(dx16 + r * ld16 + c) = v;
+    if (dmod16) {
+      uint2 m;
+      m.x = pack2(dv[0] * a[0], dv[1] * a[1], 1);
+      m.y = pack2(dv[2] * a[2], dv[3] * a[3], 1);
+      *reinterpret_cast<uint2*>(dmod16 + r * lddmod16 + c) = m;
+    }
+  }
+}
+
+// co-resident grid for a cooperative launch
+template <typename K>
+inline Tiling coop_tiling(K kernel, int64_t rows, int C) {
+  static int per_sm = 0;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0);
+  if (occ < 1) occ = 1;
+  per_sm = occ > 4 ? 4 : occ;
+  Tiling t = make_tiling(rows, C, per_sm);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
+  if (static_cast<int64_t>(t.grid.x) * t.grid.y > cap) {
+    int64_t gy = cap / t.grid.x;
+    if (gy < 1) gy = 1;
+    t.grid.y = static_cast<unsigned>(gy);
+  }
+  return t;
+}
+
 }  // namespace
 }  // namespace cpcsv
 
@@ -462,4 +719,83 @@ extern "C" int cpcsv_bn_bwd_apply(const float* x, const float* dy, int64_t rows,
       has_bn, dx, lddx, static_cast<uint16_t*>(dx16), ld16, dmod, lddmod, static_cast<uint16_t*>(dmod16),
       lddmod16, dgamma, dbeta, t.qpb, t.rpb);
   return launched("bn_bwd_apply");
+}
+
+// Fused forward: statistics + finalize (+ running stats) + apply/activation/modulation/split in
+// ONE cooperative launch.  vec = [mean | invstd | scale | shift] (4*C floats), ws as for bn_stats.
+// Returns -4 (nothing enqueued) when the problem cannot be made co-resident; callers then use the
+// unfused entry points.
+extern "C" int cpcsv_bn_fwd_fused(const float* x, int64_t rows, int32_t C, int64_t ldx,
+                                  const float* gamma, const float* beta, float* running_mean,
+                                  float* running_var, const int32_t* chan_map, int32_t C_valid,
+                                  float eps, float momentum, int32_t act, const float* mod,
+                                  int64_t ldmod, float* y, int64_t ldy, void* hi, void* lo,
+                                  int64_t ldp, int32_t dtype, double* ws, float* vec,
+                                  cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(x && gamma && beta && ws && vec && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 &&
+                    C_valid <= C,
+                "bn_fwd_fused: args");
+  CPCSV_REQUIRE((!mod || ldmod % 4 == 0) && (!y || ldy % 4 == 0) && (!hi || ldp % 4 == 0) && (hi || y) &&
+                    (!lo || hi),
+                "bn_fwd_fused: outputs");
+  uint16_t* h = static_cast<uint16_t*>(hi);
+  uint16_t* l = static_cast<uint16_t*>(lo);
+  int qpb = 0, rpb = 0;
+  void* args[] = {&x, &rows, &C, &ldx, &gamma, &beta, &running_mean, &running_var, &chan_map, &C_valid,
+                  &eps, &momentum, &act, &mod, &ldmod, &y, &ldy, &h, &l, &ldp, &dtype, &ws, &vec, &qpb,
+                  &rpb};
+  const void* fn = nullptr;
+  Tiling t;
+#define PICK(M, Y, H, L)                                              \
+  {                                                                   \
+    fn = reinterpret_cast<const void*>(bn_fwd_fused_kernel<M, Y, H, L>); \
+    t = coop_tiling(bn_fwd_fused_kernel<M, Y, H, L>, rows, C);         \
+  }
+  const int key = (mod ? 8 : 0) | (y ? 4 : 0) | (hi ? 2 : 0) | (lo ? 1 : 0);
+  switch (key) {
+    case 2: PICK(false, false, true, false) break;
+    case 3: PICK(false, false, true, true) break;
+    case 4: PICK(false, true, false, false) break;
+    case 6: PICK(false, true, true, false) break;
+    case 7: PICK(false, true, true, true) break;
+    case 10: PICK(true, false, true, false) break;
+    case 11: PICK(true, false, true, true) break;
+    case 12: PICK(true, true, false, false) break;
+    case 14: PICK(true, true, true, false) break;
+    case 15: PICK(true, true, true, true) break;
+    default: return fail(-1, "bn_fwd_fused: unsupported output combination %d", key);
+  }
+#undef PICK
+  if (static_cast<int64_t>(t.grid.x) * t.grid.y > static_cast<int64_t>(num_sms()) * 4)
+    return fail(-4, "bn_fwd_fused: %u x %u blocks cannot be co-resident", t.grid.x, t.grid.y);
+  qpb = t.qpb;
+  rpb = t.rpb;
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, t.grid, dim3(256), args, 0, STREAM(stream));
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "bn_fwd_fused: %s", cudaGetErrorString(e));
+  return launched("bn_fwd_fused");
+}
+
+// Fused backward: reduction + tree sum + apply in one cooperative launch (bf16 outputs only).
+extern "C" int cpcsv_bn_bwd_fused(const float* x, const float* dy, int64_t rows, int32_t C,
+                                  int64_t ldx, int64_t lddy, const float* scale, const float* shift,
+                                  const float* mean, const float* invstd, const int32_t* chan_map,
+                                  int32_t C_valid, int32_t act, const float* mod, int64_t ldmod,
+                                  double* ws, void* dx16, int64_t ld16, void* dmod16,
+                                  int64_t lddmod16, float* dgamma, float* dbeta,
+                                  cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(x && dy && scale && shift && mean && invstd && ws && dx16 && rows > 0 && C > 0 &&
+                    C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && ld16 % 4 == 0,
+                "bn_bwd_fused: args");
+  const Tiling t = coop_tiling(bn_bwd_fused_kernel, rows, C);
+  if (static_cast<int64_t>(t.grid.x) * t.grid.y > static_cast<int64_t>(num_sms()) * 4)
+    return fail(-4, "bn_bwd_fused: %u x %u blocks cannot be co-resident", t.grid.x, t.grid.y);
+  uint16_t* d16 = static_cast<uint16_t*>(dx16);
+  uint16_t* m16 = static_cast<uint16_t*>(dmod16);
+  int qpb = t.qpb, rpb = t.rpb;
+  void* args[] = {&x, &dy, &rows, &C, &ldx, &lddy, &scale, &shift, &mean, &invstd, &chan_map, &C_valid,
+                  &act, &mod, &ldmod, &ws, &d16, &ld16, &m16, &lddmod16, &dgamma, &dbeta, &qpb, &rpb};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(bn_bwd_fused_kernel), t.grid,
+                                              dim3(256), args, 0, STREAM(stream));
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "bn_bwd_fused: %s", cudaGetErrorString(e));
+  return launched("bn_bwd_fused");
 }

@@ -131,6 +131,24 @@ int cpcsv_bn_bwd_apply(const float* x, const float* dy, int64_t rows, int32_t C,
                        int64_t ld16, float* dmod, int64_t lddmod, void* dmod16, int64_t lddmod16,
                        float* dgamma, float* dbeta, cpcsv_stream_t stream);
 
+/* Single-launch (cooperative, grid-synchronised) forms of the two sequences above -- at the
+ * cfg/final.yml batch most BatchNorm layers are a few MB and launch count dominates:
+ *   fwd:  bn_stats + bn_finalize + bn_act_pack   (vec = [mean | invstd | scale | shift], 4*C floats)
+ *   bwd:  bn_bwd_reduce + bn_bwd_apply           (16-bit outputs)
+ * They return -4 without enqueueing anything when the grid cannot be made co-resident; the caller
+ * then uses the multi-launch entry points. */
+int cpcsv_bn_fwd_fused(const float* x, int64_t rows, int32_t C, int64_t ldx, const float* gamma,
+                       const float* beta, float* running_mean, float* running_var,
+                       const int32_t* chan_map, int32_t C_valid, float eps, float momentum, int32_t act,
+                       const float* mod, int64_t ldmod, float* y, int64_t ldy, void* hi, void* lo,
+                       int64_t ldp, int32_t dtype, double* ws, float* vec, cpcsv_stream_t stream);
+int cpcsv_bn_bwd_fused(const float* x, const float* dy, int64_t rows, int32_t C, int64_t ldx,
+                       int64_t lddy, const float* scale, const float* shift, const float* mean,
+                       const float* invstd, const int32_t* chan_map, int32_t C_valid, int32_t act,
+                       const float* mod, int64_t ldmod, double* ws, void* dx16, int64_t ld16,
+                       void* dmod16, int64_t lddmod16, float* dgamma, float* dbeta,
+                       cpcsv_stream_t stream);
+
 /* ------------------------------------------------------------------- layout / pack kernels */
 /* fp32 strided (n, c, h, w) -> NHWC 16-bit hi/lo planes with channel pitch ldp; channels
  * c >= C are zero-filled up to Cpad.  `bcast` (optional, [n, Cb]) is appended after the C

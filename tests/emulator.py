@@ -247,6 +247,27 @@ def bn_bwd_apply(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod,
         dbeta[idx[ok]] = sums[:c_valid].float()[ok]
 
 
+def bn_fwd_fused(x, gamma, beta, running_mean, running_var, chan_map, c_valid, act, mod, y, hi, lo, dtype,
+                 ws, vec, eps=1e-5, momentum=0.1):
+    Cc = x.shape[1]
+    stats = torch.zeros(2 * Cc, dtype=torch.float64)
+    bn_stats(x, stats)
+    bn_finalize(stats, x.shape[0], gamma, beta, running_mean, running_var, chan_map, c_valid,
+                vec[0], vec[1], vec[2], vec[3], eps, momentum)
+    bn_act_pack(x, vec[2], vec[3], act, mod, y, hi, lo, dtype)
+    return True
+
+
+def bn_bwd_fused(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod, ws, dx16, dmod16, dgamma,
+                 dbeta):
+    Cc = x.shape[1]
+    sums = torch.zeros(2 * Cc, dtype=torch.float64)
+    bn_bwd_reduce(x, dy, scale, shift, mean, invstd, act, mod, sums)
+    bn_bwd_apply(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod, sums, True,
+                 dx16=dx16, dmod16=dmod16, dgamma=dgamma, dbeta=dbeta)
+    return True
+
+
 # ------------------------------------------------------------------------------ layout kernels
 def pack_nchw(x, bcast, hi, lo, cpad, dtype=1):
     N, Cc, H, W = x.shape

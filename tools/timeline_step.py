@@ -32,7 +32,8 @@ if __name__ == "__main__":
         if "sleep" in name.lower() or "spin" in name.lower():
             continue
         dur = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
-        key = name.split("(")[0].split("<")[0][-70:]
+        key = name.replace("(anonymous namespace)::", "").replace("void ", "")
+        key = key.split("(")[0].split("<")[0][-70:]
         agg[key][0] += 1
         agg[key][1] += dur
         st = ev.time_range.start
