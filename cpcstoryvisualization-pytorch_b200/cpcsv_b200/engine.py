@@ -13,6 +13,9 @@ from . import conv, ops
 from .ops import ACT_NONE, ACT_RELU, ACT_LRELU, BF16  # noqa: F401
 
 
+FUSED_BN_MAX_ELEMS = 6 * 1024 * 1024   # rows * C up to which BatchNorm runs as one cooperative launch
+
+
 def rup(x, m):
     return (x + m - 1) // m * m
 
@@ -257,9 +260,11 @@ class BnActNode:
             vec = _e((4, z.C), dev)
             self.stat = vec
             rm, rv = (rmean, rvar) if t.training else (None, None)
-            # one cooperative launch; multi-launch path when the grid cannot be co-resident
-            if ops.bn_fwd_fused(zm, gamma.detach(), beta.detach(), rm, rv, self.chan_map, self.c_valid,
-                                self.act, modm, ym, him, lom, t.dtype, ws, vec):
+            # small layers: one cooperative launch (launch count dominates); large layers: the
+            # multi-launch path, whose reductions use the whole chip
+            if z.rows * z.C <= FUSED_BN_MAX_ELEMS and \
+                    ops.bn_fwd_fused(zm, gamma.detach(), beta.detach(), rm, rv, self.chan_map, self.c_valid,
+                                     self.act, modm, ym, him, lom, t.dtype, ws, vec):
                 if not t.need_grad and self.mod is None:
                     z.f32 = None
                 return
@@ -294,8 +299,9 @@ class BnActNode:
                 # every entry is written by the apply stage (all real channels are mapped)
                 self.dgamma = torch.empty_like(self.bn[0])
                 self.dbeta = torch.empty_like(self.bn[1])
-            if ops.bn_bwd_fused(zm, dym, vec[2], vec[3], vec[0], vec[1], self.chan_map, self.c_valid,
-                                self.act, modm, sums, z.mat(z.grad16), dmod16m, self.dgamma, self.dbeta):
+            if z.rows * z.C <= FUSED_BN_MAX_ELEMS and \
+                    ops.bn_bwd_fused(zm, dym, vec[2], vec[3], vec[0], vec[1], self.chan_map, self.c_valid,
+                                     self.act, modm, sums, z.mat(z.grad16), dmod16m, self.dgamma, self.dbeta):
                 out.grad = None
                 return
             ops.bn_bwd_reduce(zm, dym, vec[2], vec[3], vec[0], vec[1], self.act, modm, sums)

@@ -61,14 +61,17 @@ class BatchNorm1dFn(torch.autograd.Function):
         xp = torch.zeros(M, Cp, device=dev)
         xp[:, :C].copy_(x)
         stats = ops.bn_workspace(M, Cp, dev)
-        ops.bn_stats(xp, stats)
         vec = torch.empty(4, Cp, device=dev)
-        ops.bn_finalize(stats, M, gamma.detach(), beta.detach(), rmean if training else None,
-                        rvar if training else None, None, C, vec[0], vec[1], vec[2], vec[3])
+        yp = torch.empty(M, Cp, device=dev)
+        rm, rv = (rmean, rvar) if training else (None, None)
+        if not ops.bn_fwd_fused(xp, gamma.detach(), beta.detach(), rm, rv, None, C, ops.ACT_NONE, None, yp,
+                                None, None, ops.BF16, stats, vec):
+            ops.bn_stats(xp, stats)
+            ops.bn_finalize(stats, M, gamma.detach(), beta.detach(), rm, rv, None, C, vec[0], vec[1], vec[2],
+                            vec[3])
+            ops.bn_act_pack(xp, vec[2], vec[3], ops.ACT_NONE, y=yp)
         if training and nbt is not None:
             nbt.add_(1)
-        yp = torch.empty(M, Cp, device=dev)
-        ops.bn_act_pack(xp, vec[2], vec[3], ops.ACT_NONE, y=yp)
         out = yp
         if act_tanh:
             out = torch.empty_like(yp)

@@ -611,6 +611,9 @@ inline Tiling coop_tiling(K kernel, int64_t rows, int C) {
     if (gy < 1) gy = 1;
     t.grid.y = static_cast<unsigned>(gy);
   }
+  // the tree sum between the two grid barriers is done by ONE row of blocks while the rest of
+  // the grid waits: keep the number of partials small (the fused path is for small layers)
+  if (t.grid.y > 32) t.grid.y = 32;
   return t;
 }
 
