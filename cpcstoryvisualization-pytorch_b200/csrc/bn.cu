@@ -604,16 +604,22 @@ inline Tiling coop_tiling(K kernel, int64_t rows, int C) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0);
   if (occ < 1) occ = 1;
   per_sm = occ > 4 ? 4 : occ;
-  Tiling t = make_tiling(rows, C, per_sm);
+  // narrow channel blocks (<= 32 quads = 128 channels, 8 row lanes) so that even a [1440, 1024]
+  // layer spreads over 8 x gy blocks; the tree sum between the two grid barriers is done by the
+  // first row of blocks while the rest of the grid waits, so the partial count stays <= 128
+  const int cq = C / 4;
+  Tiling t;
+  t.qpb = 1;
+  while (t.qpb < cq && t.qpb < 32) t.qpb <<= 1;
+  t.rpb = 256 / t.qpb;
+  const int64_t gx = ceil_div(cq, t.qpb);
   const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
-  if (static_cast<int64_t>(t.grid.x) * t.grid.y > cap) {
-    int64_t gy = cap / t.grid.x;
-    if (gy < 1) gy = 1;
-    t.grid.y = static_cast<unsigned>(gy);
-  }
-  // the tree sum between the two grid barriers is done by ONE row of blocks while the rest of
-  // the grid waits: keep the number of partials small (the fused path is for small layers)
-  if (t.grid.y > 32) t.grid.y = 32;
+  int64_t gy = cap / gx;
+  const int64_t max_gy = ceil_div(rows, t.rpb);
+  if (gy > max_gy) gy = max_gy;
+  if (gy > 128) gy = 128;
+  if (gy < 1) gy = 1;
+  t.grid = dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
   return t;
 }
 
