@@ -104,6 +104,31 @@ def _cond_vectors(x, c_mu, cim_mu):
 
 
 D_NETS = ("D_se", "D_im", "D_st")
+CONCURRENT_D = True     # run the three discriminators on parallel CUDA streams
+_SIDE_STREAMS = {}
+
+
+def _concurrently(*thunks):
+    """Run independent pieces of the step on parallel CUDA streams (fork from / join into the
+    current stream; capturable into a CUDA graph as parallel branches).  Sequential on CPU or
+    when CONCURRENT_D is off."""
+    if not (CONCURRENT_D and torch.cuda.is_available() and len(thunks) > 1):
+        return [t() for t in thunks]
+    main = torch.cuda.current_stream()
+    dev = main.device
+    streams = _SIDE_STREAMS.setdefault(dev, [])
+    while len(streams) < len(thunks) - 1:
+        streams.append(torch.cuda.Stream(device=dev))
+    results = [None] * len(thunks)
+    for i, t in enumerate(thunks[1:]):
+        streams[i].wait_stream(main)
+    for i, t in enumerate(thunks[1:]):
+        with torch.cuda.stream(streams[i]):
+            results[i + 1] = t()
+    results[0] = thunks[0]()
+    for i in range(len(thunks) - 1):
+        main.wait_stream(streams[i])
+    return results
 
 
 def stage_discriminators(nets, x, labels):
@@ -124,15 +149,17 @@ def stage_discriminators(nets, x, labels):
     # (3) discriminators
     for k in ("D_im", "D_st", "D_se"):
         nets[k].zero_grad(set_to_none=True)
-    se_errD, *_rest = compute_discriminator_loss(netD_se, x["se_real"], se_fake, im_ones, im_zeros,
-                                                 x["im_labels"], im_mu, gpus)
-    im_errD, *_rest = compute_discriminator_loss(netD_im, x["im_real"], im_fake, im_ones, im_zeros,
-                                                 x["im_labels"], im_mu, gpus)
-    st_errD, *_rest = compute_discriminator_loss(netD_st, x["st_real"], st_fake, st_ones, st_zeros,
-                                                 x["st_labels"], st_mu, gpus)
-    se_errD.backward()
-    im_errD.backward()
-    st_errD.backward()
+    # the three discriminators are independent networks made of many small kernels at this
+    # batch size: run them on three concurrent streams (fork / join around the block)
+    def d_update(netD, real, fake, ones, zeros, cate, cond):
+        err = compute_discriminator_loss(netD, real, fake, ones, zeros, cate, cond, gpus)[0]
+        err.backward()
+        return err
+
+    se_errD, im_errD, st_errD = _concurrently(
+        lambda: d_update(netD_se, x["se_real"], se_fake, im_ones, im_zeros, x["im_labels"], im_mu),
+        lambda: d_update(netD_im, x["im_real"], im_fake, im_ones, im_zeros, x["im_labels"], im_mu),
+        lambda: d_update(netD_st, x["st_real"], st_fake, st_ones, st_zeros, x["st_labels"], st_mu))
     out.update(se_errD=se_errD.detach(), im_errD=im_errD.detach(), st_errD=st_errD.detach())
     return out
 
@@ -153,9 +180,10 @@ def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True):
         _, im_fake, _, _, cim_mu, cim_logvar, se_fake = netG.sample_images(x["im_motion"], x["im_content"],
                                                                          seg=True)
         st_mu, im_mu = _cond_vectors(x, c_mu, cim_mu)
-        se_errG, _, _ = compute_generator_loss(netD_se, se_fake, x["se_real"], im_ones, x["im_labels"], im_mu, gpus)
-        im_errG, _, _ = compute_generator_loss(netD_im, im_fake, x["im_real"], im_ones, x["im_labels"], im_mu, gpus)
-        st_errG, _, _ = compute_generator_loss(netD_st, st_fake, x["st_real"], st_ones, x["st_labels"], st_mu, gpus)
+        se_errG, im_errG, st_errG = _concurrently(
+            lambda: compute_generator_loss(netD_se, se_fake, x["se_real"], im_ones, x["im_labels"], im_mu, gpus)[0],
+            lambda: compute_generator_loss(netD_im, im_fake, x["im_real"], im_ones, x["im_labels"], im_mu, gpus)[0],
+            lambda: compute_generator_loss(netD_st, st_fake, x["st_real"], st_ones, x["st_labels"], st_mu, gpus)[0])
         im_kl = KL_loss(cim_mu, cim_logvar)
         st_kl = KL_loss(c_mu, c_logvar)
         kl_w = cfg.TRAIN.COEFF.KL
