@@ -56,13 +56,34 @@ class WeightCache:
         for key in [k for k in self.d if k[0] in param_ids]:
             del self.d[key]
 
+    def mark_synced(self):
+        """after the packing stream has been joined into the current one: later consumers need
+        no event wait (and must not wait on an event of an earlier graph capture)"""
+        for key, ent in list(self.d.items()):
+            if ent[2] is not None:
+                self.d[key] = (ent[0], ent[1], None, None)
+
     def get(self, key, param, build):
+        """Entries remember the stream that packed them and an event recorded after the pack
+        kernel: a consumer on another stream (concurrent network calls, pack prefetching) waits
+        on the event instead of racing with the pack."""
         tag = (param._version, param.data_ptr(), self.epoch)
         ent = self.d.get(key)
+        on_gpu = param.is_cuda
+        cur = torch.cuda.current_stream() if on_gpu else None
         if ent is not None and ent[0] == tag:
+            if on_gpu and ent[2] is not None and ent[2] != cur:
+                cur.wait_event(ent[3])
+                for tns in (ent[1] if isinstance(ent[1], (list, tuple)) else [ent[1]]):
+                    if tns is not None:
+                        tns.record_stream(cur)     # keep the allocator from recycling it early
             return ent[1]
         val = build()
-        self.d[key] = (tag, val)
+        ev = None
+        if on_gpu:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+        self.d[key] = (tag, val, cur, ev)
         return val
 
 
@@ -77,6 +98,31 @@ CONV_GEOM = {
     "up": (3, 2, 3, 16, 2),
     "s2": (4, 0, 1, 16, 0),
 }
+
+
+def pack_conv(cache, w, geom, kindcode, rows_pad, cols_pad, planes, dtype=BF16):
+    """(cached) tap-major 16-bit operand planes of a conv weight; see cpcsv_pack_conv_weight"""
+    ntap = CONV_GEOM[geom][3]
+
+    def build():
+        dev = w.device
+        t16 = ops.TORCH16[dtype]
+        hi = _e((ntap * rows_pad, cols_pad), dev, t16)
+        lo = _e((ntap * rows_pad, cols_pad), dev, t16) if planes == 2 else None
+        ops.pack_conv_weight(w.detach(), kindcode, rows_pad, cols_pad, hi, lo, dtype)
+        return [hi, lo]
+    return cache.get((id(w), kindcode, planes, dtype), w, build)
+
+
+def prefetch_conv(cache, w, geom, forward=True, backward=True):
+    """pack the training-time operand planes of one conv weight ahead of use: forward = bf16
+    hi/lo split [Co_pad, Ci_pad] taps, backward = single-plane transposed taps (dgrad)"""
+    Co_pad, Ci_pad = rup(w.shape[0], 64), rup(w.shape[1], 64)
+    _k, fkind, bkind, _nt, _uk = CONV_GEOM[geom]
+    if forward:
+        pack_conv(cache, w, geom, fkind, Co_pad, Ci_pad, 2, BF16)
+    if backward:
+        pack_conv(cache, w, geom, bkind, Ci_pad, Co_pad, 1, BF16)
 
 
 class ConvNode:
@@ -99,17 +145,7 @@ class ConvNode:
         self.dW = None
 
     def _pack(self, kindcode, rows_pad, cols_pad, planes, dtype=BF16):
-        w = self.w
-        ntap = CONV_GEOM[self.kind][3]
-
-        def build():
-            dev = w.device
-            t16 = ops.TORCH16[dtype]
-            hi = _e((ntap * rows_pad, cols_pad), dev, t16)
-            lo = _e((ntap * rows_pad, cols_pad), dev, t16) if planes == 2 else None
-            ops.pack_conv_weight(w.detach(), kindcode, rows_pad, cols_pad, hi, lo, dtype)
-            return [hi, lo]
-        return self.tape.cache.get((id(w), kindcode, planes, dtype), w, build)
+        return pack_conv(self.tape.cache, self.w, self.kind, kindcode, rows_pad, cols_pad, planes, dtype)
 
     def forward(self):
         t, x, out = self.tape, self.x, self.out

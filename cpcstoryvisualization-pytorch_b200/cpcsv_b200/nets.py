@@ -41,6 +41,50 @@ def _install_optimizer_hook():
 _install_optimizer_hook()
 
 
+def _conv_weights(module):
+    """(weight, geometry) of the tensor-core convolutions of a StoryGAN or a discriminator"""
+    out = []
+    if hasattr(module, "upsample1"):
+        for i in range(1, 5):
+            out.append((getattr(module, "upsample%d" % i)[1].weight, "up"))
+            out.append((getattr(module, "upsample%d_seg" % i)[1].weight, "up"))
+        out += [(module.seg_c.weight, "s1"), (module.seg_c1.weight, "s1")]
+    if hasattr(module, "encode_img"):
+        for idx in (2, 5, 8):
+            out.append((module.encode_img[idx].weight_orig, "s2"))
+        out.append((module.get_cond_logits.outlogits[0].weight_orig, "s1"))
+    return out
+
+
+_PREFETCH_STREAMS = {}
+
+
+def prefetch_weights(modules, forward=True, backward=True):
+    """Re-pack the conv weights of `modules` (StoryGAN / discriminators) into their bf16 operand
+    planes on a side stream, concurrently with whatever the current stream does next; consumers
+    synchronise through the cache entries' events.  Returns a handle for ``join_prefetch`` (call
+    it before the enclosing CUDA-graph capture / stage ends), or None on CPU."""
+    mods = [m for m in modules if m is not None]
+    if not mods or not next(mods[0].parameters()).is_cuda:
+        return None
+    main = torch.cuda.current_stream()
+    side = _PREFETCH_STREAMS.get(main.device)
+    if side is None:
+        side = _PREFETCH_STREAMS[main.device] = torch.cuda.Stream(device=main.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        for m in mods:
+            for w, geom in _conv_weights(m):
+                engine.prefetch_conv(_CACHE, w, geom, forward, backward)
+    return side
+
+
+def join_prefetch(handle):
+    if handle is not None:
+        torch.cuda.current_stream().wait_stream(handle)
+        _CACHE.mark_synced()
+
+
 class TapeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, *tensors):

@@ -27,6 +27,7 @@ import torch.optim as optim
 from miscc.config import cfg
 from miscc.utils import (KL_loss, compute_discriminator_loss, compute_generator_loss, count_param,
                          mkdir_p, save_model, weights_init)
+from cpcsv_b200 import nets as knets
 
 
 class GradSync:
@@ -140,6 +141,9 @@ def stage_discriminators(nets, x, labels):
     im_ones, im_zeros, st_ones, st_zeros = labels
     gpus = None
     out = {}
+    # weight re-layout for this stage's discriminator passes and for the next stage's generator
+    # passes runs on a side stream, overlapped with the no-grad generator forward below
+    prefetch = knets.prefetch_weights([netD_se, netD_im, netD_st, netG])
     # (2) fakes for the discriminator update
     with torch.no_grad():
         _, st_fake, _, _, c_mu, _, _ = netG.sample_videos(x["st_motion"], x["st_content"])
@@ -161,6 +165,7 @@ def stage_discriminators(nets, x, labels):
         lambda: d_update(netD_im, x["im_real"], im_fake, im_ones, im_zeros, x["im_labels"], im_mu),
         lambda: d_update(netD_st, x["st_real"], st_fake, st_ones, st_zeros, x["st_labels"], st_mu))
     out.update(se_errD=se_errD.detach(), im_errD=im_errD.detach(), st_errD=st_errD.detach())
+    knets.join_prefetch(prefetch)
     return out
 
 
@@ -171,6 +176,8 @@ def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True):
     im_ones, im_zeros, st_ones, st_zeros = labels
     gpus = None
     out = {}
+    # the discriminators were just updated: re-pack their weights while the generator runs
+    prefetch = knets.prefetch_weights([netD_se, netD_im, netD_st])
     netG.zero_grad(set_to_none=True)
     if skip_d_wgrad:
         for k in ("D_im", "D_st", "D_se"):
@@ -197,6 +204,7 @@ def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True):
     out.update(se_errG=se_errG.detach(), im_errG=im_errG.detach(), st_errG=st_errG.detach(),
                im_kl=im_kl.detach(), st_kl=st_kl.detach(), errG_total=total.detach())
     out["p3_st_fake"], out["p3_im_fake"], out["p3_se_fake"] = st_fake.detach(), im_fake.detach(), se_fake.detach()
+    knets.join_prefetch(prefetch)
     return out
 
 
