@@ -67,9 +67,13 @@ class WeightCache:
         """Entries remember the stream that packed them and an event recorded after the pack
         kernel: a consumer on another stream (concurrent network calls, pack prefetching) waits
         on the event instead of racing with the pack."""
-        tag = (param._version, param.data_ptr(), self.epoch)
-        ent = self.d.get(key)
         on_gpu = param.is_cuda
+        # planes packed while a CUDA graph is being captured only exist once that graph replays,
+        # and planes packed eagerly must not be waited on from inside a capture: the capture
+        # state is part of the validity tag
+        capturing = on_gpu and torch.cuda.is_current_stream_capturing()
+        tag = (param._version, param.data_ptr(), self.epoch, capturing)
+        ent = self.d.get(key)
         cur = torch.cuda.current_stream() if on_gpu else None
         if ent is not None and ent[0] == tag:
             if on_gpu and ent[2] is not None and ent[2] != cur:
