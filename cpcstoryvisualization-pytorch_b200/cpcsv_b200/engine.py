@@ -370,6 +370,22 @@ class Tape:
         if self.counters:
             torch._foreach_add_(self.counters, 1)
             self.counters = []
+        if not self.need_grad:
+            self.release()
+        else:
+            # the lo operand planes are only read by the forward GEMMs (backward GEMMs are
+            # single-pass on the hi plane): give their memory back now
+            for n in self.nodes:
+                for t4 in (getattr(n, "out", None), getattr(n, "x", None)):
+                    if t4 is not None:
+                        t4.lo = None
+
+    def release(self):
+        """break the tape <-> node reference cycle so the activations are freed by reference
+        counting right away instead of whenever Python's cycle collector runs"""
+        for n in self.nodes:
+            n.tape = None
+        self.nodes = []
 
     def add(self, node):
         self.nodes.append(node)

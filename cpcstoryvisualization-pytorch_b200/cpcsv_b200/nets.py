@@ -341,7 +341,8 @@ class TrunkRunner:
         out = [dz]
         for n, need in zip(self.names, needs[1:]):
             out.append(pg.get(n) if need else None)
-        self.tape = self.nodes = None
+        self.tape.release()
+        self.tape = self.nodes = self.alias = self.a_img = self.a_seg = self.x0 = None
         return out
 
     def _all_acts(self):
@@ -485,6 +486,7 @@ class EncoderRunner:
         self.feat = a
         Cf = enc[8].weight_orig.shape[0]
         tape.finish_forward()
+        col.lo = None
         return a.f32.permute(0, 3, 1, 2)[:, :Cf]
 
     def run_backward(self, grads, needs):
@@ -533,7 +535,8 @@ class EncoderRunner:
         out = [dx]
         for nme, need in zip(self.names, needs[1:]):
             out.append(pg.get(nme) if need else None)
-        self.tape = self.layers = None
+        self.tape.release()
+        self.tape = self.layers = self.act0 = self.z0 = self.col = self.feat = None
         return out
 
 
@@ -632,7 +635,8 @@ class LogitsRunner:
         out = [dh, None]
         for nme, need in zip(self.names, needs[2:]):
             out.append(pg.get(nme) if need else None)
-        self.tape = None
+        self.tape.release()
+        self.tape = self.cn = self.bn = self.a = self.x = None
         return out
 
 
