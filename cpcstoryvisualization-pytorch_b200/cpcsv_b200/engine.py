@@ -95,6 +95,40 @@ def _e(shape, dev, dtype=torch.float32):
     return torch.empty(shape, device=dev, dtype=dtype)
 
 
+class StateOrder:
+    """In-place module state that several network calls update (BatchNorm running statistics,
+    num_batches_tracked) must be updated in program order even when the calls run on different
+    CUDA streams (trainer runs sample_videos / sample_images concurrently).  Every update of a
+    state tensor records an event; an update issued later from another stream waits on it."""
+
+    _last = {}
+
+    @classmethod
+    def reset(cls):
+        """all streams have been joined: nothing issued later needs the recorded events"""
+        cls._last.clear()
+
+    @classmethod
+    def before(cls, tensor):
+        if tensor is None or not tensor.is_cuda:
+            return
+        ent = cls._last.get(tensor.data_ptr())
+        if ent is not None:
+            cur = torch.cuda.current_stream()
+            capturing = torch.cuda.is_current_stream_capturing()
+            if ent[0] != cur and ent[2] == capturing:
+                cur.wait_event(ent[1])
+
+    @classmethod
+    def after(cls, tensor):
+        if tensor is None or not tensor.is_cuda:
+            return
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        cls._last[tensor.data_ptr()] = (cur, ev, torch.cuda.is_current_stream_capturing())
+
+
 # ------------------------------------------------------------------------------ conv nodes
 CONV_GEOM = {
     # kind: (kernel, fwd pack kind, dgrad pack kind, wgrad taps, unpack kind, out scale)
@@ -300,17 +334,20 @@ class BnActNode:
             vec = _e((4, z.C), dev)
             self.stat = vec
             rm, rv = (rmean, rvar) if t.training else (None, None)
+            StateOrder.before(rm)
             # small layers: one cooperative launch (launch count dominates); large layers: the
             # multi-launch path, whose reductions use the whole chip
             if z.rows * z.C <= FUSED_BN_MAX_ELEMS and \
                     ops.bn_fwd_fused(zm, gamma.detach(), beta.detach(), rm, rv, self.chan_map, self.c_valid,
                                      self.act, modm, ym, him, lom, t.dtype, ws, vec):
+                StateOrder.after(rm)
                 if not t.need_grad and self.mod is None:
                     z.f32 = None
                 return
             ops.bn_stats(zm, ws)
             ops.bn_finalize(ws, z.rows, gamma.detach(), beta.detach(), rm, rv, self.chan_map, self.c_valid,
                             vec[0], vec[1], vec[2], vec[3])
+            StateOrder.after(rm)
             scale, shift = vec[2], vec[3]
         ops.bn_act_pack(zm, scale, shift, self.act, modm, ym, him, lom, t.dtype)
         if not t.need_grad and self.mod is None:
@@ -368,7 +405,9 @@ class Tape:
     def finish_forward(self):
         """one multi-tensor launch for all `num_batches_tracked += 1` of this call"""
         if self.counters:
+            StateOrder.before(self.counters[0])
             torch._foreach_add_(self.counters, 1)
+            StateOrder.after(self.counters[0])
             self.counters = []
         if not self.need_grad:
             self.release()

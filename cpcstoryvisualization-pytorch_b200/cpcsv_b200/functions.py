@@ -6,6 +6,7 @@ forward/backward below is one or a few libcpcsv.so launches; torch only allocate
 import torch
 
 from . import ops
+from .engine import StateOrder
 
 
 def _c(t):
@@ -64,6 +65,7 @@ class BatchNorm1dFn(torch.autograd.Function):
         vec = torch.empty(4, Cp, device=dev)
         yp = torch.empty(M, Cp, device=dev)
         rm, rv = (rmean, rvar) if training else (None, None)
+        StateOrder.before(rm)
         if not ops.bn_fwd_fused(xp, gamma.detach(), beta.detach(), rm, rv, None, C, ops.ACT_NONE, None, yp,
                                 None, None, ops.BF16, stats, vec):
             ops.bn_stats(xp, stats)
@@ -72,6 +74,7 @@ class BatchNorm1dFn(torch.autograd.Function):
             ops.bn_act_pack(xp, vec[2], vec[3], ops.ACT_NONE, y=yp)
         if training and nbt is not None:
             nbt.add_(1)
+        StateOrder.after(rm)
         out = yp
         if act_tanh:
             out = torch.empty_like(yp)

@@ -79,6 +79,12 @@ def prefetch_weights(modules, forward=True, backward=True):
     return side
 
 
+def sync_point():
+    """every side stream has been joined into the current one: forget cross-stream events"""
+    engine.StateOrder.reset()
+    _CACHE.mark_synced()
+
+
 def join_prefetch(handle):
     if handle is not None:
         torch.cuda.current_stream().wait_stream(handle)

@@ -106,14 +106,16 @@ def _cond_vectors(x, c_mu, cim_mu):
 
 D_NETS = ("D_se", "D_im", "D_st")
 CONCURRENT_D = True     # run the three discriminators on parallel CUDA streams
+CONCURRENT_G = True     # run sample_videos / sample_images of one phase on two streams
 _SIDE_STREAMS = {}
 
 
-def _concurrently(*thunks):
+def _concurrently(*thunks, enabled=None):
     """Run independent pieces of the step on parallel CUDA streams (fork from / join into the
     current stream; capturable into a CUDA graph as parallel branches).  Sequential on CPU or
-    when CONCURRENT_D is off."""
-    if not (CONCURRENT_D and torch.cuda.is_available() and len(thunks) > 1):
+    when switched off."""
+    enabled = CONCURRENT_D if enabled is None else enabled
+    if not (enabled and torch.cuda.is_available() and len(thunks) > 1):
         return [t() for t in thunks]
     main = torch.cuda.current_stream()
     dev = main.device
@@ -121,14 +123,18 @@ def _concurrently(*thunks):
     while len(streams) < len(thunks) - 1:
         streams.append(torch.cuda.Stream(device=dev))
     results = [None] * len(thunks)
-    for i, t in enumerate(thunks[1:]):
+    for i in range(len(thunks) - 1):
         streams[i].wait_stream(main)
-    for i, t in enumerate(thunks[1:]):
+    # issue order = list order (in-place module state shared by two pieces, e.g. the BatchNorm
+    # running statistics of two generator calls, is updated in that order: engine.StateOrder);
+    # the last piece runs on the current stream
+    for i, t in enumerate(thunks[:-1]):
         with torch.cuda.stream(streams[i]):
-            results[i + 1] = t()
-    results[0] = thunks[0]()
+            results[i] = t()
+    results[-1] = thunks[-1]()
     for i in range(len(thunks) - 1):
         main.wait_stream(streams[i])
+    knets.sync_point()
     return results
 
 
@@ -145,9 +151,14 @@ def stage_discriminators(nets, x, labels):
     # passes runs on a side stream, overlapped with the no-grad generator forward below
     prefetch = knets.prefetch_weights([netD_se, netD_im, netD_st, netG])
     # (2) fakes for the discriminator update
-    with torch.no_grad():
-        _, st_fake, _, _, c_mu, _, _ = netG.sample_videos(x["st_motion"], x["st_content"])
-        _, im_fake, _, _, cim_mu, _, se_fake = netG.sample_images(x["im_motion"], x["im_content"], seg=True)
+    def no_grad(fn, *a, **kw):
+        with torch.no_grad():      # grad mode is thread-local state, so set it inside the thunk
+            return fn(*a, **kw)
+
+    (_, st_fake, _, _, c_mu, _, _), (_, im_fake, _, _, cim_mu, _, se_fake) = _concurrently(
+        lambda: no_grad(netG.sample_videos, x["st_motion"], x["st_content"]),
+        lambda: no_grad(netG.sample_images, x["im_motion"], x["im_content"], seg=True),
+        enabled=CONCURRENT_G)
     st_mu, im_mu = _cond_vectors(x, c_mu, cim_mu)
     out["p1_st_fake"], out["p1_im_fake"], out["p1_se_fake"] = st_fake, im_fake, se_fake
     # (3) discriminators
@@ -183,9 +194,10 @@ def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True):
         for k in ("D_im", "D_st", "D_se"):
             _set_requires_grad(nets[k], False)
     try:
-        _, st_fake, _, _, c_mu, c_logvar, _ = netG.sample_videos(x["st_motion"], x["st_content"])
-        _, im_fake, _, _, cim_mu, cim_logvar, se_fake = netG.sample_images(x["im_motion"], x["im_content"],
-                                                                         seg=True)
+        (_, st_fake, _, _, c_mu, c_logvar, _), (_, im_fake, _, _, cim_mu, cim_logvar, se_fake) = _concurrently(
+            lambda: netG.sample_videos(x["st_motion"], x["st_content"]),
+            lambda: netG.sample_images(x["im_motion"], x["im_content"], seg=True),
+            enabled=CONCURRENT_G)
         st_mu, im_mu = _cond_vectors(x, c_mu, cim_mu)
         se_errG, im_errG, st_errG = _concurrently(
             lambda: compute_generator_loss(netD_se, se_fake, x["se_real"], im_ones, x["im_labels"], im_mu, gpus)[0],
