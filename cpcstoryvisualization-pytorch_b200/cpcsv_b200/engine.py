@@ -56,11 +56,12 @@ class WeightCache:
         for key in [k for k in self.d if k[0] in param_ids]:
             del self.d[key]
 
-    def mark_synced(self):
-        """after the packing stream has been joined into the current one: later consumers need
-        no event wait (and must not wait on an event of an earlier graph capture)"""
+    def mark_synced(self, streams=None):
+        """after packing streams have been joined into the current one: later consumers need no
+        event wait (and must not wait on an event of an earlier graph capture).  `streams` = the
+        streams that were joined (None: every stream)"""
         for key, ent in list(self.d.items()):
-            if ent[2] is not None:
+            if ent[2] is not None and (streams is None or ent[2] in streams):
                 self.d[key] = (ent[0], ent[1], None, None)
 
     def get(self, key, param, build):
@@ -251,7 +252,10 @@ class SpectralNorm:
         scratch = _e((R + w2d.shape[1],), dev)
         ops.spectral_sigma(w2d, self.u, self.v, training, sig[0:1], sig[1:2], scratch)
         if need_grad:
-            self.saved = (self.u.clone(), self.v.clone(), sig)
+            # one cat kernel instead of two clone()s: device-to-device memcpy NODES of parallel
+            # CUDA-graph branches execute in one shared order (like memset nodes), kernels do not
+            uv = torch.cat((self.u.detach().reshape(-1), self.v.detach().reshape(-1)))
+            self.saved = (uv[:R], uv[R:], sig)
         return sig[1:2]
 
     def backward(self, g, w_orig):

@@ -79,16 +79,19 @@ def prefetch_weights(modules, forward=True, backward=True):
     return side
 
 
-def sync_point():
-    """every side stream has been joined into the current one: forget cross-stream events"""
-    engine.StateOrder.reset()
-    _CACHE.mark_synced()
+def sync_point(streams=None, reset_state_order=True):
+    """side streams (`streams`; None = all of them) have been joined into the current one:
+    forget their cross-stream events.  `reset_state_order=False` while other streams that touch
+    ordered module state are still running detached."""
+    if reset_state_order:
+        engine.StateOrder.reset()
+    _CACHE.mark_synced(streams)
 
 
 def join_prefetch(handle):
     if handle is not None:
         torch.cuda.current_stream().wait_stream(handle)
-        _CACHE.mark_synced()
+        _CACHE.mark_synced([handle])
 
 
 class TapeFn(torch.autograd.Function):

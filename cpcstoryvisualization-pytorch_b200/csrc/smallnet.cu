@@ -376,6 +376,21 @@ __global__ void sn_bwd_apply_kernel(const float* __restrict__ G, const float* __
   }
 }
 
+// Zero fill as a kernel: inside the whole-step CUDA graph, memset NODES of independent branches
+// were observed to execute in one shared order (a branch's first memset waited ~6 ms for memsets
+// of two other branches), kernel nodes are not.
+__global__ void zero_f32_kernel(float* __restrict__ p, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    p[i] = 0.f;
+}
+
+static inline void zero_f32(float* p, int64_t n, cudaStream_t stream) {
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 148) blocks = 148;
+  zero_f32_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p, n);
+}
+
 }  // namespace cpcsv
 
 using namespace cpcsv;
@@ -385,7 +400,7 @@ extern "C" int cpcsv_linear_f32(const float* X, int64_t ldx, const float* W, int
                                 const float* bias, float* Y, int64_t ldy, int32_t M, int32_t N,
                                 int32_t K, int32_t accumulate, cpcsv_stream_t stream) {
   if (N <= 16 && K >= 2048 && ldy == N && X && W && Y && M > 0) {
-    if (!accumulate) cudaMemsetAsync(Y, 0, sizeof(float) * M * N, STREAM(stream));
+    if (!accumulate) zero_f32(Y, static_cast<int64_t>(M) * N, STREAM(stream));
     const int kchunk = 2048;
     dim3 grid(static_cast<unsigned>(ceil_div(K, kchunk)), static_cast<unsigned>(M));
     linear_skinny_kernel<<<grid, 256, 0, STREAM(stream)>>>(X, ldx, W, ldw, bias, Y, ldy, N, K, kchunk);
@@ -489,7 +504,7 @@ extern "C" int cpcsv_spectral_sigma(const float* W, int32_t R, int32_t C, float*
   float* tc = scratch;      // [C]
   float* tr = scratch + C;  // [R]
   if (do_power_iteration) {
-    cudaMemsetAsync(tc, 0, sizeof(float) * C, stream);
+    zero_f32(tc, C, stream);
     dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), static_cast<unsigned>(ceil_div(R, 32)));
     sn_wt_u_kernel<<<grid, 128, 0, stream>>>(W, R, C, u, tc);
     int rc = launched("spectral_sigma/Wt_u");
@@ -511,7 +526,7 @@ extern "C" int cpcsv_spectral_bwd(const float* G, const float* W, const float* u
   cudaStream_t stream = STREAM(stream_);
   CPCSV_REQUIRE(G && W && u && v && sigma && dW && scratch && R > 0 && C > 0, "spectral_bwd: args");
   const int64_t n = static_cast<int64_t>(R) * C;
-  cudaMemsetAsync(scratch, 0, sizeof(float), stream);
+  zero_f32(scratch, 1, stream);
   int blocks = static_cast<int>(ceil_div(n, 256 * 8));
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
   if (blocks < 1) blocks = 1;

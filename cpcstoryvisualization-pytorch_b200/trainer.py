@@ -107,7 +107,17 @@ def _cond_vectors(x, c_mu, cim_mu):
 D_NETS = ("D_se", "D_im", "D_st")
 CONCURRENT_D = True     # run the three discriminators on parallel CUDA streams
 CONCURRENT_G = True     # run sample_videos / sample_images of one phase on two streams
+EARLY_G = True          # issue the generator-update forward alongside the discriminator update
 _SIDE_STREAMS = {}
+_DETACHED_STREAMS = {}
+_DETACHED_OPEN = [0]    # detached branches issued and not yet joined
+
+
+def _side_streams(pool, dev, n):
+    streams = pool.setdefault(dev, [])
+    while len(streams) < n:
+        streams.append(torch.cuda.Stream(device=dev))
+    return streams[:n]
 
 
 def _concurrently(*thunks, enabled=None):
@@ -118,13 +128,10 @@ def _concurrently(*thunks, enabled=None):
     if not (enabled and torch.cuda.is_available() and len(thunks) > 1):
         return [t() for t in thunks]
     main = torch.cuda.current_stream()
-    dev = main.device
-    streams = _SIDE_STREAMS.setdefault(dev, [])
-    while len(streams) < len(thunks) - 1:
-        streams.append(torch.cuda.Stream(device=dev))
+    streams = _side_streams(_SIDE_STREAMS, main.device, len(thunks) - 1)
     results = [None] * len(thunks)
-    for i in range(len(thunks) - 1):
-        streams[i].wait_stream(main)
+    for st in streams:
+        st.wait_stream(main)
     # issue order = list order (in-place module state shared by two pieces, e.g. the BatchNorm
     # running statistics of two generator calls, is updated in that order: engine.StateOrder);
     # the last piece runs on the current stream
@@ -132,33 +139,83 @@ def _concurrently(*thunks, enabled=None):
         with torch.cuda.stream(streams[i]):
             results[i] = t()
     results[-1] = thunks[-1]()
-    for i in range(len(thunks) - 1):
-        main.wait_stream(streams[i])
-    knets.sync_point()
+    for st in streams:
+        main.wait_stream(st)
+    knets.sync_point(streams, reset_state_order=_DETACHED_OPEN[0] == 0)
     return results
 
 
-def stage_discriminators(nets, x, labels):
+class Detached:
+    """Independent pieces of the step issued on their own streams and joined LATER (not at the end
+    of the issuing block): they overlap with everything the current stream does in between.
+    ``after`` is an event of the current stream the pieces have to wait for (their inputs)."""
+
+    def __init__(self, thunks, after=None):
+        self.results = None
+        self.streams = []
+        if not torch.cuda.is_available():
+            self.results = [t() for t in thunks]
+            return
+        main = torch.cuda.current_stream()
+        self.streams = _side_streams(_DETACHED_STREAMS, main.device, len(thunks))
+        self.results = []
+        _DETACHED_OPEN[0] += 1
+        for st, t in zip(self.streams, thunks):
+            if after is not None:
+                st.wait_event(after)
+            else:
+                st.wait_stream(main)
+            with torch.cuda.stream(st):
+                self.results.append(t())
+
+    def join(self):
+        if self.streams:
+            main = torch.cuda.current_stream()
+            for st in self.streams:
+                main.wait_stream(st)
+            _DETACHED_OPEN[0] -= 1
+            knets.sync_point(self.streams, reset_state_order=_DETACHED_OPEN[0] == 0)
+            self.streams = []
+        return self.results
+
+
+def stage_discriminators(nets, x, labels, early_generator=False):
     """reference trainer.py:290-343 minus the optimiser steps: no-grad fakes, the three
     discriminator losses and their backward passes.  The three discriminators are independent
     networks, so running all backward passes before any of their Adam steps (instead of the
-    reference's se.step() between se.backward() and im.backward()) gives identical results."""
+    reference's se.step() between se.backward() and im.backward()) gives identical results.
+
+    ``early_generator``: also issue the forward pass of the generator update (reference
+    trainer.py:365-368) on detached streams.  It reads only the generator's weights (updated at
+    the very end of the step) and fresh noise, so it does not depend on the discriminator update
+    and fills the tensor cores while the discriminators' many small kernels run.  It is issued
+    after the no-grad calls, so noise is drawn and BatchNorm running statistics are updated in
+    the reference's order.  The handle comes back under ``out['early_generator']``."""
     netG, netD_im, netD_st, netD_se = nets["G"], nets["D_im"], nets["D_st"], nets["D_se"]
     im_ones, im_zeros, st_ones, st_zeros = labels
     gpus = None
     out = {}
+    start = None
+    if early_generator and torch.cuda.is_available():
+        start = torch.cuda.Event()
+        start.record()
     # weight re-layout for this stage's discriminator passes and for the next stage's generator
     # passes runs on a side stream, overlapped with the no-grad generator forward below
-    prefetch = knets.prefetch_weights([netD_se, netD_im, netD_st, netG])
+    prefetch = knets.prefetch_weights([netG, netD_se, netD_im, netD_st])
     # (2) fakes for the discriminator update
     def no_grad(fn, *a, **kw):
         with torch.no_grad():      # grad mode is thread-local state, so set it inside the thunk
             return fn(*a, **kw)
 
+    if early_generator:
+        _DETACHED_OPEN[0] += 1     # keep the ordered-state events alive across the join below
     (_, st_fake, _, _, c_mu, _, _), (_, im_fake, _, _, cim_mu, _, se_fake) = _concurrently(
         lambda: no_grad(netG.sample_videos, x["st_motion"], x["st_content"]),
         lambda: no_grad(netG.sample_images, x["im_motion"], x["im_content"], seg=True),
         enabled=CONCURRENT_G)
+    if early_generator:
+        _DETACHED_OPEN[0] -= 1
+        out["early_generator"] = generator_forward(nets, x, after=start)
     st_mu, im_mu = _cond_vectors(x, c_mu, cim_mu)
     out["p1_st_fake"], out["p1_im_fake"], out["p1_se_fake"] = st_fake, im_fake, se_fake
     # (3) discriminators
@@ -180,24 +237,39 @@ def stage_discriminators(nets, x, labels):
     return out
 
 
-def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True):
-    """reference trainer.py:365-415: generator forward with fresh noise, the three adversarial
-    losses + KL terms, backward."""
+def generator_forward(nets, x, after=None):
+    """the two generator calls of the generator update (reference trainer.py:365-368), issued on
+    detached streams; ``.join()`` gives the two 7-tuples"""
+    netG = nets["G"]
+    netG.zero_grad(set_to_none=True)
+    return Detached([lambda: netG.sample_videos(x["st_motion"], x["st_content"]),
+                     lambda: netG.sample_images(x["im_motion"], x["im_content"], seg=True)], after=after)
+
+
+def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True, forward=None):
+    """reference trainer.py:365-415: generator forward with fresh noise (or the already issued
+    ``forward`` handle of ``generator_forward``), the three adversarial losses + KL terms,
+    backward."""
     netG, netD_im, netD_st, netD_se = nets["G"], nets["D_im"], nets["D_st"], nets["D_se"]
     im_ones, im_zeros, st_ones, st_zeros = labels
     gpus = None
     out = {}
     # the discriminators were just updated: re-pack their weights while the generator runs
     prefetch = knets.prefetch_weights([netD_se, netD_im, netD_st])
-    netG.zero_grad(set_to_none=True)
+    if forward is None:
+        netG.zero_grad(set_to_none=True)
     if skip_d_wgrad:
         for k in ("D_im", "D_st", "D_se"):
             _set_requires_grad(nets[k], False)
     try:
-        (_, st_fake, _, _, c_mu, c_logvar, _), (_, im_fake, _, _, cim_mu, cim_logvar, se_fake) = _concurrently(
-            lambda: netG.sample_videos(x["st_motion"], x["st_content"]),
-            lambda: netG.sample_images(x["im_motion"], x["im_content"], seg=True),
-            enabled=CONCURRENT_G)
+        if forward is not None:
+            g_vid, g_img = forward.join()
+        else:
+            g_vid, g_img = _concurrently(
+                lambda: netG.sample_videos(x["st_motion"], x["st_content"]),
+                lambda: netG.sample_images(x["im_motion"], x["im_content"], seg=True),
+                enabled=CONCURRENT_G)
+        (_, st_fake, _, _, c_mu, c_logvar, _), (_, im_fake, _, _, cim_mu, cim_logvar, se_fake) = g_vid, g_img
         st_mu, im_mu = _cond_vectors(x, c_mu, cim_mu)
         se_errG, im_errG, st_errG = _concurrently(
             lambda: compute_generator_loss(netD_se, se_fake, x["se_real"], im_ones, x["im_labels"], im_mu, gpus)[0],
@@ -231,12 +303,12 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
     """One iteration of the reference's hot loop (trainer.py:290-416).  ``x`` from
     ``prepare_inputs`` (device tensors), ``labels`` = (im_ones, im_zeros, st_ones, st_zeros).
     Returns a dict of loss tensors (no host sync)."""
-    out = stage_discriminators(nets, x, labels)
+    out = stage_discriminators(nets, x, labels, early_generator=EARLY_G)
     sync_grads(nets, D_NETS, grad_sync)
     if apply_optim:
         for k in D_NETS:
             opts[k].step()
-    out.update(stage_generator(nets, x, labels, ratio, skip_d_wgrad))
+    out.update(stage_generator(nets, x, labels, ratio, skip_d_wgrad, forward=out.pop("early_generator", None)))
     sync_grads(nets, ("G",), grad_sync)
     if apply_optim:
         opts["G"].step()
