@@ -226,14 +226,14 @@ class StepEngine:
         self.knets.invalidate_weight_cache()
         if self.grad_sync is None:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=self.trainer.step_stream(self.device)):
                 self._step_body()
             return
         self.graphs = []
         pool = None
         for seg in (self._seg_d, self._seg_g, self._seg_opt):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with torch.cuda.graph(g, pool=pool, stream=self.trainer.step_stream(self.device)):
                 seg()
             pool = g.pool()
             self.graphs.append(g)

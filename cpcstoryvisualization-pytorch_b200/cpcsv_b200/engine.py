@@ -130,6 +130,49 @@ class StateOrder:
         cls._last[tensor.data_ptr()] = (cur, ev, torch.cuda.is_current_stream_capturing())
 
 
+# ------------------------------------------------------------------------------ aux branch
+WGRAD_ON_AUX_STREAM = True
+_AUX_STREAMS = {}
+
+
+class AuxBranch:
+    """Side stream of one tape's backward pass for work nothing later in the same pass waits for:
+    the weight-gradient GEMM of a layer (+ its un-packing and spectral-norm backward) runs there
+    while the data-gradient chain (dgrad -> BN backward -> dgrad ...) continues on the tape's own
+    stream.  ``run`` forks after everything issued so far; ``join`` makes the tape's stream wait
+    for the branch (call it before handing the gradients back to autograd)."""
+
+    def __init__(self):
+        self.stream = None
+        self.keep = []
+
+    def run(self, fn, *keep):
+        """`keep`: tensors the branch reads that the caller is about to drop -- held until
+        ``join`` so the allocator cannot recycle them under the branch's kernels"""
+        if not (WGRAD_ON_AUX_STREAM and torch.cuda.is_available()):
+            fn()
+            return
+        cur = torch.cuda.current_stream()
+        if self.stream is None:
+            key = (cur.device, cur.cuda_stream)
+            st = _AUX_STREAMS.get(key)
+            if st is None:
+                st = _AUX_STREAMS[key] = torch.cuda.Stream(device=cur.device, priority=cur.priority)
+            self.stream = st
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.stream.wait_event(ev)
+        self.keep.extend(keep)
+        with torch.cuda.stream(self.stream):
+            fn()
+
+    def join(self):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.stream = None
+        self.keep = []
+
+
 # ------------------------------------------------------------------------------ conv nodes
 CONV_GEOM = {
     # kind: (kernel, fwd pack kind, dgrad pack kind, wgrad taps, unpack kind, out scale)
@@ -208,19 +251,8 @@ class ConvNode:
         assert dz is not None, self.name
         dev = dz.device
         k, _, dkind, ntap, ukind = CONV_GEOM[self.kind]
-        if need_wgrad:
-            dwt = _e((ntap, self.Co_pad, self.Ci_pad), dev)
-            if self.kind == "s1":
-                job = conv.conv_s1_wgrad(dz, x.hi, dwt, 3)
-            elif self.kind == "up":
-                job = conv.upconv_wgrad(dz, x.hi, dwt)
-            else:
-                job = conv.conv_s2_wgrad(dz, x.hi, dwt)
-            ops.conv_gemm(job)
-            g = _e(tuple(self.w.shape), dev)
-            ops.unpack_conv_wgrad(dwt, self.Co_pad * self.Ci_pad, self.Ci_pad, ukind, None, g)
-            self.dW = self.sn.backward(g, self.w) if self.sn is not None else g
         if x.needs_grad:
+            # data gradient first: it is what the rest of the backward chain waits for
             wt = self._pack(dkind, self.Ci_pad, self.Co_pad, 1)[0]
             acc = x.grad is not None
             if not acc:
@@ -233,7 +265,25 @@ class ConvNode:
                 assert not acc
                 job = conv.conv_s2_dgrad(dz, wt, x.grad, self.alpha)
             ops.conv_gemm(job)
+        if need_wgrad:
+            self.tape.aux.run(lambda: self._wgrad(dz), dz)
         out.grad16 = None
+
+    def _wgrad(self, dz):
+        x = self.x
+        dev = dz.device
+        _k, _f, _d, ntap, ukind = CONV_GEOM[self.kind]
+        dwt = _e((ntap, self.Co_pad, self.Ci_pad), dev)
+        if self.kind == "s1":
+            job = conv.conv_s1_wgrad(dz, x.hi, dwt, 3)
+        elif self.kind == "up":
+            job = conv.upconv_wgrad(dz, x.hi, dwt)
+        else:
+            job = conv.conv_s2_wgrad(dz, x.hi, dwt)
+        ops.conv_gemm(job)
+        g = _e(tuple(self.w.shape), dev)
+        ops.unpack_conv_wgrad(dwt, self.Co_pad * self.Ci_pad, self.Ci_pad, ukind, None, g)
+        self.dW = self.sn.backward(g, self.w) if self.sn is not None else g
 
 
 class SpectralNorm:
@@ -290,15 +340,17 @@ class GemmNode:
         x, out = self.x, self.out
         dz = out.grad16.view(x.rows, self.npad)
         dev = dz.device
-        if need_wgrad:
-            self.dwt = _e((self.npad, x.C), dev)
-            ops.conv_gemm(conv.gemm_tn(dz, x.hi.view(x.rows, x.C), self.dwt))
         if x.needs_grad:
             acc = x.grad is not None
             if not acc:
                 x.grad = _e((x.N, x.H, x.W, x.C), dev)
             ops.conv_gemm(conv.gemm_nt([dz, None], [self.pack_bwd(), None], x.grad.view(x.rows, x.C),
                                        accumulate=acc))
+        if need_wgrad:
+            def wgrad():
+                self.dwt = _e((self.npad, x.C), dev)
+                ops.conv_gemm(conv.gemm_tn(dz, x.hi.view(x.rows, x.C), self.dwt))
+            self.tape.aux.run(wgrad, dz)
         out.grad16 = None
 
 
@@ -405,6 +457,7 @@ class Tape:
         self.dtype = dtype if dtype is not None else (ops.BF16 if need_grad else ops.FP16)
         self.nodes = []
         self.counters = []      # num_batches_tracked buffers to bump once the forward is done
+        self.aux = AuxBranch()  # weight-gradient side branch of the backward pass
 
     def finish_forward(self):
         """one multi-tensor launch for all `num_batches_tracked += 1` of this call"""
@@ -426,6 +479,7 @@ class Tape:
     def release(self):
         """break the tape <-> node reference cycle so the activations are freed by reference
         counting right away instead of whenever Python's cycle collector runs"""
+        self.aux.join()
         for n in self.nodes:
             n.tape = None
         self.nodes = []

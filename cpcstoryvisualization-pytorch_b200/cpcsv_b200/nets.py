@@ -70,7 +70,7 @@ def prefetch_weights(modules, forward=True, backward=True):
     main = torch.cuda.current_stream()
     side = _PREFETCH_STREAMS.get(main.device)
     if side is None:
-        side = _PREFETCH_STREAMS[main.device] = torch.cuda.Stream(device=main.device)
+        side = _PREFETCH_STREAMS[main.device] = torch.cuda.Stream(device=main.device, priority=-1)
     side.wait_stream(main)
     with torch.cuda.stream(side):
         for m in mods:
@@ -288,23 +288,23 @@ class TrunkRunner:
         ops.tanh_to_nchw(z.view(a.rows, 16), a.N, Co, a.H, a.W, y)
         return y
 
-    def _head_bwd(self, a, w, y, dy, need_w):
-        """returns dW; accumulates d(a) into a.grad"""
+    def _head_bwd(self, a, w, y, dy, need_w, pg, name):
+        """accumulates d(a) into a.grad; the weight gradient goes to pg[name] (aux branch)"""
         dev = y.device
         Co, Ci = w.shape[0], w.shape[1]
         col = _e((a.rows, 64), dev, torch.bfloat16)
         ops.tanh_bwd_im2col(dy, y, col)
-        dW = None
-        if need_w:
-            d = _e((a.C, 64), dev)
-            ops.conv_gemm(conv.gemm_tn(a.hi.view(a.rows, a.C), col, d))
-            dW = d[:Ci, :9 * Co].reshape(Ci, 3, 3, Co).permute(3, 0, 1, 2).contiguous()
         acc = a.grad is not None
         if not acc:
             a.grad = _e((a.N, a.H, a.W, a.C), dev)
         ops.conv_gemm(conv.gemm_nt([col, None], [self._head_pack(w, "bwd"), None], a.grad.view(a.rows, a.C),
                                    accumulate=acc))
-        return dW
+        if need_w:
+            def wgrad():
+                d = _e((a.C, 64), dev)
+                ops.conv_gemm(conv.gemm_tn(a.hi.view(a.rows, a.C), col, d))
+                pg[name] = d[:Ci, :9 * Co].reshape(Ci, 3, 3, Co).permute(3, 0, 1, 2).contiguous()
+            self.tape.aux.run(wgrad, col)
 
     # ---------------------------------------------------------------- backward
     def run_backward(self, grads, needs):
@@ -315,10 +315,10 @@ class TrunkRunner:
         for t in self._all_acts():
             t.needs_grad = True
         if d_img is not None:
-            pg["img.0.weight"] = self._head_bwd(self.a_img, G.img[0].weight, self.img, d_img, need_w)
+            self._head_bwd(self.a_img, G.img[0].weight, self.img, d_img, need_w, pg, "img.0.weight")
         seg_tail = d_seg is not None
         if seg_tail:
-            pg["img_seg.0.weight"] = self._head_bwd(self.a_seg, G.img_seg[0].weight, self.seg, d_seg, need_w)
+            self._head_bwd(self.a_seg, G.img_seg[0].weight, self.seg, d_seg, need_w, pg, "img_seg.0.weight")
 
         def bn_conv_bwd(bn_name, conv_name, prefix_bn, prefix_conv):
             bn, cv = nodes[bn_name], nodes[conv_name]
@@ -344,6 +344,7 @@ class TrunkRunner:
             bn_conv_bwd("upsample%d_seg.bn" % i, "upsample%d_seg" % i, "upsample%d_seg.2" % i,
                         "upsample%d_seg.1.weight" % i)
         self._fc_bwd("fc_seg", need_w, pg)
+        self.tape.aux.join()
         dz = None
         if needs[0] and self.x0.grad is not None:
             dz = self.x0.grad.view(self.x0.N, self.x0.C)[:, :self.K]
@@ -374,9 +375,12 @@ class TrunkRunner:
             lin = getattr(self.G, name)[0]
             C = lin.weight.shape[0] // 16
             perm = self._fc_maps(C, lin.weight.device)
-            dw = torch.empty_like(lin.weight)
-            ops.scatter_rows_f32(fc.dwt, perm, dw, fc.npad, lin.weight.shape[1])
-            pg[name + ".0.weight"] = dw
+
+            def scatter():      # after the weight-gradient GEMM, on the same branch
+                dw = torch.empty_like(lin.weight)
+                ops.scatter_rows_f32(fc.dwt, perm, dw, fc.npad, lin.weight.shape[1])
+                pg[name + ".0.weight"] = dw
+            self.tape.aux.run(scatter)
 
 
 def _alias(t, N, H, W, C):

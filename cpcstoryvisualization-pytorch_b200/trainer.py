@@ -113,10 +113,17 @@ _DETACHED_STREAMS = {}
 _DETACHED_OPEN = [0]    # detached branches issued and not yet joined
 
 
-def _side_streams(pool, dev, n):
+HIGH_PRIORITY = -1      # CUDA: numerically lower = scheduled first
+# priority of the detached generator forward.  Measured on B200 (profiles/r01_schedule_notes.md):
+# a lower priority (0) stretches it across the whole discriminator update, but the tensor-core
+# GEMMs of both then interleave and the step is 0.3 ms slower than with equal priorities.
+LOW_PRIORITY = -1
+
+
+def _side_streams(pool, dev, n, priority=HIGH_PRIORITY):
     streams = pool.setdefault(dev, [])
     while len(streams) < n:
-        streams.append(torch.cuda.Stream(device=dev))
+        streams.append(torch.cuda.Stream(device=dev, priority=priority))
     return streams[:n]
 
 
@@ -157,7 +164,9 @@ class Detached:
             self.results = [t() for t in thunks]
             return
         main = torch.cuda.current_stream()
-        self.streams = _side_streams(_DETACHED_STREAMS, main.device, len(thunks))
+        # detached work is filler: whatever the issuing stream does meanwhile (on a high-priority
+        # stream, see step_stream) gets the SMs first at every kernel boundary
+        self.streams = _side_streams(_DETACHED_STREAMS, main.device, len(thunks), LOW_PRIORITY)
         self.results = []
         _DETACHED_OPEN[0] += 1
         for st, t in zip(self.streams, thunks):
@@ -177,6 +186,12 @@ class Detached:
             knets.sync_point(self.streams, reset_state_order=_DETACHED_OPEN[0] == 0)
             self.streams = []
         return self.results
+
+
+def step_stream(device=None):
+    """a high-priority stream to run (or capture) train_step on: the detached generator forward
+    then runs at lower priority than the step's critical path"""
+    return torch.cuda.Stream(device=device, priority=HIGH_PRIORITY)
 
 
 def stage_discriminators(nets, x, labels, early_generator=False):
