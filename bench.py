@@ -167,7 +167,8 @@ def run_reference_arm(args):
 class StepEngine:
     """The public train_step API around static device buffers, optionally as one CUDA graph."""
 
-    def __init__(self, p, device, use_graph, grad_sync):
+    def __init__(self, p, device, use_graph, grad_sync, segmented=False):
+        self.segmented = segmented
         from miscc.config import cfg
         apply_cfg(cfg, p)
         import miscc.utils as mu
@@ -209,24 +210,32 @@ class StepEngine:
     # --- the step in three segments, with the NCCL gradient exchange between them ------------
     def _seg_d(self):
         self._x = self.trainer.prepare_inputs(self.dev_st, self.dev_im)
-        self._out = self.trainer.stage_discriminators(self.nets, self._x, self.labels)
+        self._out = self.trainer.stage_discriminators(self.nets, self._x, self.labels,
+                                                      early_generator=self.trainer.EARLY_G)
+        if "early_generator" in self._out:
+            self._out["early_generator"].join()      # every branch joins before the segment ends
 
     def _seg_g(self):
         for k in self.trainer.D_NETS:
             self.opts[k].step()
-        self._out.update(self.trainer.stage_generator(self.nets, self._x, self.labels, 1.0))
+        self._out.update(self.trainer.stage_generator(self.nets, self._x, self.labels, 1.0,
+                                                      forward=self._out.pop("early_generator", None)))
 
     def _seg_opt(self):
         self.opts["G"].step()
         self.loss_dev.copy_(torch.stack([self._out[k].reshape(()) for k in self.loss_keys]))
 
     def capture(self):
-        """Single-GPU: the whole step is ONE CUDA graph.  Multi-GPU: three graphs with the two
-        NCCL all-reduces issued eagerly between them (collectives are kept out of the capture)."""
+        """The whole step is ONE CUDA graph; with N > 1 the two NCCL gradient all-reduces are
+        captured inside it.  ``--segmented``: three graphs with the all-reduces issued eagerly
+        between them (collectives kept out of the capture)."""
         self.knets.invalidate_weight_cache()
-        if self.grad_sync is None:
+        if not self.segmented:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=self.trainer.step_stream(self.device)):
+            kw = {}
+            if self.grad_sync is not None and self.grad_sync.enabled:
+                kw["capture_error_mode"] = "thread_local"   # the NCCL watchdog thread keeps running
+            with torch.cuda.graph(self.graph, stream=self.trainer.step_stream(self.device), **kw):
                 self._step_body()
             return
         self.graphs = []
@@ -242,7 +251,7 @@ class StepEngine:
     def step(self):
         if self.graph is None:
             self._step_body()
-        elif self.grad_sync is None:
+        elif not self.segmented:
             self.graph.replay()
         else:
             self.graphs[0].replay()
@@ -313,13 +322,20 @@ def main():
     ap.add_argument("--impl", default="cpcsv_b200")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--whole-graph", action="store_true",
+                    help="N > 1: capture the NCCL all-reduces inside ONE step graph (experimental)")
     ap.add_argument("--segmented", action="store_true",
-                    help="single GPU: use the three-graph multi-GPU step structure (for testing)")
+                    help="three CUDA graphs with the gradient all-reduces issued eagerly between them "
+                         "instead of one graph that contains them")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
     args.warmup = max(args.warmup, 3)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.whole_graph:
+        # capturing the NCCL all-reduces inside the one-graph step hung on the 2-GPU box (r01):
+        # multi-GPU runs use the three-graph step with the collectives between the graphs
+        args.segmented = True
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -336,7 +352,7 @@ def main():
     grad_sync = trainer.GradSync() if world > 1 else None
     if args.segmented and world == 1:
         grad_sync = trainer.GradSync(enabled=False)
-    eng = StepEngine(p, device, use_graph=not args.no_graph, grad_sync=grad_sync)
+    eng = StepEngine(p, device, use_graph=not args.no_graph, grad_sync=grad_sync, segmented=args.segmented)
 
     # warm-up (eager: builds caches, sets kernel attributes), then capture
     side = torch.cuda.Stream()

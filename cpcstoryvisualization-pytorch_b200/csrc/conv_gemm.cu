@@ -31,6 +31,13 @@ constexpr int kMaxStages = 8;
 constexpr int kAPlaneBytes = kBlockM * 128;  // 128 rows x 64 16-bit (mode 0) / 2 x [64 pix x 64 ch] (mode 1)
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarrierBytes = 256;
+// Epilogue staging: each epilogue warp transposes its 32 rows x 32 columns through shared memory
+// so that global stores / red.adds cover whole 128 B row segments (4 rows per instruction)
+// instead of 32 different rows per instruction.  Row pitch 36 floats: conflict-free for the
+// row-per-lane v4 writes and for the 8-lanes-per-row v4 reads.
+constexpr int kEpiPitch = 36;
+constexpr int kEpiWarpFloats = 32 * kEpiPitch;
+constexpr int kEpiBytes = 4 * kEpiWarpFloats * 4;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;  // columns between the two accumulator stages
 
@@ -92,6 +99,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + P.stages * P.stage_bytes + kBarrierBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -222,6 +230,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ------------------------------------------------------------------ epilogue (4 warps)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
+    float* stg = epi_stage + q * kEpiWarpFloats;
+    const int sub = lane >> 3;  // coalesced phase: this lane stores rows 4 * i + sub ...
+    const int cq = lane & 7;    // ... columns [4 * cq, 4 * cq + 4) of the 32-column chunk
     uint32_t acc = 0, acc_phase = 0;
     const float alpha = P.alpha ? __ldg(P.alpha) : 1.0f;
     const bool atomic = (P.accumulate != 0) || (P.splits > 1);
@@ -244,40 +255,77 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         row_valid = m < P.m_valid;
         row_ptr = P.out + P.taps[tc.group].out_off + static_cast<int64_t>(m) * P.ldc;
       }
+      // output rows this lane writes in the coalesced phase (owned by lane 4 * i + sub)
+      float* rp[8];
+      uint32_t rv = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int src = 4 * i + sub;
+        rp[i] = reinterpret_cast<float*>(
+            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(row_ptr), src));
+        rv |= (__shfl_sync(0xffffffffu, row_valid ? 1u : 0u, src) & 1u) << i;
+      }
       const int32_t col0 = tc.n_idx * P.block_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
       for (int32_t c0 = 0; c0 < P.block_n; c0 += 32) {
-        uint32_t r[32];
-        int width = 32;
         if (P.block_n - c0 >= 32) {
+          uint32_t r[32];
           tmem_ld_32x32(taddr + c0, r);
-        } else {
-          uint32_t r16[16];
-          tmem_ld_32x16(taddr + c0, r16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = r16[j];
-          width = 16;
-        }
-        tmem_ld_wait();
-        if (row_valid) {
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const int32_t col = col0 + c0 + j;
-            if (j < width && col < P.n_valid) {
-              float4 v;
-              v.x = __uint_as_float(r[j]) * alpha;
-              v.y = __uint_as_float(r[j + 1]) * alpha;
-              v.z = __uint_as_float(r[j + 2]) * alpha;
-              v.w = __uint_as_float(r[j + 3]) * alpha;
-              float* dst = row_ptr + col;
-              if (atomic) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x),
-                             "f"(v.y), "f"(v.z), "f"(v.w)
-                             : "memory");
-              } else {
-                *reinterpret_cast<float4*>(dst) = v;
+            float4 v;
+            v.x = __uint_as_float(r[j]) * alpha;
+            v.y = __uint_as_float(r[j + 1]) * alpha;
+            v.z = __uint_as_float(r[j + 2]) * alpha;
+            v.w = __uint_as_float(r[j + 3]) * alpha;
+            *reinterpret_cast<float4*>(stg + lane * kEpiPitch + j) = v;
+          }
+          __syncwarp();
+          const int32_t col = col0 + c0 + 4 * cq;
+          if (col < P.n_valid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if ((rv >> i) & 1u) {
+                const float4 v =
+                    *reinterpret_cast<const float4*>(stg + (4 * i + sub) * kEpiPitch + 4 * cq);
+                float* dst = rp[i] + col;
+                if (atomic) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst),
+                               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                               : "memory");
+                } else {
+                  *reinterpret_cast<float4*>(dst) = v;
+                }
+              }
+            }
+          }
+          __syncwarp();
+        } else {
+          // 16-column tail (narrow heads): one row per lane
+          uint32_t r16[16];
+          tmem_ld_32x16(taddr + c0, r16);
+          tmem_ld_wait();
+          if (row_valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const int32_t col = col0 + c0 + j;
+              if (col < P.n_valid) {
+                float4 v;
+                v.x = __uint_as_float(r16[j]) * alpha;
+                v.y = __uint_as_float(r16[j + 1]) * alpha;
+                v.z = __uint_as_float(r16[j + 2]) * alpha;
+                v.w = __uint_as_float(r16[j + 3]) * alpha;
+                float* dst = row_ptr + col;
+                if (atomic) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst),
+                               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                               : "memory");
+                } else {
+                  *reinterpret_cast<float4*>(dst) = v;
+                }
               }
             }
           }
@@ -425,11 +473,12 @@ extern "C" int cpcsv_conv_gemm(const cpcsv_gemm_t* job, cpcsv_stream_t stream_) 
                        static_cast<uint32_t>(J.block_n));
   P.b_plane_bytes = J.block_n * 128;
   P.stage_bytes = J.planes * (kAPlaneBytes + P.b_plane_bytes);
-  int stages = (kSmemLimit - 1024 - kBarrierBytes) / P.stage_bytes;
+  int stages = (kSmemLimit - 1024 - kBarrierBytes - kEpiBytes) / P.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   CPCSV_REQUIRE(stages >= 2, "conv_gemm: tile does not fit shared memory");
   P.stages = stages;
-  const size_t smem_bytes = static_cast<size_t>(stages) * P.stage_bytes + 1024 + kBarrierBytes;
+  const size_t smem_bytes =
+      static_cast<size_t>(stages) * P.stage_bytes + 1024 + kBarrierBytes + kEpiBytes;
 
   CUtensorMap tmA[2], tmB[2];
   uint32_t boxA[5], boxB[5];

@@ -31,24 +31,41 @@ from cpcsv_b200 import nets as knets
 
 
 class GradSync:
-    """Average gradients across ranks: one flat NCCL all-reduce per network per step."""
+    """Average gradients across ranks: per network ONE copy of its gradients into a flat buffer
+    (a single multi-tensor launch), ONE all-reduce (NCCL: averaging inside the collective), and
+    the parameters' ``.grad`` re-pointed at slices of the reduced buffer (no copy back).
+    Capturable into the step's CUDA graph together with the kernels around it."""
+
+    ALIGN = 64      # elements: every slice starts 256-byte aligned (vectorised optimiser loads)
 
     def __init__(self, enabled=None):
         self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
             if enabled is None else enabled
         self.world = dist.get_world_size() if self.enabled else 1
+        self.avg_in_collective = self.enabled and dist.is_initialized() and dist.get_backend() == "nccl"
 
     def __call__(self, params):
         if not self.enabled:
             return
-        grads = [p.grad for p in params if p.grad is not None]
-        if not grads:
+        owners = [p for p in params if p.grad is not None]
+        if not owners:
             return
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat)
-        flat.div_(self.world)
-        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g.copy_(f)
+        grads = [p.grad for p in owners]
+        offs, total = [], 0
+        for g in grads:
+            offs.append(total)
+            total += (g.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        flat = torch.zeros(total, device=grads[0].device, dtype=grads[0].dtype)
+        views = [flat[o:o + g.numel()].view(g.shape) for o, g in zip(offs, grads)]
+        torch._foreach_copy_(views, grads)
+        if self.world > 1:
+            if self.avg_in_collective:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(flat)
+                flat.div_(self.world)
+        for p, v in zip(owners, views):
+            p.grad = v
 
 
 def build_networks(video_len=None):
