@@ -18,6 +18,10 @@ import sys
 import threading
 import time
 
+# the step forks into many parallel stream branches; must be set before CUDA initialises
+# (see cpcsv_b200/__init__.py)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "cpcstoryvisualization-pytorch_b200")
 for _p in (ROOT, PKG):
@@ -296,8 +300,8 @@ def profile_gemm_launches(engine, steps):
     # one stream: a launch's event pair then brackets that kernel alone (with the step's
     # concurrent branches the second event would also wait for kernels of other streams)
     tr = engine.trainer
-    flags = (tr.CONCURRENT_D, tr.CONCURRENT_G, tr.EARLY_G)
-    tr.CONCURRENT_D = tr.CONCURRENT_G = tr.EARLY_G = False
+    flags = (tr.CONCURRENT_D, tr.CONCURRENT_G, tr.EARLY_G, tr.streams.ENABLED)
+    tr.CONCURRENT_D = tr.CONCURRENT_G = tr.EARLY_G = tr.streams.ENABLED = False
     ops.conv_gemm = timed
     try:
         for i in range(steps + 1):
@@ -307,7 +311,7 @@ def profile_gemm_launches(engine, steps):
         torch.cuda.synchronize()
     finally:
         ops.conv_gemm = orig
-        tr.CONCURRENT_D, tr.CONCURRENT_G, tr.EARLY_G = flags
+        tr.CONCURRENT_D, tr.CONCURRENT_G, tr.EARLY_G, tr.streams.ENABLED = flags
     ms = sum(a.elapsed_time(b) for a, b, _ in recs)
     fl = sum(f for _, _, f in recs)
     return {"launches_per_step": len(recs) / steps, "gemm_ms_per_step": ms / steps,

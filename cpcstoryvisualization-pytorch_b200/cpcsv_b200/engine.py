@@ -207,6 +207,12 @@ def prefetch_conv(cache, w, geom, forward=True, backward=True):
         pack_conv(cache, w, geom, bkind, Ci_pad, Co_pad, 1, BF16)
 
 
+def prefetch_conv_nograd(cache, w, geom):
+    """the single-plane fp16 forward taps a no-grad generator call uses"""
+    Co_pad, Ci_pad = rup(w.shape[0], 64), rup(w.shape[1], 64)
+    pack_conv(cache, w, geom, CONV_GEOM[geom][1], Co_pad, Ci_pad, 1, ops.FP16)
+
+
 class ConvNode:
     """3x3 s1 / nearest-x2+3x3 / 4x4 s2 convolution, optionally spectrally normalised
     (weight = weight_orig / sigma applied as the epilogue scalar alpha)."""
@@ -300,12 +306,16 @@ class SpectralNorm:
         w2d = w_orig.detach().view(R, -1)
         sig = _e((2,), dev)
         scratch = _e((R + w2d.shape[1],), dev)
+        # u / v are updated in place once per call: calls of the same module that run on parallel
+        # streams (real / fake / wrong-pair passes) iterate in issue order
+        StateOrder.before(self.u)
         ops.spectral_sigma(w2d, self.u, self.v, training, sig[0:1], sig[1:2], scratch)
         if need_grad:
             # one cat kernel instead of two clone()s: device-to-device memcpy NODES of parallel
             # CUDA-graph branches execute in one shared order (like memset nodes), kernels do not
             uv = torch.cat((self.u.detach().reshape(-1), self.v.detach().reshape(-1)))
             self.saved = (uv[:R], uv[R:], sig)
+        StateOrder.after(self.u)
         return sig[1:2]
 
     def backward(self, g, w_orig):

@@ -106,58 +106,74 @@ class BatchNorm1dFn(torch.autograd.Function):
         return dx[:, :C], dgamma, dbeta, None, None, None, None, None
 
 
-class GRUCellFn(torch.autograd.Function):
-    """torch.nn.GRUCell semantics, gate order (r, z, n)."""
+class GRUSeqFn(torch.autograd.Function):
+    """T steps of torch.nn.GRUCell (gate order r, z, n) over a known input sequence.
+
+    x_all [T, B, I], h0 [B, H] -> h_all [T, B, H].  The input projections of all steps are ONE
+    GEMM (they do not depend on the recurrence); each step is then one recurrent GEMM + one gate
+    kernel.  Backward: per step one gate kernel + one GEMM for the carried dh; the weight / bias /
+    input gradients are single GEMMs over all T*B rows after the loop."""
 
     @staticmethod
-    def forward(ctx, x, h, w_ih, w_hh, b_ih, b_hh):
-        x, h = _rowmat(x), _c(h)
-        B, H = h.shape
-        dev = x.device
-        gi = torch.empty(B, 3 * H, device=dev)
+    def forward(ctx, x_all, h0, w_ih, w_hh, b_ih, b_hh):
+        T, B, I = x_all.shape
+        H = h0.shape[1]
+        dev = x_all.device
+        x2 = _c(x_all).view(T * B, I)
+        gi = torch.empty(T * B, 3 * H, device=dev)
+        ops.linear_f32(x2, w_ih, b_ih, gi)
+        # rows [0, B) of h_in hold h0, rows of step t+1 hold h_t: h_in[:T*B] are the step inputs
+        h_in = torch.empty((T + 1) * B, H, device=dev)
+        h_in[:B].copy_(h0)
+        save = torch.empty(T * B, 4 * H, device=dev)
         gh = torch.empty(B, 3 * H, device=dev)
-        ops.linear_f32(x, w_ih, b_ih, gi)
-        ops.linear_f32(h, w_hh, b_hh, gh)
-        hnew = torch.empty(B, H, device=dev)
-        save = torch.empty(B, 4 * H, device=dev)
-        ops.gru_gates_fwd(gi, gh, h, hnew, save)
-        ctx.save_for_backward(x, h, w_ih, w_hh, save)
-        return hnew
+        for t in range(T):
+            hp = h_in[t * B:(t + 1) * B]
+            ops.linear_f32(hp, w_hh, b_hh, gh)
+            ops.gru_gates_fwd(gi[t * B:(t + 1) * B], gh, hp, h_in[(t + 1) * B:(t + 2) * B],
+                              save[t * B:(t + 1) * B])
+        ctx.save_for_backward(x2, h_in, w_ih, w_hh, save)
+        ctx.dims = (T, B, I, H)
+        return h_in[B:].view(T, B, H)
 
     @staticmethod
-    def backward(ctx, dhn):
-        x, h, w_ih, w_hh, save = ctx.saved_tensors
-        B, H = h.shape
-        dev = x.device
-        dhn = _c(dhn)
-        dgi = torch.empty(B, 3 * H, device=dev)
-        dgh = torch.empty(B, 3 * H, device=dev)
-        dh = torch.empty(B, H, device=dev)
-        ops.gru_gates_bwd(dhn, h, save, dgi, dgh, dh)
+    def backward(ctx, dh_all):
+        x2, h_in, w_ih, w_hh, save = ctx.saved_tensors
+        T, B, I, H = ctx.dims
+        dev = x2.device
+        dh_all = _c(dh_all)
+        dgi = torch.empty(T * B, 3 * H, device=dev)
+        dgh = torch.empty(T * B, 3 * H, device=dev)
+        dh = None          # gradient carried into h_{t-1}
+        for t in range(T - 1, -1, -1):
+            dhn = dh_all[t] if dh is None else dh_all[t] + dh
+            dh = torch.empty(B, H, device=dev)
+            ops.gru_gates_bwd(dhn, h_in[t * B:(t + 1) * B], save[t * B:(t + 1) * B],
+                              dgi[t * B:(t + 1) * B], dgh[t * B:(t + 1) * B], dh)
+            if t > 0 or ctx.needs_input_grad[1]:
+                ops.linear_nn_f32(dgh[t * B:(t + 1) * B], w_hh, dh, accumulate=True)
         dx = dwi = dwh = dbi = dbh = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty(x.shape, device=dev)
+            dx = torch.empty(T * B, I, device=dev)
             ops.linear_nn_f32(dgi, w_ih, dx)
-        if ctx.needs_input_grad[1]:
-            ops.linear_nn_f32(dgh, w_hh, dh, accumulate=True)
-        else:
-            dh = None
+            dx = dx.view(T, B, I)
         if ctx.needs_input_grad[2]:
             dwi = torch.empty(w_ih.shape, device=dev)
-            ops.linear_tn_f32(dgi, x, dwi)
+            ops.linear_tn_f32(dgi, x2, dwi)
         if ctx.needs_input_grad[3]:
             dwh = torch.empty(w_hh.shape, device=dev)
-            ops.linear_tn_f32(dgh, h, dwh)
-        ones = torch.ones(B, 1, device=dev)
-        if ctx.needs_input_grad[4]:
-            dbi = torch.empty(3 * H, 1, device=dev)
-            ops.linear_tn_f32(dgi, ones, dbi)
-            dbi = dbi.view(-1)
-        if ctx.needs_input_grad[5]:
-            dbh = torch.empty(3 * H, 1, device=dev)
-            ops.linear_tn_f32(dgh, ones, dbh)
-            dbh = dbh.view(-1)
-        return dx, dh, dwi, dwh, dbi, dbh
+            ops.linear_tn_f32(dgh, h_in[:T * B], dwh)
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+            ones = torch.ones(T * B, 1, device=dev)
+            if ctx.needs_input_grad[4]:
+                dbi = torch.empty(3 * H, 1, device=dev)
+                ops.linear_tn_f32(dgi, ones, dbi)
+                dbi = dbi.view(-1)
+            if ctx.needs_input_grad[5]:
+                dbh = torch.empty(3 * H, 1, device=dev)
+                ops.linear_tn_f32(dgh, ones, dbh)
+                dbh = dbh.view(-1)
+        return dx, (dh if ctx.needs_input_grad[1] else None), dwi, dwh, dbi, dbh
 
 
 class CondAugFn(torch.autograd.Function):
@@ -210,6 +226,11 @@ def batch_norm_1d(x, bn, act_tanh=False):
                                bn.num_batches_tracked, bn.training, act_tanh)
 
 
+def gru_sequence(x_all, h0, cell):
+    """cell: nn.GRUCell holder module; x_all [T, B, I], h0 [B, H] -> h_all [T, B, H]."""
+    return GRUSeqFn.apply(x_all, h0, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)
+
+
 def gru_cell(x, h, cell):
-    """cell: nn.GRUCell holder module."""
-    return GRUCellFn.apply(x, h, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)
+    """one step (torch.nn.GRUCell semantics)"""
+    return gru_sequence(x.unsqueeze(0), h, cell)[0]

@@ -56,10 +56,66 @@ def _conv_weights(module):
     return out
 
 
+def fc_maps(G, C, dev):
+    """fc emits feature j = c*16 + p (``view(-1, C, 4, 4)``, model.py:379); the trunk wants NHWC
+    order j' = p*Cp + c with Cp = C rounded up to 64.  perm[j'] = j, or -1 for the padding
+    channels (zero weight rows, zero BN scale)."""
+    key = ("fcperm", C, str(dev))
+    m = G._cpcsv_maps.get(key)
+    if m is None:
+        Cp = rup(C, 64)
+        jp = torch.arange(16 * Cp, device=dev)
+        c, p = jp % Cp, jp // Cp
+        m = torch.where(c < C, c * 16 + p, torch.full_like(jp, -1)).to(torch.int32)
+        G._cpcsv_maps[key] = m
+    return m
+
+
+def pack_fc_fwd(cache, G, lin, C, Kp, planes, dtype):
+    """(cached) operand planes [16*Cp, Kp] of fc / fc_seg for the forward GEMM (rows re-ordered to NHWC)"""
+    w = lin.weight
+    K, Cp = w.shape[1], rup(C, 64)
+    perm = fc_maps(G, C, w.device)
+
+    def build():
+        t16 = ops.TORCH16[dtype]
+        hi = _e((16 * Cp, Kp), w.device, t16)
+        lo = _e((16 * Cp, Kp), w.device, t16) if planes == 2 else None
+        ops.pack_matrix(w.detach(), 16 * Cp, Kp, K, K, 1, perm, hi, lo, dtype)
+        return [hi, lo]
+    return cache.get((id(w), "fc_fwd", planes, dtype), w, build)
+
+
+def pack_fc_bwd(cache, G, lin, C, Kp):
+    """(cached) transposed bf16 plane [Kp, 16*Cp] for the data-gradient GEMM"""
+    w = lin.weight
+    K, Cp = w.shape[1], rup(C, 64)
+    perm = fc_maps(G, C, w.device)
+
+    def build():
+        hi = _e((Kp, 16 * Cp), w.device, torch.bfloat16)
+        # out[r = k, c = j'] = w[perm[j'], k]
+        ops.pack_matrix(w.detach(), Kp, 16 * Cp, 16 * Cp, 1, K, _row_pad_map(K, Kp, w.device), hi, None,
+                        col_map=perm)
+        return hi
+    return cache.get((id(w), "fc_bwd", 1), w, build)
+
+
+def _prefetch_fc(G, no_grad_forward, forward, backward):
+    for lin, C in ((G.fc[0], G.gf_dim), (G.fc_seg[0], G.gf_dim_seg)):
+        Kp = rup(lin.weight.shape[1], 64)
+        if no_grad_forward:
+            pack_fc_fwd(_CACHE, G, lin, C, Kp, 1, ops.FP16)
+        if forward:
+            pack_fc_fwd(_CACHE, G, lin, C, Kp, 2, ops.BF16)
+        if backward:
+            pack_fc_bwd(_CACHE, G, lin, C, Kp)
+
+
 _PREFETCH_STREAMS = {}
 
 
-def prefetch_weights(modules, forward=True, backward=True):
+def prefetch_weights(modules, forward=True, backward=True, no_grad_forward=False):
     """Re-pack the conv weights of `modules` (StoryGAN / discriminators) into their bf16 operand
     planes on a side stream, concurrently with whatever the current stream does next; consumers
     synchronise through the cache entries' events.  Returns a handle for ``join_prefetch`` (call
@@ -73,9 +129,21 @@ def prefetch_weights(modules, forward=True, backward=True):
         side = _PREFETCH_STREAMS[main.device] = torch.cuda.Stream(device=main.device, priority=-1)
     side.wait_stream(main)
     with torch.cuda.stream(side):
-        for m in mods:
-            for w, geom in _conv_weights(m):
-                engine.prefetch_conv(_CACHE, w, geom, forward, backward)
+        # in the order the step consumes them: no-grad generator pass, forward planes, backward planes
+        gens = [m for m in mods if hasattr(m, "fc_seg")]
+        if no_grad_forward:
+            for G in gens:
+                _prefetch_fc(G, True, False, False)
+                for w, geom in _conv_weights(G):
+                    engine.prefetch_conv_nograd(_CACHE, w, geom)
+        for fwd, bwd in ((forward, False), (False, backward)):
+            if not (fwd or bwd):
+                continue
+            for m in mods:
+                if m in gens:
+                    _prefetch_fc(m, False, fwd, bwd)
+                for w, geom in _conv_weights(m):
+                    engine.prefetch_conv(_CACHE, w, geom, fwd, bwd)
     return side
 
 
@@ -144,46 +212,12 @@ class TrunkRunner:
         return TapeFn.apply(self, zmc_all, *[self.params[n] for n in self.names])
 
     # ---------------------------------------------------------------- helpers
-    def _fc_maps(self, C, dev):
-        """fc emits feature j = c*16 + p (``view(-1, C, 4, 4)``, model.py:379); the trunk wants
-        NHWC order j' = p*Cp + c with Cp = C rounded up to 64.  perm[j'] = j, or -1 for the
-        padding channels (zero weight rows, zero BN scale)."""
-        key = ("fcperm", C, str(dev))
-        m = self.G._cpcsv_maps.get(key)
-        if m is None:
-            Cp = rup(C, 64)
-            jp = torch.arange(16 * Cp, device=dev)
-            c, p = jp % Cp, jp // Cp
-            m = torch.where(c < C, c * 16 + p, torch.full_like(jp, -1)).to(torch.int32)
-            self.G._cpcsv_maps[key] = m
-        return m
-
     def _fc_node(self, tape, x0, lin, C, name):
-        w = lin.weight
-        K, Kp = w.shape[1], x0.C
-        Cp = rup(C, 64)
-        perm = self._fc_maps(C, w.device)
-        cache = tape.cache
-
-        def pack_fwd(planes, dtype):
-            def build():
-                t16 = ops.TORCH16[dtype]
-                hi = _e((16 * Cp, Kp), w.device, t16)
-                lo = _e((16 * Cp, Kp), w.device, t16) if planes == 2 else None
-                ops.pack_matrix(w.detach(), 16 * Cp, Kp, K, K, 1, perm, hi, lo, dtype)
-                return [hi, lo]
-            return cache.get((id(w), "fc_fwd", planes, dtype), w, build)
-
-        def pack_bwd():
-            def build():
-                hi = _e((Kp, 16 * Cp), w.device, torch.bfloat16)
-                # out[r = k, c = j'] = w[perm[j'], k]
-                ops.pack_matrix(w.detach(), Kp, 16 * Cp, 16 * Cp, 1, K, _row_pad_map(K, Kp, w.device), hi,
-                                None, col_map=perm)
-                return hi
-            return cache.get((id(w), "fc_bwd", 1), w, build)
-
-        node = GemmNode(tape, x0, 16 * Cp, pack_fwd, pack_bwd, name)
+        G, Kp = self.G, x0.C
+        perm = fc_maps(G, C, lin.weight.device)
+        node = GemmNode(tape, x0, 16 * rup(C, 64),
+                        lambda planes, dtype: pack_fc_fwd(tape.cache, G, lin, C, Kp, planes, dtype),
+                        lambda: pack_fc_bwd(tape.cache, G, lin, C, Kp), name)
         return node, perm
 
     # ---------------------------------------------------------------- forward
@@ -257,35 +291,30 @@ class TrunkRunner:
         tape.finish_forward()
         return img, seg
 
-    def _head_pack(self, w, kind, planes=2, dtype=ops.BF16):
-        """3x3 head conv with 3 / 1 output channels.  kind 'fwd': [9 * 16, Ci] tap-major K-major;
-        kind 'bwd': [Ci, 64] with column tap*Co + co (the im2col'd-gradient GEMM)."""
+    def _head_pack(self, w):
+        """3x3 head conv weight as the B operand of the im2col'd-gradient GEMM: [Ci_pad, 64] with
+        column tap*Co + co"""
         Co, Ci = w.shape[0], w.shape[1]
         Cip = rup(Ci, 64)
 
         def build():
-            if kind == "fwd":
-                t16 = ops.TORCH16[dtype]
-                hi = _e((9 * 16, Cip), w.device, t16)
-                lo = _e((9 * 16, Cip), w.device, t16) if planes == 2 else None
-                ops.pack_conv_weight(w.detach(), 0, 16, Cip, hi, lo, dtype)
-                return [hi, lo]
             w2 = w.detach().permute(1, 2, 3, 0).reshape(Ci, 9 * Co).contiguous()   # [ci, tap*Co+co]
             hi = _e((Cip, 64), w.device, torch.bfloat16)
-            rmap = None
-            ops.pack_matrix(w2, Cip, 64, 9 * Co, 9 * Co, 1, rmap, hi, None) if Cip == Ci else \
-                ops.pack_matrix(w2, Cip, 64, 9 * Co, 9 * Co, 1, _row_pad_map(Ci, Cip, w.device), hi, None)
+            ops.pack_matrix(w2, Cip, 64, 9 * Co, 9 * Co, 1, None if Cip == Ci else _row_pad_map(Ci, Cip, w.device),
+                            hi, None)
             return hi
-        return _CACHE.get((id(w), "head_" + kind, planes, dtype), w, build)
+        return _CACHE.get((id(w), "head_bwd", 1, ops.BF16), w, build)
 
     def _head_fwd(self, a, w, Co, name):
+        """img / img_seg: direct conv3x3 + tanh kernel on the operand planes (HBM-bound; a GEMM with
+        3 or 1 output channels would re-read the activation once per tap)"""
         dev = a.hi.device
-        z = _e((a.N, a.H, a.W, 16), dev)
         tp = self.tape
-        ops.conv_gemm(conv.conv_s1_fwd(a.planes(tp.planes), self._head_pack(w, "fwd", tp.planes, tp.dtype), z, 3,
-                                       dtype=tp.dtype))
+        wd = w.detach()
+        if wd.shape[1] != a.C:                       # channel-padded activation: zero weight columns
+            wd = torch.nn.functional.pad(wd, (0, 0, 0, 0, 0, a.C - wd.shape[1]))
         y = _e((a.N, Co, a.H, a.W), dev)
-        ops.tanh_to_nchw(z.view(a.rows, 16), a.N, Co, a.H, a.W, y)
+        ops.head_conv_tanh_fwd(a.hi, a.lo if tp.planes == 2 else None, wd.contiguous(), y, tp.dtype)
         return y
 
     def _head_bwd(self, a, w, y, dy, need_w, pg, name):
@@ -297,7 +326,7 @@ class TrunkRunner:
         acc = a.grad is not None
         if not acc:
             a.grad = _e((a.N, a.H, a.W, a.C), dev)
-        ops.conv_gemm(conv.gemm_nt([col, None], [self._head_pack(w, "bwd"), None], a.grad.view(a.rows, a.C),
+        ops.conv_gemm(conv.gemm_nt([col, None], [self._head_pack(w), None], a.grad.view(a.rows, a.C),
                                    accumulate=acc))
         if need_w:
             def wgrad():
@@ -374,7 +403,7 @@ class TrunkRunner:
         if need_w:
             lin = getattr(self.G, name)[0]
             C = lin.weight.shape[0] // 16
-            perm = self._fc_maps(C, lin.weight.device)
+            perm = fc_maps(self.G, C, lin.weight.device)
 
             def scatter():      # after the weight-gradient GEMM, on the same branch
                 dw = torch.empty_like(lin.weight)

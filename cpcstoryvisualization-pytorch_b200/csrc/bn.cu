@@ -596,14 +596,17 @@ bn_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ dy, i
   }
 }
 
+constexpr int kCoopBlocksPerSm = 1;
+
 // co-resident grid for a cooperative launch
 template <typename K>
 inline Tiling coop_tiling(K kernel, int64_t rows, int C) {
-  static int per_sm = 0;
-  int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0);
-  if (occ < 1) occ = 1;
-  per_sm = occ > 4 ? 4 : occ;
+  // ONE block per SM: a cooperative grid only starts when all of its blocks fit at once, next to
+  // whatever else is resident.  Sized to fill the machine (4 blocks / SM) these launches could
+  // never overlap the persistent tensor-core GEMM of another branch (which leaves 27 KB of shared
+  // memory per SM) nor each other, and the step's parallel branches serialised on them.
+  (void)kernel;
+  const int per_sm = kCoopBlocksPerSm;
   // narrow channel blocks (<= 32 quads = 128 channels, 8 row lanes) so that even a [1440, 1024]
   // layer spreads over 8 x gy blocks; the tree sum between the two grid barriers is done by the
   // first row of blocks while the rest of the grid waits, so the partial count stays <= 128

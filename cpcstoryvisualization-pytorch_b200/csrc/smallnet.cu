@@ -7,36 +7,47 @@ namespace cpcsv {
 
 // C[m][n] (+)= sum_k A(m,k) * B(n,k) + bias[n], with A(m,k) = A[m*sam + k*sak] and
 // B(n,k) = B[n*sbn + k*sbk].  32x32 output tile, 256 threads (4 outputs each), K step 32.
+// These GEMMs have a handful of output tiles and are latency-bound: the K range is split over
+// gridDim.z (partial sums combined with atomicAdd into a pre-zeroed / accumulated C) so the
+// whole chip works on one problem, and the next K tile is fetched into registers while the
+// current one is multiplied.
 __global__ void __launch_bounds__(256)
 sgemm_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                      const float* __restrict__ B, int64_t sbn, int64_t sbk,
                      const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N,
-                     int K, int accumulate) {
+                     int K, int accumulate, int k_chunk) {
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty in 0..7
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < K; k0 += 32) {
-    // load tiles: choose the thread->element mapping that is contiguous in memory
+  const int k_begin = blockIdx.z * k_chunk;
+  const int k_end = min(K, k_begin + k_chunk);
+  // thread -> tile element mapping that is contiguous in memory for either operand layout
+  const bool a_kfast = (sak == 1), b_kfast = (sbk == 1);
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = ty + 8 * i;
-      {
-        // A tile element (m = m0 + a_m, k = k0 + a_k)
-        const int a_m = (sak == 1) ? r : tx;
-        const int a_k = (sak == 1) ? tx : r;
-        const int m = m0 + a_m, k = k0 + a_k;
-        As[a_m][a_k] = (m < M && k < K) ? A[m * sam + k * sak] : 0.f;
-      }
-      {
-        const int b_n = (sbk == 1) ? r : tx;
-        const int b_k = (sbk == 1) ? tx : r;
-        const int n = n0 + b_n, k = k0 + b_k;
-        Bs[b_n][b_k] = (n < N && k < K) ? B[n * sbn + k * sbk] : 0.f;
-      }
+      const int a_m = a_kfast ? r : tx, a_k = a_kfast ? tx : r;
+      const int m = m0 + a_m, ka = k0 + a_k;
+      ra[i] = (m < M && ka < k_end) ? __ldg(A + m * sam + ka * sak) : 0.f;
+      const int b_n = b_kfast ? r : tx, b_k = b_kfast ? tx : r;
+      const int n = n0 + b_n, kb = k0 + b_k;
+      rb[i] = (n < N && kb < k_end) ? __ldg(B + n * sbn + kb * sbk) : 0.f;
+    }
+  };
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k_begin < k_end) fetch(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 8 * i;
+      As[a_kfast ? r : tx][a_kfast ? tx : r] = ra[i];
+      Bs[b_kfast ? r : tx][b_kfast ? tx : r] = rb[i];
     }
     __syncthreads();
+    if (k0 + 32 < k_end) fetch(k0 + 32);
 #pragma unroll 8
     for (int k = 0; k < 32; ++k) {
       const float b = Bs[tx][k];
@@ -47,17 +58,28 @@ sgemm_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
   }
   const int n = n0 + tx;
   if (n < N) {
-    const float bv = bias ? bias[n] : 0.f;
+    const float bv = (bias && blockIdx.z == 0) ? bias[n] : 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int m = m0 + ty + 8 * i;
       if (m < M) {
-        float v = acc[i] + bv;
+        const float v = acc[i] + bv;
         float* dst = C + static_cast<int64_t>(m) * ldc + n;
-        *dst = accumulate ? (*dst + v) : v;
+        if (gridDim.z > 1) {
+          atomicAdd(dst, v);
+        } else {
+          *dst = accumulate ? (*dst + v) : v;
+        }
       }
     }
   }
+}
+
+__global__ void zero_rows_kernel(float* __restrict__ C, int64_t ldc, int M, int N) {
+  const int64_t total = static_cast<int64_t>(M) * N;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    C[(i / N) * ldc + (i % N)] = 0.f;
 }
 
 static int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
@@ -65,8 +87,22 @@ static int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64
                  cudaStream_t stream, const char* what) {
   CPCSV_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "%s: args", what);
   dim3 grid(static_cast<unsigned>(ceil_div(N, 32)), static_cast<unsigned>(ceil_div(M, 32)));
+  // split K until ~2 CTAs per SM are busy, keeping >= 2 K tiles per split
+  const int64_t ctas = static_cast<int64_t>(grid.x) * grid.y;
+  const int ksteps = static_cast<int>(ceil_div(K, 32));
+  int splits = static_cast<int>(ceil_div(2 * num_sms(), ctas));
+  if (splits > ksteps / 2) splits = ksteps / 2;
+  if (splits < 1) splits = 1;
+  const int k_chunk = static_cast<int>(ceil_div(ksteps, splits)) * 32;
+  splits = static_cast<int>(ceil_div(K, k_chunk));
+  grid.z = static_cast<unsigned>(splits);
+  if (splits > 1 && !accumulate) {
+    int64_t zb = ceil_div(static_cast<int64_t>(M) * N, 256);
+    if (zb > 148) zb = 148;
+    zero_rows_kernel<<<static_cast<unsigned>(zb), 256, 0, stream>>>(C, ldc, M, N);
+  }
   sgemm_strided_kernel<<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, bias, C, ldc, M, N, K,
-                                                 accumulate);
+                                                 accumulate, k_chunk);
   return launched(what);
 }
 

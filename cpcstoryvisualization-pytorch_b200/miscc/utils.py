@@ -17,6 +17,14 @@ import torch.nn.functional as F
 from miscc.config import cfg  # noqa: F401
 
 SYNC_ACCURACY = True   # reference behaviour: .cpu().numpy() round trip per call (host sync)
+PARALLEL_PASSES = True  # real / fake (/ wrong-pair) passes of one discriminator on parallel CUDA streams
+
+
+def _parallel(*thunks):
+    """independent passes through the same discriminator on parallel streams; module state they
+    share (BatchNorm running statistics, spectral-norm u / v) is still updated in call order"""
+    from cpcsv_b200 import streams
+    return streams.concurrently(*thunks, enabled=PARALLEL_PASSES)
 
 
 def _call(module, *inputs):
@@ -42,12 +50,13 @@ def compute_discriminator_loss(netD, real_imgs, fake_imgs, real_labels, fake_lab
         raise NotImplementedError("uncond logits / sequence-consistency critic are disabled in cfg/final.yml")
     batch_size = real_imgs.size(0)
     cond = conditions.detach()
-    real_features = _call(netD, real_imgs)
-    fake_features = _call(netD, fake_imgs.detach())
+    real_features, fake_features = _parallel(lambda: _call(netD, real_imgs),
+                                             lambda: _call(netD, fake_imgs.detach()))
     head = netD.get_cond_logits
-    errD_real = F.binary_cross_entropy(_call(head, real_features, cond), real_labels)
-    errD_wrong = F.binary_cross_entropy(_call(head, real_features[:batch_size - 1], cond[1:]), fake_labels[1:])
-    errD_fake = F.binary_cross_entropy(_call(head, fake_features, cond), fake_labels)
+    errD_real, errD_wrong, errD_fake = _parallel(
+        lambda: F.binary_cross_entropy(_call(head, real_features, cond), real_labels),
+        lambda: F.binary_cross_entropy(_call(head, real_features[:batch_size - 1], cond[1:]), fake_labels[1:]),
+        lambda: F.binary_cross_entropy(_call(head, fake_features, cond), fake_labels))
     errD = errD_real + (errD_fake + errD_wrong) * 0.5
     acc = 0
     if netD.cate_classify is not None:

@@ -189,26 +189,23 @@ class StoryGAN(nn.Module):
 
     def sample_z_motion(self, motion_input, video_len=None):
         video_len = video_len if video_len is not None else self.video_len
-        h = self._lin_bn(self.m_net, self.get_gru_initial_state(motion_input.shape[0]))
-        outs = []
-        for t in range(video_len):
-            m_t = motion_input if motion_input.dim() == 2 else motion_input[:, t, :]
-            h = Fx.gru_cell(self.get_iteration_input(m_t), h, self.recurrent)
-            outs.append(h)
-        return torch.stack(outs, 1).reshape(-1, self.motion_dim)
+        h0 = self._lin_bn(self.m_net, self.get_gru_initial_state(motion_input.shape[0]))
+        # the step inputs (fresh noise | motion_t) do not depend on the recurrence: draw them in
+        # the reference's order, then run the whole sequence as one op
+        xs = [self.get_iteration_input(motion_input if motion_input.dim() == 2 else motion_input[:, t, :])
+              for t in range(video_len)]
+        h_all = Fx.gru_sequence(torch.stack(xs, 0), h0, self.recurrent)            # [T, B, H]
+        return h_all.transpose(0, 1).reshape(-1, self.motion_dim)
 
     def motion_content_rnn(self, motion_input, content_input):
-        h = self._lin_bn(self.c_net, content_input)
+        h0 = self._lin_bn(self.c_net, content_input)
         if motion_input.dim() == 2:
             motion_input = motion_input.unsqueeze(1)
             steps = 1
         else:
             steps = self.video_len
-        outs = []
-        for t in range(steps):
-            h = Fx.gru_cell(motion_input[:, t, :], h, self.mocornn)
-            outs.append(h)
-        return torch.stack(outs, 1).reshape(-1, self.content_dim)
+        h_all = Fx.gru_sequence(motion_input[:, :steps].transpose(0, 1), h0, self.mocornn)   # [T, B, H]
+        return h_all.transpose(0, 1).reshape(-1, self.content_dim)
 
     def _latent(self, motion_flat, crnn_code, zm_code, c_mu_rows):
         zmc_code = torch.cat((zm_code, c_mu_rows), dim=1)

@@ -28,6 +28,7 @@ from miscc.config import cfg
 from miscc.utils import (KL_loss, compute_discriminator_loss, compute_generator_loss, count_param,
                          mkdir_p, save_model, weights_init)
 from cpcsv_b200 import nets as knets
+from cpcsv_b200 import streams
 
 
 class GradSync:
@@ -125,90 +126,12 @@ D_NETS = ("D_se", "D_im", "D_st")
 CONCURRENT_D = True     # run the three discriminators on parallel CUDA streams
 CONCURRENT_G = True     # run sample_videos / sample_images of one phase on two streams
 EARLY_G = True          # issue the generator-update forward alongside the discriminator update
-_SIDE_STREAMS = {}
-_DETACHED_STREAMS = {}
-_DETACHED_OPEN = [0]    # detached branches issued and not yet joined
-
-
-HIGH_PRIORITY = -1      # CUDA: numerically lower = scheduled first
-# priority of the detached generator forward.  Measured on B200 (profiles/r01_schedule_notes.md):
-# a lower priority (0) stretches it across the whole discriminator update, but the tensor-core
-# GEMMs of both then interleave and the step is 0.3 ms slower than with equal priorities.
-LOW_PRIORITY = -1
-
-
-def _side_streams(pool, dev, n, priority=HIGH_PRIORITY):
-    streams = pool.setdefault(dev, [])
-    while len(streams) < n:
-        streams.append(torch.cuda.Stream(device=dev, priority=priority))
-    return streams[:n]
+step_stream = streams.step_stream
+Detached = streams.Detached
 
 
 def _concurrently(*thunks, enabled=None):
-    """Run independent pieces of the step on parallel CUDA streams (fork from / join into the
-    current stream; capturable into a CUDA graph as parallel branches).  Sequential on CPU or
-    when switched off."""
-    enabled = CONCURRENT_D if enabled is None else enabled
-    if not (enabled and torch.cuda.is_available() and len(thunks) > 1):
-        return [t() for t in thunks]
-    main = torch.cuda.current_stream()
-    streams = _side_streams(_SIDE_STREAMS, main.device, len(thunks) - 1)
-    results = [None] * len(thunks)
-    for st in streams:
-        st.wait_stream(main)
-    # issue order = list order (in-place module state shared by two pieces, e.g. the BatchNorm
-    # running statistics of two generator calls, is updated in that order: engine.StateOrder);
-    # the last piece runs on the current stream
-    for i, t in enumerate(thunks[:-1]):
-        with torch.cuda.stream(streams[i]):
-            results[i] = t()
-    results[-1] = thunks[-1]()
-    for st in streams:
-        main.wait_stream(st)
-    knets.sync_point(streams, reset_state_order=_DETACHED_OPEN[0] == 0)
-    return results
-
-
-class Detached:
-    """Independent pieces of the step issued on their own streams and joined LATER (not at the end
-    of the issuing block): they overlap with everything the current stream does in between.
-    ``after`` is an event of the current stream the pieces have to wait for (their inputs)."""
-
-    def __init__(self, thunks, after=None):
-        self.results = None
-        self.streams = []
-        if not torch.cuda.is_available():
-            self.results = [t() for t in thunks]
-            return
-        main = torch.cuda.current_stream()
-        # detached work is filler: whatever the issuing stream does meanwhile (on a high-priority
-        # stream, see step_stream) gets the SMs first at every kernel boundary
-        self.streams = _side_streams(_DETACHED_STREAMS, main.device, len(thunks), LOW_PRIORITY)
-        self.results = []
-        _DETACHED_OPEN[0] += 1
-        for st, t in zip(self.streams, thunks):
-            if after is not None:
-                st.wait_event(after)
-            else:
-                st.wait_stream(main)
-            with torch.cuda.stream(st):
-                self.results.append(t())
-
-    def join(self):
-        if self.streams:
-            main = torch.cuda.current_stream()
-            for st in self.streams:
-                main.wait_stream(st)
-            _DETACHED_OPEN[0] -= 1
-            knets.sync_point(self.streams, reset_state_order=_DETACHED_OPEN[0] == 0)
-            self.streams = []
-        return self.results
-
-
-def step_stream(device=None):
-    """a high-priority stream to run (or capture) train_step on: the detached generator forward
-    then runs at lower priority than the step's critical path"""
-    return torch.cuda.Stream(device=device, priority=HIGH_PRIORITY)
+    return streams.concurrently(*thunks, enabled=CONCURRENT_D if enabled is None else enabled)
 
 
 def stage_discriminators(nets, x, labels, early_generator=False):
@@ -233,20 +156,20 @@ def stage_discriminators(nets, x, labels, early_generator=False):
         start.record()
     # weight re-layout for this stage's discriminator passes and for the next stage's generator
     # passes runs on a side stream, overlapped with the no-grad generator forward below
-    prefetch = knets.prefetch_weights([netG, netD_se, netD_im, netD_st])
+    prefetch = knets.prefetch_weights([netG, netD_se, netD_im, netD_st], no_grad_forward=True)
     # (2) fakes for the discriminator update
     def no_grad(fn, *a, **kw):
         with torch.no_grad():      # grad mode is thread-local state, so set it inside the thunk
             return fn(*a, **kw)
 
     if early_generator:
-        _DETACHED_OPEN[0] += 1     # keep the ordered-state events alive across the join below
+        streams.hold_state_order()     # keep the ordered-state events alive across the join below
     (_, st_fake, _, _, c_mu, _, _), (_, im_fake, _, _, cim_mu, _, se_fake) = _concurrently(
         lambda: no_grad(netG.sample_videos, x["st_motion"], x["st_content"]),
         lambda: no_grad(netG.sample_images, x["im_motion"], x["im_content"], seg=True),
         enabled=CONCURRENT_G)
     if early_generator:
-        _DETACHED_OPEN[0] -= 1
+        streams.release_state_order()
         out["early_generator"] = generator_forward(nets, x, after=start)
     st_mu, im_mu = _cond_vectors(x, c_mu, cim_mu)
     out["p1_st_fake"], out["p1_im_fake"], out["p1_se_fake"] = st_fake, im_fake, se_fake

@@ -39,7 +39,7 @@ if __name__ == "__main__":
     dev = torch.device("cuda", 0)
     eng = bench.StepEngine(bench.preset_dict(), dev, use_graph=False, grad_sync=None)
     tr = eng.trainer
-    tr.CONCURRENT_D = tr.CONCURRENT_G = tr.EARLY_G = False
+    tr.CONCURRENT_D = tr.CONCURRENT_G = tr.EARLY_G = tr.streams.ENABLED = False
     from cpcsv_b200 import engine, ops
     engine.WGRAD_ON_AUX_STREAM = False
     for _ in range(3):
