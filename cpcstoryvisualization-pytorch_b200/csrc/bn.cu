@@ -64,6 +64,31 @@ inline Tiling make_tiling(int64_t rows, int C, int blocks_per_sm) {
 
 inline int reduction_parts(int64_t rows, int C) { return static_cast<int>(make_tiling(rows, C, 4).grid.y); }
 
+// Sum the 8 per-thread fp64 values v[0..8) over the rpb row lanes of each channel quad and hand
+// the totals of lanes rl == 0 to `dst` (dst[c + j] = v[j] totals, dst[C + c + j] = v[4 + j]
+// totals).  Two passes through an 8 KB buffer: with 16 KB these kernels would not fit next to a
+// resident tensor-core GEMM block (which leaves ~15 KB of shared memory per SM), and the step's
+// parallel branches could not overlap.
+__device__ __forceinline__ void reduce_rows_to(double (*sh)[4], const double* v, int qpb, int rpb,
+                                               int ql, int rl, bool active, double* __restrict__ dst,
+                                               int C, int c) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if (half) __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sh[threadIdx.x][j] = v[4 * half + j];
+    __syncthreads();
+    if (rl == 0 && active) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double t = 0;
+        for (int k = 0; k < rpb; ++k) t += sh[k * qpb + ql][j];
+        dst[half * C + c + j] = t;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------- statistics
 // partial[blockIdx.y][0..C) = sum x, [C..2C) = sum x^2  (fp64), written behind the 2C result slots
 __global__ void __launch_bounds__(256)
@@ -95,23 +120,9 @@ stats_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx, doub
       s[3] += v.w; ss[3] += static_cast<double>(v.w) * v.w;
     }
   }
-  __shared__ double sh[256][8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sh[threadIdx.x][j] = s[j];
-    sh[threadIdx.x][4 + j] = ss[j];
-  }
-  __syncthreads();
-  if (rl == 0 && c < C) {
-    double* part = ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      double t = 0;
-      for (int k = 0; k < rpb; ++k) t += sh[k * qpb + ql][j];
-      if (j < 4) part[c + j] = t;
-      else part[C + c + (j - 4)] = t;
-    }
-  }
+  __shared__ double sh[256][4];
+  const double v8[8] = {s[0], s[1], s[2], s[3], ss[0], ss[1], ss[2], ss[3]};
+  reduce_rows_to(sh, v8, qpb, rpb, ql, rl, c < C, ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y), C, c);
 }
 
 // ws[i] = sum_p ws[n * (1 + p) + i]: 32 columns x 8 part lanes per block
@@ -277,23 +288,9 @@ bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, int
       }
     }
   }
-  __shared__ double sh[256][8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sh[threadIdx.x][j] = s[j];
-    sh[threadIdx.x][4 + j] = sx[j];
-  }
-  __syncthreads();
-  if (rl == 0 && c < C) {
-    double* part = ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      double t = 0;
-      for (int kk = 0; kk < rpb; ++kk) t += sh[kk * qpb + ql][j];
-      if (j < 4) part[c + j] = t;
-      else part[C + c + (j - 4)] = t;
-    }
-  }
+  __shared__ double sh[256][4];
+  const double v8[8] = {s[0], s[1], s[2], s[3], sx[0], sx[1], sx[2], sx[3]};
+  reduce_rows_to(sh, v8, qpb, rpb, ql, rl, c < C, ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y), C, c);
 }
 
 __global__ void __launch_bounds__(256)
@@ -367,7 +364,7 @@ __device__ __forceinline__ void grid_sync() { cooperative_groups::this_grid().sy
 // every block of channel-block blockIdx.x sums the per-row-block partials of its quads: only the
 // blocks with blockIdx.y == 0 do it and publish the totals in ws[0 .. 2C)
 __device__ __forceinline__ void sum_partials_block(double* __restrict__ ws, int C, int c, int ql, int rl,
-                                                   int qpb, int rpb, int parts, double (*sh)[8]) {
+                                                   int qpb, int rpb, int parts, double (*sh)[4]) {
   double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c < C) {
     for (int p = rl; p < parts; p += rpb) {
@@ -379,18 +376,7 @@ __device__ __forceinline__ void sum_partials_block(double* __restrict__ ws, int 
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = t[j];
-  __syncthreads();
-  if (rl == 0 && c < C) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      double a = 0;
-      for (int k = 0; k < rpb; ++k) a += sh[k * qpb + ql][j];
-      if (j < 4) ws[c + j] = a;
-      else ws[C + c + (j - 4)] = a;
-    }
-  }
+  reduce_rows_to(sh, t, qpb, rpb, ql, rl, c < C, ws, C, c);
 }
 
 template <bool kMod, bool kY, bool kHi, bool kLo>
@@ -405,7 +391,7 @@ bn_fwd_fused_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ld
   const int ql = threadIdx.x % qpb, rl = threadIdx.x / qpb;
   const int c = (blockIdx.x * qpb + ql) * 4;
   const int64_t step = static_cast<int64_t>(gridDim.y) * rpb;
-  __shared__ double sh[256][8];
+  __shared__ double sh[256][4];
   // --- phase A: per-block partial sums
   {
     double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
@@ -427,22 +413,8 @@ bn_fwd_fused_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ld
         s[3] += v.w; ss[3] += static_cast<double>(v.w) * v.w;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sh[threadIdx.x][j] = s[j];
-      sh[threadIdx.x][4 + j] = ss[j];
-    }
-    __syncthreads();
-    if (rl == 0 && c < C) {
-      double* part = ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        double t = 0;
-        for (int k = 0; k < rpb; ++k) t += sh[k * qpb + ql][j];
-        if (j < 4) part[c + j] = t;
-        else part[C + c + (j - 4)] = t;
-      }
-    }
+    const double v8[8] = {s[0], s[1], s[2], s[3], ss[0], ss[1], ss[2], ss[3]};
+    reduce_rows_to(sh, v8, qpb, rpb, ql, rl, c < C, ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y), C, c);
   }
   __threadfence();
   grid_sync();
@@ -519,7 +491,7 @@ bn_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ dy, i
   const int ql = threadIdx.x % qpb, rl = threadIdx.x / qpb;
   const int c = (blockIdx.x * qpb + ql) * 4;
   const int64_t step = static_cast<int64_t>(gridDim.y) * rpb;
-  __shared__ double sh[256][8];
+  __shared__ double sh[256][4];
   ChanConst k;
   if (c < C) k = load_const(scale, shift, mean, invstd, c);
   {
@@ -535,22 +507,8 @@ bn_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ dy, i
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sh[threadIdx.x][j] = s[j];
-      sh[threadIdx.x][4 + j] = sx[j];
-    }
-    __syncthreads();
-    if (rl == 0 && c < C) {
-      double* part = ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        double t = 0;
-        for (int kk = 0; kk < rpb; ++kk) t += sh[kk * qpb + ql][j];
-        if (j < 4) part[c + j] = t;
-        else part[C + c + (j - 4)] = t;
-      }
-    }
+    const double v8[8] = {s[0], s[1], s[2], s[3], sx[0], sx[1], sx[2], sx[3]};
+    reduce_rows_to(sh, v8, qpb, rpb, ql, rl, c < C, ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y), C, c);
   }
   __threadfence();
   grid_sync();

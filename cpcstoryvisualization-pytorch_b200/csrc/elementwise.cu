@@ -547,17 +547,21 @@ __device__ __forceinline__ void merged_range(int a, int i, int& lo, int& hi) {
 // Tiled variant: a block owns a 16 (co) x 32 (ci) tile of the weight for ALL taps.  The source
 // w[co][ci][t] is read as contiguous runs of 32*T floats per co, staged in shared memory, and
 // written out per tap with the threads running along the destination's contiguous dimension.
+constexpr int kPackCo = 8, kPackCi = 16;
+
 __global__ void __launch_bounds__(256)
 pack_conv_weight_tiled_kernel(const float* __restrict__ w, int Cout, int Cin, int T, int kind,
                               int rows_pad, int cols_pad, uint16_t* __restrict__ hi,
                               uint16_t* __restrict__ lo, int dtype) {
-  __shared__ float s[16][32 * 16 + 1];
-  const int co0 = blockIdx.y * 16, ci0 = blockIdx.x * 32;
+  // 8 (co) x 16 (ci) x T tile = 8.2 KB of shared memory: small enough to be resident next to a
+  // tensor-core GEMM block of another stream (the re-layout runs on the prefetch stream)
+  __shared__ float s[kPackCo][kPackCi * 16 + 1];
+  const int co0 = blockIdx.y * kPackCo, ci0 = blockIdx.x * kPackCi;
   const bool transposed = (kind == 1 || kind == 3);
   const int ntap = kind >= 2 ? 16 : T;
-  // load: 16 rows (co) of 32*T contiguous floats
-  const int run = 32 * T;
-  for (int i = threadIdx.x; i < 16 * run; i += 256) {
+  // load: kPackCo rows (co) of kPackCi*T contiguous floats
+  const int run = kPackCi * T;
+  for (int i = threadIdx.x; i < kPackCo * run; i += 256) {
     const int r = i / run, j = i - r * run;
     const int co = co0 + r, ci = ci0 + j / T;
     s[r][j] = (co < Cout && ci < Cin) ? w[(static_cast<int64_t>(co) * Cin + ci0) * T + j] : 0.f;
@@ -565,11 +569,12 @@ pack_conv_weight_tiled_kernel(const float* __restrict__ w, int Cout, int Cin, in
   __syncthreads();
   // store: every thread emits 8 consecutive elements (one 16-byte store per plane) along the
   // output's contiguous dimension: ci for [tap][co][ci], co for [tap][ci][co]
-  for (int i = threadIdx.x; i < ntap * 64; i += 256) {
-    const int tap = i >> 6;
+  constexpr int kVec = kPackCo * kPackCi / 8;   // 16-byte output vectors per tap
+  for (int i = threadIdx.x; i < ntap * kVec; i += 256) {
+    const int tap = i / kVec, v = i % kVec;
     int r0, c0, dr, dc;      // first (co, ci) element inside the tile and the step along the vector
-    if (!transposed) { c0 = (i & 3) * 8; r0 = (i >> 2) & 15; dr = 0; dc = 1; }
-    else             { r0 = (i & 1) * 8; c0 = (i >> 1) & 31; dr = 1; dc = 0; }
+    if (!transposed) { c0 = (v % (kPackCi / 8)) * 8; r0 = v / (kPackCi / 8); dr = 0; dc = 1; }
+    else             { r0 = (v % (kPackCo / 8)) * 8; c0 = v / (kPackCo / 8); dr = 1; dc = 0; }
     int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
     if (kind >= 2) {
       const int a = tap >> 3, b = (tap >> 2) & 1, ti = (tap >> 1) & 1, tj = tap & 1;
@@ -915,7 +920,8 @@ extern "C" int cpcsv_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin,
   if (kh * kw <= 16 && cols_pad % 8 == 0) {
     // tiles cover the PADDED index space so the zero padding is written too
     const int co_ext = tr ? cols_pad : rows_pad, ci_ext = tr ? rows_pad : cols_pad;
-    dim3 grid(static_cast<unsigned>(ceil_div(ci_ext, 32)), static_cast<unsigned>(ceil_div(co_ext, 16)));
+    dim3 grid(static_cast<unsigned>(ceil_div(ci_ext, kPackCi)),
+              static_cast<unsigned>(ceil_div(co_ext, kPackCo)));
     pack_conv_weight_tiled_kernel<<<grid, 256, 0, STREAM(stream)>>>(
         w, Cout, Cin, kh * kw, kind, rows_pad, cols_pad, static_cast<uint16_t*>(hi),
         static_cast<uint16_t*>(lo), dtype);

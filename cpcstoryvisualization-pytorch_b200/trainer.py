@@ -134,7 +134,7 @@ def _concurrently(*thunks, enabled=None):
     return streams.concurrently(*thunks, enabled=CONCURRENT_D if enabled is None else enabled)
 
 
-def stage_discriminators(nets, x, labels, early_generator=False):
+def stage_discriminators(nets, x, labels, early_generator=False, opts=None):
     """reference trainer.py:290-343 minus the optimiser steps: no-grad fakes, the three
     discriminator losses and their backward passes.  The three discriminators are independent
     networks, so running all backward passes before any of their Adam steps (instead of the
@@ -145,7 +145,12 @@ def stage_discriminators(nets, x, labels, early_generator=False):
     the very end of the step) and fresh noise, so it does not depend on the discriminator update
     and fills the tensor cores while the discriminators' many small kernels run.  It is issued
     after the no-grad calls, so noise is drawn and BatchNorm running statistics are updated in
-    the reference's order.  The handle comes back under ``out['early_generator']``."""
+    the reference's order.  The handle comes back under ``out['early_generator']``.
+
+    ``opts``: when given (single-process training, no gradient exchange), every discriminator's
+    Adam step and the re-layout of its updated weights for the generator stage are issued on that
+    discriminator's own stream right after its backward pass, so they overlap with the other
+    discriminators still running instead of forming a tensor-core-idle gap after the join."""
     netG, netD_im, netD_st, netD_se = nets["G"], nets["D_im"], nets["D_st"], nets["D_se"]
     im_ones, im_zeros, st_ones, st_zeros = labels
     gpus = None
@@ -178,15 +183,19 @@ def stage_discriminators(nets, x, labels, early_generator=False):
         nets[k].zero_grad(set_to_none=True)
     # the three discriminators are independent networks made of many small kernels at this
     # batch size: run them on three concurrent streams (fork / join around the block)
-    def d_update(netD, real, fake, ones, zeros, cate, cond):
+    def d_update(key, real, fake, ones, zeros, cate, cond):
+        netD = nets[key]
         err = compute_discriminator_loss(netD, real, fake, ones, zeros, cate, cond, gpus)[0]
         err.backward()
+        if opts is not None:
+            opts[key].step()
+            knets.prefetch_weights([netD])      # joined with `prefetch` below (same side stream)
         return err
 
     se_errD, im_errD, st_errD = _concurrently(
-        lambda: d_update(netD_se, x["se_real"], se_fake, im_ones, im_zeros, x["im_labels"], im_mu),
-        lambda: d_update(netD_im, x["im_real"], im_fake, im_ones, im_zeros, x["im_labels"], im_mu),
-        lambda: d_update(netD_st, x["st_real"], st_fake, st_ones, st_zeros, x["st_labels"], st_mu))
+        lambda: d_update("D_se", x["se_real"], se_fake, im_ones, im_zeros, x["im_labels"], im_mu),
+        lambda: d_update("D_im", x["im_real"], im_fake, im_ones, im_zeros, x["im_labels"], im_mu),
+        lambda: d_update("D_st", x["st_real"], st_fake, st_ones, st_zeros, x["st_labels"], st_mu))
     out.update(se_errD=se_errD.detach(), im_errD=im_errD.detach(), st_errD=st_errD.detach())
     knets.join_prefetch(prefetch)
     return out
@@ -258,9 +267,11 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
     """One iteration of the reference's hot loop (trainer.py:290-416).  ``x`` from
     ``prepare_inputs`` (device tensors), ``labels`` = (im_ones, im_zeros, st_ones, st_zeros).
     Returns a dict of loss tensors (no host sync)."""
-    out = stage_discriminators(nets, x, labels, early_generator=EARLY_G)
+    exchange = grad_sync is not None and getattr(grad_sync, "enabled", True)
+    step_inside = apply_optim and not exchange
+    out = stage_discriminators(nets, x, labels, early_generator=EARLY_G, opts=opts if step_inside else None)
     sync_grads(nets, D_NETS, grad_sync)
-    if apply_optim:
+    if apply_optim and not step_inside:
         for k in D_NETS:
             opts[k].step()
     out.update(stage_generator(nets, x, labels, ratio, skip_d_wgrad, forward=out.pop("early_generator", None)))
