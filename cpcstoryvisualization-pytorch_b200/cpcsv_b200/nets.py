@@ -126,7 +126,9 @@ def prefetch_weights(modules, forward=True, backward=True, no_grad_forward=False
     main = torch.cuda.current_stream()
     side = _PREFETCH_STREAMS.get(main.device)
     if side is None:
-        side = _PREFETCH_STREAMS[main.device] = torch.cuda.Stream(device=main.device, priority=-1)
+        # lowest priority: the re-layout kernels are many small blocks that would otherwise fill
+        # every SM's block slots and delay the latency-bound kernels of the critical path
+        side = _PREFETCH_STREAMS[main.device] = torch.cuda.Stream(device=main.device, priority=0)
     side.wait_stream(main)
     with torch.cuda.stream(side):
         # in the order the step consumes them: no-grad generator pass, forward planes, backward planes
