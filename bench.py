@@ -285,37 +285,48 @@ def job_flops(job):
 
 
 def profile_gemm_launches(engine, steps):
-    """per-launch CUDA-event timing of every tcgen05 GEMM launch over `steps` eager steps"""
+    """Average launch duration of the dominant kernel, measured live with CUDA events: the step is
+    run eagerly on ONE stream behind a long device-side sleep (so the host stays ahead and each
+    event pair brackets its kernel alone; with the step's concurrent branches the second event
+    would also wait for kernels of other streams).  The zero fill of split-K outputs is kept
+    outside the brackets."""
+    from cpcsv_b200 import engine as keng
     from cpcsv_b200 import ops
     orig = ops.conv_gemm
     recs = []
 
     def timed(job):
+        restore = False
+        if job.splits > 1 and not job.accumulate:
+            job.out.zero_()
+            job.accumulate, restore = True, True
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         orig(job)
         e1.record()
+        if restore:
+            job.accumulate = False
         recs.append((e0, e1, job_flops(job)))
 
-    # one stream: a launch's event pair then brackets that kernel alone (with the step's
-    # concurrent branches the second event would also wait for kernels of other streams)
     tr = engine.trainer
-    flags = (tr.CONCURRENT_D, tr.CONCURRENT_G, tr.EARLY_G, tr.streams.ENABLED)
-    tr.CONCURRENT_D = tr.CONCURRENT_G = tr.EARLY_G = tr.streams.ENABLED = False
-    ops.conv_gemm = timed
+    flags = (tr.CONCURRENT_D, tr.CONCURRENT_G, tr.EARLY_G, tr.streams.ENABLED, keng.WGRAD_ON_AUX_STREAM)
+    tr.CONCURRENT_D = tr.CONCURRENT_G = tr.EARLY_G = tr.streams.ENABLED = keng.WGRAD_ON_AUX_STREAM = False
     try:
-        for i in range(steps + 1):
-            if i == 1:
-                del recs[:]          # first serial step re-packs weights / warms up
-            engine._step_body()
+        engine._step_body()              # serial warm-up: re-packs weights on this stream
         torch.cuda.synchronize()
+        ops.conv_gemm = timed
+        for _ in range(steps):
+            torch.cuda._sleep(int(0.4 * 1.9e9))
+            engine._step_body()
+            torch.cuda.synchronize()
     finally:
         ops.conv_gemm = orig
-        tr.CONCURRENT_D, tr.CONCURRENT_G, tr.EARLY_G, tr.streams.ENABLED = flags
+        tr.CONCURRENT_D, tr.CONCURRENT_G, tr.EARLY_G, tr.streams.ENABLED, keng.WGRAD_ON_AUX_STREAM = flags
     ms = sum(a.elapsed_time(b) for a, b, _ in recs)
     fl = sum(f for _, _, f in recs)
     return {"launches_per_step": len(recs) / steps, "gemm_ms_per_step": ms / steps,
-            "executed_gflop_per_step": fl / steps / 1e9, "achieved_tflops": fl / (ms * 1e-3) / 1e12}
+            "executed_gflop_per_step": fl / steps / 1e9, "achieved_tflops": fl / (ms * 1e-3) / 1e12,
+            "avg_launch_us": 1e3 * ms / len(recs)}
 
 
 def main():
@@ -447,6 +458,10 @@ def main():
                      "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM)", "peak_source": peak_src,
                      "executed_gflop_per_step": prof["executed_gflop_per_step"],
                      "gemm_launches_per_step": prof["launches_per_step"],
+                     "avg_launch_us": prof["avg_launch_us"],
+                     "method": "CUDA events around every conv_gemm launch of 2 eager single-stream steps "
+                               "queued behind a device-side sleep; achieved = executed tensor-core FLOPs / "
+                               "summed launch durations",
                      "gemm_ms_per_step_serial_events": prof["gemm_ms_per_step"]},
         "clocks": clocks,
     }

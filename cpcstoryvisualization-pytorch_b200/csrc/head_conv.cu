@@ -20,9 +20,11 @@ namespace cpcsv {
 
 constexpr int kHeadTileH = 8;     // output rows per CTA
 constexpr int kHeadTileW = 64;    // output columns per CTA
-constexpr int kHeadChunk = 16;    // input channels staged per pass
+constexpr int kHeadChunk = 16;    // input channels staged per pass (32 B = one sector per pixel and plane)
 constexpr int kHeadPitch = 20;    // floats per staged pixel (16 + 4: conflict-free float4 access)
 constexpr int kHeadThreads = 128; // thread = (column, strip of 4 rows)
+constexpr int kHeadPix = (kHeadTileH + 2) * (kHeadTileW + 2);
+constexpr int kHeadIters = (kHeadPix + kHeadThreads - 1) / kHeadThreads;   // halo pixels per thread
 
 __device__ __forceinline__ float cvt16(uint16_t v, int dtype) {
   if (dtype == 1) return __uint_as_float(static_cast<uint32_t>(v) << 16);
@@ -38,59 +40,63 @@ __device__ __forceinline__ void unpack8(const uint4& q, int dtype, float* f) {
   }
 }
 
-// stage channels [c0, c0 + 16) of the (8 + 2) x (64 + 2) halo tile as fp32 (hi + lo).  The
-// global loads of three pixels per thread are issued back to back before any of them is
-// converted (memory-level parallelism: the staging is latency-bound otherwise).
-__device__ __forceinline__ void stage_halo(const uint16_t* __restrict__ hi,
-                                           const uint16_t* __restrict__ lo, int dtype, int n, int H,
-                                           int W, int C, int y0, int x0, int c0, float* a_s) {
-  constexpr int kPix = (kHeadTileH + 2) * (kHeadTileW + 2);
-  constexpr int kBatch = 3;
-  for (int base = threadIdx.x; base < kPix; base += kBatch * kHeadThreads) {
-    uint4 qh[kBatch][2], ql[kBatch][2];
-    bool ok[kBatch];
+// Halo staging, software pipelined: `fetch` issues the global loads of channels [c0, c0 + 16) of
+// the (8 + 2) x (64 + 2) halo tile into registers (all of a thread's pixels back to back),
+// `commit` converts them to fp32 (hi + lo) and writes them to shared memory.  The kernel fetches
+// chunk k + 1 before it multiplies chunk k, so the HBM latency is hidden behind the arithmetic.
+struct HaloRegs {
+  uint4 h[kHeadIters][2];
+  uint4 l[kHeadIters][2];
+  uint32_t ok;
+};
+
+__device__ __forceinline__ void halo_fetch(HaloRegs& R, const uint16_t* __restrict__ hi,
+                                           const uint16_t* __restrict__ lo, int n, int H, int W, int C,
+                                           int y0, int x0, int c0) {
+  R.ok = 0;
 #pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-      const int idx = base + b * kHeadThreads;
-      const int r = idx / (kHeadTileW + 2), cx = idx - r * (kHeadTileW + 2);
-      const int gy = y0 - 1 + r, gx = x0 - 1 + cx;
-      ok[b] = idx < kPix && gy >= 0 && gy < H && gx >= 0 && gx < W;
-      if (ok[b]) {
-        const int64_t off = ((static_cast<int64_t>(n) * H + gy) * W + gx) * C + c0;
-        const uint4* ph = reinterpret_cast<const uint4*>(hi + off);
-        qh[b][0] = __ldg(ph);
-        qh[b][1] = __ldg(ph + 1);
-        if (lo) {
-          const uint4* pl = reinterpret_cast<const uint4*>(lo + off);
-          ql[b][0] = __ldg(pl);
-          ql[b][1] = __ldg(pl + 1);
-        }
+  for (int b = 0; b < kHeadIters; ++b) {
+    const int idx = threadIdx.x + b * kHeadThreads;
+    const int r = idx / (kHeadTileW + 2), cx = idx - r * (kHeadTileW + 2);
+    const int gy = y0 - 1 + r, gx = x0 - 1 + cx;
+    if (idx < kHeadPix && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      R.ok |= 1u << b;
+      const int64_t off = ((static_cast<int64_t>(n) * H + gy) * W + gx) * C + c0;
+      const uint4* ph = reinterpret_cast<const uint4*>(hi + off);
+      R.h[b][0] = __ldg(ph);
+      R.h[b][1] = __ldg(ph + 1);
+      if (lo) {
+        const uint4* pl = reinterpret_cast<const uint4*>(lo + off);
+        R.l[b][0] = __ldg(pl);
+        R.l[b][1] = __ldg(pl + 1);
       }
     }
+  }
+}
+
+__device__ __forceinline__ void halo_commit(const HaloRegs& R, bool two, int dtype, float* a_s) {
 #pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-      const int idx = base + b * kHeadThreads;
-      if (idx >= kPix) break;
-      float f[16];
-      if (ok[b]) {
-        unpack8(qh[b][0], dtype, f);
-        unpack8(qh[b][1], dtype, f + 8);
-        if (lo) {
-          float g[16];
-          unpack8(ql[b][0], dtype, g);
-          unpack8(ql[b][1], dtype, g + 8);
+  for (int b = 0; b < kHeadIters; ++b) {
+    const int idx = threadIdx.x + b * kHeadThreads;
+    if (idx >= kHeadPix) break;
+    float f[16];
+    if ((R.ok >> b) & 1u) {
+      unpack8(R.h[b][0], dtype, f);
+      unpack8(R.h[b][1], dtype, f + 8);
+      if (two) {
+        float g[16];
+        unpack8(R.l[b][0], dtype, g);
+        unpack8(R.l[b][1], dtype, g + 8);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] += g[i];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = 0.f;
+        for (int i = 0; i < 16; ++i) f[i] += g[i];
       }
-      float4* dst = reinterpret_cast<float4*>(a_s + idx * kHeadPitch);
+    } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      for (int i = 0; i < 16; ++i) f[i] = 0.f;
     }
+    float4* dst = reinterpret_cast<float4*>(a_s + idx * kHeadPitch);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
   }
 }
 
@@ -117,8 +123,10 @@ head_conv_tanh_fwd_kernel(const uint16_t* __restrict__ hi, const uint16_t* __res
 #pragma unroll
     for (int co = 0; co < CO; ++co) acc[i][co] = 0.f;
 
+  HaloRegs R;
+  halo_fetch(R, hi, lo, n, H, W, C, y0, x0, 0);
   for (int c0 = 0; c0 < C; c0 += kHeadChunk) {
-    stage_halo(hi, lo, dtype, n, H, W, C, y0, x0, c0, a_s);
+    halo_commit(R, lo != nullptr, dtype, a_s);
     for (int idx = threadIdx.x; idx < 9 * CO * kHeadChunk; idx += kHeadThreads) {
       const int c = idx % kHeadChunk;
       const int q = idx / kHeadChunk;
@@ -126,18 +134,20 @@ head_conv_tanh_fwd_kernel(const uint16_t* __restrict__ hi, const uint16_t* __res
       w_s[idx] = __ldg(w + (static_cast<int64_t>(co) * C + c0 + c) * 9 + tap);
     }
     __syncthreads();
+    if (c0 + kHeadChunk < C) halo_fetch(R, hi, lo, n, H, W, C, y0, x0, c0 + kHeadChunk);
 #pragma unroll
     for (int c4 = 0; c4 < kHeadChunk / 4; ++c4) {
-      float4 wr[9][CO];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap)
+      for (int dx = 0; dx < 3; ++dx) {
+        // the three taps of this filter column stay in registers (9 float4 for CO = 3)
+        float4 wr[3][CO];
 #pragma unroll
-        for (int co = 0; co < CO; ++co)
-          wr[tap][co] = *reinterpret_cast<const float4*>(w_s + (tap * CO + co) * kHeadChunk + 4 * c4);
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
+          for (int co = 0; co < CO; ++co)
+            wr[ky][co] = *reinterpret_cast<const float4*>(w_s + ((ky * 3 + dx) * CO + co) * kHeadChunk + 4 * c4);
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
+        for (int r = 0; r < 6; ++r) {
           const float4 v = *reinterpret_cast<const float4*>(
               a_s + ((strip * 4 + r) * (kHeadTileW + 2) + x + dx) * kHeadPitch + 4 * c4);
 #pragma unroll
@@ -146,7 +156,7 @@ head_conv_tanh_fwd_kernel(const uint16_t* __restrict__ hi, const uint16_t* __res
             if (ky >= 0 && ky < 3) {
 #pragma unroll
               for (int co = 0; co < CO; ++co) {
-                const float4 ww = wr[ky * 3 + dx][co];
+                const float4 ww = wr[ky][co];
                 acc[i][co] = fmaf(v.x, ww.x, acc[i][co]);
                 acc[i][co] = fmaf(v.y, ww.y, acc[i][co]);
                 acc[i][co] = fmaf(v.z, ww.z, acc[i][co]);

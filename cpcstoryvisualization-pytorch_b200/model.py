@@ -31,7 +31,7 @@ except ImportError:  # copied elsewhere: fall back to the recorded install locat
     import cpcsv_b200  # noqa: F401
 
 from cpcsv_b200 import functions as Fx
-from cpcsv_b200 import nets
+from cpcsv_b200 import nets, streams
 from miscc.config import cfg
 
 
@@ -207,13 +207,19 @@ class StoryGAN(nn.Module):
         h_all = Fx.gru_sequence(motion_input[:, :steps].transpose(0, 1), h0, self.mocornn)   # [T, B, H]
         return h_all.transpose(0, 1).reshape(-1, self.content_dim)
 
-    def _latent(self, motion_flat, crnn_code, zm_code, c_mu_rows):
-        zmc_code = torch.cat((zm_code, c_mu_rows), dim=1)
-        m_image = self._lin_bn(self.image_net, motion_flat, tanh=True).reshape(-1, self.filter_num, self.image_size)
-        c_filter = self._lin_bn(self.filter_net, crnn_code).reshape(-1, self.out_num, self.filter_num,
-                                                                   self.filter_size)
+    def _conditioning(self, motion_input, motion_flat, content_code, c_mu_rows, video_len):
+        """everything between the text embeddings and the trunk input (reference model.py:363-378 /
+        436-443) as three independent chains on parallel streams: context GRU -> filter_net,
+        motion GRU, image_net; then the dynamic filter and the concatenation.  The chains are
+        issued in the reference's order, so noise is drawn in the reference's order."""
+        crnn_filter, zm_code, m_image = streams.concurrently(
+            lambda: self._lin_bn(self.filter_net, self.motion_content_rnn(motion_input, content_code)),
+            lambda: self.sample_z_motion(motion_input, video_len),
+            lambda: self._lin_bn(self.image_net, motion_flat, tanh=True))
+        m_image = m_image.reshape(-1, self.filter_num, self.image_size)
+        c_filter = crnn_filter.reshape(-1, self.out_num, self.filter_num, self.filter_size)
         mc_image = self.dfn_layer([m_image, c_filter])
-        return torch.cat((zmc_code, mc_image.squeeze(1)), dim=1)
+        return torch.cat((zm_code, c_mu_rows, mc_image.squeeze(1)), dim=1)
 
     def _trunk(self, zmc_all, seg):
         need_grad = torch.is_grad_enabled() and (
@@ -230,10 +236,8 @@ class StoryGAN(nn.Module):
         content = content_input.reshape(B, cfg.VIDEO_LEN * content_input.shape[2])
         r_code, r_mu, r_logvar = self.ca_net(content)
         c_mu = r_mu.repeat(self.video_len, 1)
-        crnn_code = self.motion_content_rnn(motion_input, r_code)
         m_flat = motion_input.reshape(-1, motion_input.shape[2])
-        zm_code = self.sample_z_motion(motion_input, self.video_len)
-        zmc_all = self._latent(m_flat, crnn_code, zm_code, c_mu)
+        zmc_all = self._conditioning(motion_input, m_flat, r_code, c_mu, self.video_len)
         img, segm = self._trunk(zmc_all, seg)
         fake = img.view(B, self.video_len, self.n_channels, self.segment_size, self.segment_size)
         fake = fake.permute(0, 2, 1, 3, 4)
@@ -245,9 +249,7 @@ class StoryGAN(nn.Module):
         N = motion_input.shape[0]
         content = content_input.reshape(N, cfg.VIDEO_LEN * content_input.shape[2])
         _c_code, c_mu, c_logvar = self.ca_net(content)
-        crnn_code = self.motion_content_rnn(motion_input, c_mu)
-        zm_code = self.sample_z_motion(motion_input, 1)
-        zmc_all = self._latent(motion_input, crnn_code, zm_code, c_mu)
+        zmc_all = self._conditioning(motion_input, motion_input, c_mu, c_mu, 1)
         img, segm = self._trunk(zmc_all, seg)
         return None, img, motion_input, motion_input, c_mu, c_logvar, (segm if seg else None)
 
