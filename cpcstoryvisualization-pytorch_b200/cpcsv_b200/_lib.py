@@ -27,7 +27,7 @@ class Gemm(C.Structure):
         ("tile_n", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
         ("groups", C.c_int32), ("taps_per_group", C.c_int32), ("k_blocks", C.c_int32),
         ("m_valid", C.c_int32), ("n_valid", C.c_int32), ("block_n", C.c_int32),
-        ("n_tiles", C.c_int32), ("splits", C.c_int32), ("accumulate", C.c_int32),
+        ("n_tiles", C.c_int32), ("splits", C.c_int32), ("accumulate", C.c_int32), ("cta_pair", C.c_int32),
         ("out_stride_n", C.c_int64), ("out_stride_h", C.c_int64), ("out_stride_w", C.c_int64),
         ("ldc", C.c_int64),
         ("alpha", C.c_void_p), ("out", C.c_void_p),

@@ -54,6 +54,14 @@ def pick_splits(tiles, iters, penalty=0.04):
     return best
 
 
+def use_pair(grid, tile, block_n):
+    """Run a fprop / dgrad job as cta_group::2 pairs?  Measured on B200 at every job shape of the
+    step (tools/sweep_pair.py, profiles/r01_sweep_pair.txt: median of 9, L2 flushed): 0.79-0.87x the
+    time with hi/lo split operands, 0.91-1.00x single-plane, never slower -- so whenever there are
+    two 128-row tiles to pair and the B tile can be halved."""
+    return _m_tiles(grid, tile) >= 2 and block_n >= 32 and (block_n // 2) % 8 == 0
+
+
 def _m_tiles(grid, tile):
     n = 1
     for g, t in zip(grid, tile):
@@ -72,7 +80,7 @@ def _fwd_job(a_planes, b_planes, grid, groups, taps_per_group, taps, k_blocks, o
                    taps_per_group=taps_per_group, k_blocks=k_blocks, taps=taps, a=a_planes,
                    b=b_planes, out=out, n_valid=npad, block_n=block_n, n_tiles=n_tiles,
                    splits=splits, accumulate=accumulate, out_strides=out_strides, alpha=alpha,
-                   dtype=dtype)
+                   dtype=dtype, pair=use_pair(grid, tile, block_n))
 
 
 def _wgrad_job(a_view, b_view, grid, taps, m_valid, npad, out, ldc, dtype=BF16, splits=None):

@@ -84,7 +84,7 @@ class GemmJob:
 
     def __init__(self, mode, planes, grid, tile, groups, taps_per_group, k_blocks, taps, a, b, out,
                  n_valid, block_n, n_tiles, m_valid=0, splits=1, accumulate=False,
-                 out_strides=(0, 0, 0), ldc=0, alpha=None, dtype=BF16):
+                 out_strides=(0, 0, 0), ldc=0, alpha=None, dtype=BF16, pair=False):
         self.mode, self.planes, self.dtype = mode, planes, dtype
         self.grid, self.tile = tuple(grid), tuple(tile)      # (N, H, W), (tile_n, tile_h, tile_w)
         self.groups, self.taps_per_group, self.k_blocks = groups, taps_per_group, k_blocks
@@ -94,6 +94,7 @@ class GemmJob:
         self.n_valid, self.block_n, self.n_tiles, self.m_valid = n_valid, block_n, n_tiles, m_valid
         self.splits, self.accumulate = splits, bool(accumulate)
         self.out_strides, self.ldc, self.alpha = tuple(out_strides), ldc, alpha
+        self.pair = bool(pair)      # mode 0: cta_group::2 pairs (see conv.use_pair)
 
 
 def conv_gemm(job):
@@ -103,7 +104,7 @@ def conv_gemm(job):
     g.tile_n, g.tile_h, g.tile_w = job.tile
     g.groups, g.taps_per_group, g.k_blocks = job.groups, job.taps_per_group, job.k_blocks
     g.m_valid, g.n_valid, g.block_n, g.n_tiles = job.m_valid, job.n_valid, job.block_n, job.n_tiles
-    g.splits, g.accumulate = job.splits, int(job.accumulate)
+    g.splits, g.accumulate, g.cta_pair = job.splits, int(job.accumulate), int(job.pair)
     g.out_stride_n, g.out_stride_h, g.out_stride_w = job.out_strides
     g.ldc = job.ldc
     g.alpha = _ptr(job.alpha, torch.float32).value if job.alpha is not None else None

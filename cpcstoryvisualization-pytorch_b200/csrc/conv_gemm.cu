@@ -18,6 +18,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.h"
@@ -48,6 +50,7 @@ struct GemmParams {
   int32_t tiles_n, tiles_h, tiles_w;
   int32_t groups, taps_per_group, k_blocks;
   int32_t m_tiles, n_tiles, block_n;
+  int32_t m_units;     // m_tiles, or pairs of m tiles in CTA-pair mode
   int32_t m_valid, n_valid;
   int32_t splits, iters_total;
   int32_t accumulate;
@@ -65,10 +68,13 @@ struct TileCoord {
   int32_t it0, it1;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, uint32_t t) {
+// `t` counts work units: 128-row tiles, or (CTA-pair mode) pairs of them of which CTA `rank`
+// takes the `rank`-th; an odd tail unit has m_idx == m_tiles (every row out of range)
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, uint32_t t, uint32_t pair,
+                                                 uint32_t rank) {
   TileCoord c;
-  c.m_idx = t % P.m_tiles;
-  t /= P.m_tiles;
+  c.m_idx = static_cast<int32_t>((t % P.m_units) * (pair ? 2u : 1u) + rank);
+  t /= P.m_units;
   c.n_idx = t % P.n_tiles;
   t /= P.n_tiles;
   c.split = t % P.splits;
@@ -87,6 +93,12 @@ __device__ __forceinline__ void pixel_tile_origin(const GemmParams& P, int32_t q
   n0 = (q / P.tiles_h) * P.tile_n;
 }
 
+// kPair: the two CTAs of a cluster work as one cta_group::2 unit: each loads its own 128 pixel
+// rows of A and HALF of the B tile, the leader issues M = 256 MMAs that read B from both CTAs'
+// shared memory, each CTA's TMEM receives its own 128 accumulator rows.  Per CTA and k-step that
+// is 16 + block_n/16 KB instead of 16 + block_n/8 KB from L2 -- the L2 -> SM feed is what bounds
+// the single-CTA kernel (ncu: 11.7 TB/s of 12.4 TB/s on single-plane jobs).
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -103,6 +115,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t tile0 = kPair ? (blockIdx.x >> 1) : blockIdx.x;
+  const uint32_t tstep = kPair ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -119,16 +134,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], kPair ? 8 : 4);   // pair: the peer's epilogue warps arrive remotely
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -139,16 +159,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (uint32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(P, tile);
+      for (uint32_t tile = tile0; tile < P.total_tiles; tile += tstep) {
+        const TileCoord tc = decode_tile(P, tile, kPair, rank);
         int32_t n0 = 0, h0 = 0, w0 = 0;
         if (P.mode == 0) pixel_tile_origin(P, tc.m_idx, n0, h0, w0);
         for (int32_t it = tc.it0; it < tc.it1; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], stage_tx);
           uint8_t* sa = smem + stage * P.stage_bytes;
           uint8_t* sb = sa + P.planes * kAPlaneBytes;
-          if (P.mode == 0) {
+          if (kPair) {
+            // both CTAs' bytes are accounted on the leader's barrier
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
+            const uint32_t bar = mapa_u32(&full_bar[stage], 0);
+            const int32_t t = it / P.k_blocks;
+            const int32_t kb = it - t * P.k_blocks;
+            const cpcsv_tap_t& tap = P.taps[tc.group * P.taps_per_group + t];
+            for (int pl = 0; pl < P.planes; ++pl) {
+              tma_load_5d_pair(pl ? &tmA1 : &tmA0, bar, sa + pl * kAPlaneBytes, tap.a[0] + kb * 64,
+                               w0 + tap.a[1], tap.a[2], h0 + tap.a[3], n0);
+              tma_load_5d_pair(pl ? &tmB1 : &tmB0, bar, sb + pl * P.b_plane_bytes, kb * 64,
+                               tap.b[0] + tc.n_idx * P.block_n + static_cast<int32_t>(rank) * (P.block_n / 2),
+                               0, 0, 0);
+            }
+          } else if (P.mode == 0) {
+            mbar_expect_tx(&full_bar[stage], stage_tx);
             const int32_t t = it / P.k_blocks;
             const int32_t kb = it - t * P.k_blocks;
             const cpcsv_tap_t& tap = P.taps[tc.group * P.taps_per_group + t];
@@ -159,6 +193,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                           tap.b[0] + tc.n_idx * P.block_n, 0, 0, 0);
             }
           } else {
+            mbar_expect_tx(&full_bar[stage], stage_tx);
             const cpcsv_tap_t& tap = P.taps[tc.group];
             pixel_tile_origin(P, it, n0, h0, w0);
             for (int pl = 0; pl < P.planes; ++pl) {
@@ -183,12 +218,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t acc = 0, acc_phase = 0;
-      for (uint32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(P, tile);
+      for (uint32_t tile = tile0; tile < P.total_tiles; tile += tstep) {
+        const TileCoord tc = decode_tile(P, tile, kPair, rank);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
@@ -206,21 +241,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint64_t a_hi = make_smem_desc(sa + koff, lbo, 1024);
             const uint64_t b_hi = make_smem_desc(sb + koff, lbo, 1024);
             const uint32_t first = (it > tc.it0 || k > 0) ? 1u : 0u;
-            umma_f16(tmem_d, a_hi, b_hi, P.idesc, first);
+            if (kPair) umma_f16_pair(tmem_d, a_hi, b_hi, P.idesc, first);
+            else umma_f16(tmem_d, a_hi, b_hi, P.idesc, first);
             if (P.planes == 2) {
               const uint64_t a_lo = make_smem_desc(sa + kAPlaneBytes + koff, lbo, 1024);
               const uint64_t b_lo = make_smem_desc(sb + P.b_plane_bytes + koff, lbo, 1024);
-              umma_f16(tmem_d, a_lo, b_hi, P.idesc, 1u);
-              umma_f16(tmem_d, a_hi, b_lo, P.idesc, 1u);
+              if (kPair) {
+                umma_f16_pair(tmem_d, a_lo, b_hi, P.idesc, 1u);
+                umma_f16_pair(tmem_d, a_hi, b_lo, P.idesc, 1u);
+              } else {
+                umma_f16(tmem_d, a_lo, b_hi, P.idesc, 1u);
+                umma_f16(tmem_d, a_hi, b_lo, P.idesc, 1u);
+              }
             }
           }
-          umma_commit(&empty_bar[stage]);
+          if (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == P.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);
+        if (kPair) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -236,8 +277,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t acc = 0, acc_phase = 0;
     const float alpha = P.alpha ? __ldg(P.alpha) : 1.0f;
     const bool atomic = (P.accumulate != 0) || (P.splits > 1);
-    for (uint32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(P, tile);
+    for (uint32_t tile = tile0; tile < P.total_tiles; tile += tstep) {
+      const TileCoord tc = decode_tile(P, tile, kPair, rank);
       float* row_ptr;
       bool row_valid;
       if (P.mode == 0) {
@@ -333,15 +374,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (kPair && rank != 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (kPair) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -382,6 +429,15 @@ static int make_map(CUtensorMap* tm, const cpcsv_view5_t& v, const uint32_t box[
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-3, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
   return 0;
+}
+
+// CPCSV_PAIR=0 in the environment switches the cta_group::2 path off (A/B measurements)
+static bool pair_mode_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CPCSV_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 int num_sms() {
@@ -466,12 +522,17 @@ extern "C" int cpcsv_conv_gemm(const cpcsv_gemm_t* job, cpcsv_stream_t stream_) 
     P.taps[i] = J.taps[i];
     CPCSV_REQUIRE(J.taps[i].out_off % 4 == 0, "conv_gemm: tap %d out_off alignment", i);
   }
-  const int64_t total = static_cast<int64_t>(P.groups) * P.splits * P.n_tiles * P.m_tiles;
+  // CTA-pair mode (cta_group::2): fprop / dgrad jobs with at least two 128-row tiles
+  CPCSV_REQUIRE(J.cta_pair == 0 || (J.mode == 0 && J.block_n >= 32 && (J.block_n / 2) % 8 == 0),
+                "conv_gemm: cta_pair needs mode 0 and block_n a multiple of 16 >= 32");
+  const bool pair = J.cta_pair != 0 && pair_mode_enabled() && P.m_tiles >= 2;
+  P.m_units = pair ? (P.m_tiles + 1) / 2 : P.m_tiles;
+  const int64_t total = static_cast<int64_t>(P.groups) * P.splits * P.n_tiles * P.m_units;
   CPCSV_REQUIRE(total > 0 && total < (1ll << 31), "conv_gemm: tile count %lld", (long long)total);
   P.total_tiles = static_cast<uint32_t>(total);
-  P.idesc = make_idesc(static_cast<uint32_t>(J.dtype), static_cast<uint32_t>(J.mode), kBlockM,
-                       static_cast<uint32_t>(J.block_n));
-  P.b_plane_bytes = J.block_n * 128;
+  P.idesc = make_idesc(static_cast<uint32_t>(J.dtype), static_cast<uint32_t>(J.mode),
+                       pair ? 2 * kBlockM : kBlockM, static_cast<uint32_t>(J.block_n));
+  P.b_plane_bytes = (pair ? J.block_n / 2 : J.block_n) * 128;
   P.stage_bytes = J.planes * (kAPlaneBytes + P.b_plane_bytes);
   int stages = (kSmemLimit - 1024 - kBarrierBytes - kEpiBytes) / P.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -484,7 +545,7 @@ extern "C" int cpcsv_conv_gemm(const cpcsv_gemm_t* job, cpcsv_stream_t stream_) 
   uint32_t boxA[5], boxB[5];
   boxA[0] = 64; boxA[1] = J.tile_w; boxA[2] = 1; boxA[3] = J.tile_h; boxA[4] = J.tile_n;
   if (J.mode == 0) {
-    boxB[0] = 64; boxB[1] = J.block_n; boxB[2] = 1; boxB[3] = 1; boxB[4] = 1;
+    boxB[0] = 64; boxB[1] = pair ? J.block_n / 2 : J.block_n; boxB[2] = 1; boxB[3] = 1; boxB[4] = 1;
   } else {
     for (int i = 0; i < 5; ++i) boxB[i] = boxA[i];
   }
@@ -499,15 +560,37 @@ extern "C" int cpcsv_conv_gemm(const cpcsv_gemm_t* job, cpcsv_stream_t stream_) 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemLimit);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kSmemLimit);
   });
   if (attr_err != cudaSuccess)
     return fail(static_cast<int>(attr_err), "conv_gemm: cudaFuncSetAttribute: %s",
                 cudaGetErrorString(attr_err));
 
-  uint32_t grid = P.total_tiles < static_cast<uint32_t>(num_sms()) ? P.total_tiles
-                                                                  : static_cast<uint32_t>(num_sms());
-  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA[0], tmA[1], tmB[0], tmB[1], P);
+  const uint32_t sms = static_cast<uint32_t>(num_sms());
+  if (pair) {
+    const uint32_t clusters = P.total_tiles < sms / 2 ? P.total_tiles : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, tmA[0], tmA[1], tmB[0], tmB[1], P);
+    if (e != cudaSuccess)
+      return fail(static_cast<int>(e), "conv_gemm (pair): %s", cudaGetErrorString(e));
+    return launched("conv_gemm");
+  }
+  const uint32_t grid = P.total_tiles < sms ? P.total_tiles : sms;
+  conv_gemm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tmA[0], tmA[1], tmB[0], tmB[1], P);
   return launched("conv_gemm");
 }

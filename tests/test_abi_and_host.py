@@ -47,4 +47,5 @@ def test_gemm_struct_layout_matches_header():
     import ctypes as C
     assert C.sizeof(_lib.View5) == 8 + 5 * 8 + 5 * 8
     assert C.sizeof(_lib.Tap) == 40
-    assert C.sizeof(_lib.Gemm) == 18 * 4 + 4 * 8 + 2 * 8 + 4 * 88 + 16 * 40
+    # 19 int32 fields (incl. cta_pair) padded to 20 x 4 bytes before the int64 members
+    assert C.sizeof(_lib.Gemm) == 20 * 4 + 4 * 8 + 2 * 8 + 4 * 88 + 16 * 40
