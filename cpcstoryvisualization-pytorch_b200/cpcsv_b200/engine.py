@@ -217,7 +217,7 @@ class ConvNode:
     """3x3 s1 / nearest-x2+3x3 / 4x4 s2 convolution, optionally spectrally normalised
     (weight = weight_orig / sigma applied as the epilogue scalar alpha)."""
 
-    def __init__(self, tape, kind, x, weight, name, sn=None):
+    def __init__(self, tape, kind, x, weight, name, sn=None, alpha=None):
         self.tape, self.kind, self.x, self.w, self.name, self.sn = tape, kind, x, weight, name, sn
         Co, Ci = weight.shape[0], weight.shape[1]
         self.Co, self.Ci = Co, Ci
@@ -229,7 +229,7 @@ class ConvNode:
         elif kind == "s2":
             H, W = H // 2, W // 2
         self.out = T4(N, H, W, self.Co_pad)
-        self.alpha = None
+        self.alpha = alpha          # 1/sigma of a spectral norm whose power iteration already ran
         self.dW = None
 
     def _pack(self, kindcode, rows_pad, cols_pad, planes, dtype=BF16):
@@ -238,7 +238,7 @@ class ConvNode:
     def forward(self):
         t, x, out = self.tape, self.x, self.out
         dev = x.hi.device
-        if self.sn is not None:
+        if self.sn is not None and self.alpha is None:     # not already computed ahead of the chain
             self.alpha = self.sn.forward(self.w, t.training, t.need_grad)
         wp = self._pack(CONV_GEOM[self.kind][1], self.Co_pad, self.Ci_pad, t.planes, t.dtype)
         out.f32 = _e((out.N, out.H, out.W, out.C), dev)

@@ -493,24 +493,34 @@ class EncoderRunner:
         self.tape = tape
         self.x_shape = (n, Cin, H, W)
         xd = x.detach()
-        # layer 0: im2col + GEMM (+ SN alpha for the story discriminator)
+        # The spectral-norm power iterations depend on the weights only: all of them run on a side
+        # stream while layer 0 (im2col + GEMM + activation) runs here, instead of sitting in front
+        # of every convolution of the chain.
         Ho, Wo = H // 2, W // 2
-        col = T4(n, Ho, Wo, 64)
-        col.hi = _e((n, Ho, Wo, 64), dev, torch.bfloat16)
-        col.lo = _e((n, Ho, Wo, 64), dev, torch.bfloat16)
-        ops.im2col_small(xd, 4, 2, 1, col.hi, col.lo, 64)
-        self.col = col
         w0 = self._w0()
         Cop = rup(w0.shape[0], 64)
-        self.sn_first = None
-        alpha0 = None
-        if self.sn0:
-            self.sn_first = SpectralNorm(enc[0].weight_u, enc[0].weight_v)
-            alpha0 = self.sn_first.forward(w0, D.training, self.need_grad)
+        sns = [SpectralNorm(enc[idx].weight_u, enc[idx].weight_v) for idx in (2, 5, 8)]
+        self.sn_first = SpectralNorm(enc[0].weight_u, enc[0].weight_v) if self.sn0 else None
+
+        def power_iterations():
+            a0 = self.sn_first.forward(w0, D.training, self.need_grad) if self.sn_first is not None else None
+            return a0, [sn.forward(enc[idx].weight_orig, D.training, self.need_grad)
+                        for sn, idx in zip(sns, (2, 5, 8))]
+
+        def im2col():
+            col = T4(n, Ho, Wo, 64)
+            col.hi = _e((n, Ho, Wo, 64), dev, torch.bfloat16)
+            col.lo = _e((n, Ho, Wo, 64), dev, torch.bfloat16)
+            ops.im2col_small(xd, 4, 2, 1, col.hi, col.lo, 64)
+            return col, self._pack0("fwd")
+
+        from . import streams
+        (alpha0, alphas), (col, w0p) = streams.concurrently(power_iterations, im2col)
+        self.col = col
         self.alpha0 = alpha0
         z0 = T4(n, Ho, Wo, Cop)
         z0.f32 = _e((n, Ho, Wo, Cop), dev)
-        ops.conv_gemm(conv.gemm_nt([col.hi.view(-1, 64), col.lo.view(-1, 64)], self._pack0("fwd"),
+        ops.conv_gemm(conv.gemm_nt([col.hi.view(-1, 64), col.lo.view(-1, 64)], w0p,
                                    z0.f32.view(-1, Cop), alpha=alpha0))
         self.z0 = z0
         act0 = BnActNode(tape, z0, None, ops.ACT_LRELU, "enc0.act")
@@ -519,8 +529,7 @@ class EncoderRunner:
         self.layers = []
         for li, idx in enumerate((2, 5, 8)):
             cmod, bmod = enc[idx], enc[idx + 1]
-            sn = SpectralNorm(cmod.weight_u, cmod.weight_v)
-            cn = ConvNode(tape, "s2", a, cmod.weight_orig, "enc%d" % idx, sn=sn)
+            cn = ConvNode(tape, "s2", a, cmod.weight_orig, "enc%d" % idx, sn=sns[li], alpha=alphas[li])
             z = tape.add(cn)
             last = (li == 2)
             bn = BnActNode(tape, z, _bn_tuple(bmod), ops.ACT_LRELU, "enc%d.bn" % idx, want_f32=last,
@@ -618,21 +627,29 @@ class LogitsRunner:
         tape = Tape(_CACHE, training=L.training, need_grad=self.need_grad, planes=2, dtype=ops.BF16)
         self.tape = tape
         x = T4(n, H, W, Cc)
-        x.hi = _e((n, H, W, Cc), dev, torch.bfloat16)
-        x.lo = _e((n, H, W, Cc), dev, torch.bfloat16)
-        ops.pack_nchw(h_code.detach(), c_code.detach().contiguous().view(n, Ce), x.hi, x.lo, Cc)
-        self.x, self.Cf = x, Cf
         sn = SpectralNorm(seq[0].weight_u, seq[0].weight_v)
-        cn = ConvNode(tape, "s1", x, seq[0].weight_orig, "logits.conv", sn=sn)
+        self.sn3 = SpectralNorm(seq[3].weight_u, seq[3].weight_v)
+        w3 = seq[3].weight_orig
+
+        def power_iterations():      # weights only: off the activation chain (side stream)
+            return (sn.forward(seq[0].weight_orig, L.training, self.need_grad),
+                    self.sn3.forward(w3, L.training, self.need_grad))
+
+        def pack_input():
+            x.hi = _e((n, H, W, Cc), dev, torch.bfloat16)
+            x.lo = _e((n, H, W, Cc), dev, torch.bfloat16)
+            ops.pack_nchw(h_code.detach(), c_code.detach().contiguous().view(n, Ce), x.hi, x.lo, Cc)
+
+        from . import streams
+        (alpha, inv_sigma), _ = streams.concurrently(power_iterations, pack_input)
+        self.x, self.Cf = x, Cf
+        cn = ConvNode(tape, "s1", x, seq[0].weight_orig, "logits.conv", sn=sn, alpha=alpha)
         z = tape.add(cn)
         bn = BnActNode(tape, z, _bn_tuple(seq[1]), ops.ACT_LRELU, "logits.bn", want_f32=True,
                        want_planes=False)
         a = tape.add(bn)
         self.cn, self.bn, self.a = cn, bn, a
         # final layer: dot product over the 4x4 x C features, spectral norm on a [1, 16C] matrix
-        w3 = seq[3].weight_orig
-        self.sn3 = SpectralNorm(seq[3].weight_u, seq[3].weight_v)
-        inv_sigma = self.sn3.forward(w3, L.training, self.need_grad)
         feat = a.f32.view(n, H * W * a.C)
         wrow = self._w3_perm(a.C)
         t = _e((n, 1), dev)

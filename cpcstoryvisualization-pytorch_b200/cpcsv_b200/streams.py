@@ -14,14 +14,25 @@ HIGH_PRIORITY = -1      # CUDA: numerically lower = scheduled first
 LOW_PRIORITY = -1
 
 _POOLS = {}             # (kind, device, parent stream id) -> [streams]
+_LENT = {}              # same key -> number of pool streams lent to forks that are still open
 _DETACHED_OPEN = [0]    # detached branches issued and not yet joined
 
 
-def _side_streams(kind, parent, n, priority=HIGH_PRIORITY):
-    streams = _POOLS.setdefault((kind, parent.device, parent.cuda_stream), [])
-    while len(streams) < n:
+def _borrow(kind, parent, n, priority=HIGH_PRIORITY):
+    """n side streams of `parent` that no open fork of the same parent is using: the last piece of
+    a fork runs on the parent itself and may fork again (nested), and must not be handed the
+    streams its siblings are running on"""
+    key = (kind, parent.device, parent.cuda_stream)
+    streams = _POOLS.setdefault(key, [])
+    first = _LENT.get(key, 0)
+    while len(streams) < first + n:
         streams.append(torch.cuda.Stream(device=parent.device, priority=priority))
-    return streams[:n]
+    _LENT[key] = first + n
+    return key, streams[first:first + n]
+
+
+def _give_back(key, n):
+    _LENT[key] -= n
 
 
 def step_stream(device=None):
@@ -47,16 +58,19 @@ def concurrently(*thunks, enabled=True):
     if not (enabled and ENABLED and torch.cuda.is_available() and len(thunks) > 1):
         return [t() for t in thunks]
     main = torch.cuda.current_stream()
-    streams = _side_streams("fork", main, len(thunks) - 1)
-    results = [None] * len(thunks)
-    for st in streams:
-        st.wait_stream(main)
-    for i, t in enumerate(thunks[:-1]):
-        with torch.cuda.stream(streams[i]):
-            results[i] = t()
-    results[-1] = thunks[-1]()
-    for st in streams:
-        main.wait_stream(st)
+    key, streams = _borrow("fork", main, len(thunks) - 1)
+    try:
+        results = [None] * len(thunks)
+        for st in streams:
+            st.wait_stream(main)
+        for i, t in enumerate(thunks[:-1]):
+            with torch.cuda.stream(streams[i]):
+                results[i] = t()
+        results[-1] = thunks[-1]()
+        for st in streams:
+            main.wait_stream(st)
+    finally:
+        _give_back(key, len(streams))
     knets.sync_point(streams, reset_state_order=_DETACHED_OPEN[0] == 0)
     return results
 
@@ -73,7 +87,7 @@ class Detached:
             self.results = [t() for t in thunks]
             return
         main = torch.cuda.current_stream()
-        self.streams = _side_streams("detached", main, len(thunks), LOW_PRIORITY)
+        self._key, self.streams = _borrow("detached", main, len(thunks), LOW_PRIORITY)
         self.results = []
         _DETACHED_OPEN[0] += 1
         for st, t in zip(self.streams, thunks):
@@ -90,6 +104,7 @@ class Detached:
             for st in self.streams:
                 main.wait_stream(st)
             _DETACHED_OPEN[0] -= 1
+            _give_back(self._key, len(self.streams))
             knets.sync_point(self.streams, reset_state_order=_DETACHED_OPEN[0] == 0)
             self.streams = []
         return self.results
