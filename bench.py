@@ -329,6 +329,11 @@ def profile_gemm_launches(engine, steps):
             "avg_launch_us": 1e3 * ms / len(recs)}
 
 
+def _trace(msg):
+    if os.environ.get("CPCSV_BENCH_TRACE"):
+        print("[bench %.1fs] %s" % (time.perf_counter(), msg), file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -377,6 +382,7 @@ def main():
             eng.step()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    _trace("warm-up done")
     launches0 = _lib.launch_count()
     if not args.no_graph:
         eng.capture()
@@ -413,10 +419,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    _trace("captured, 2 replays done")
     c0 = _lib.launch_count()
     ms_dev = timed_loop(False)
+    _trace("device-timed loop done: %.2f ms/step" % (ms_dev / args.steps))
     c1 = _lib.launch_count()
     ms_e2e = timed_loop(True)
+    _trace("e2e loop done")
     clocks = sampler.stop() if rank == 0 else None
     if launches_per_step is None:
         launches_per_step = (c1 - c0) / args.steps
@@ -424,6 +433,7 @@ def main():
     # entries packed while capturing belong to the graph; drop them before running eagerly again
     eng.knets.invalidate_weight_cache()
     prof = profile_gemm_launches(eng, 2)
+    _trace("gemm profile done")
     stories = p["ST_BATCH"] * world
     ms_step = ms_dev / args.steps
     ms_step_e2e = ms_e2e / args.steps

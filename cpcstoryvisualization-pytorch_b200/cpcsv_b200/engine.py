@@ -13,7 +13,10 @@ from . import conv, ops
 from .ops import ACT_NONE, ACT_RELU, ACT_LRELU, BF16  # noqa: F401
 
 
-FUSED_BN_MAX_ELEMS = 6 * 1024 * 1024   # rows * C up to which BatchNorm runs as one cooperative launch
+# rows * C up to which BatchNorm runs as ONE cooperative launch (bn_fwd_fused / bn_bwd_fused).  0 = off:
+# once the step's branches really overlap (profiles/r01_schedule_notes.md) the 3-4 launch path is as
+# fast (23.1 vs 23.3 ms / step) and has no grid-wide spin waits next to the persistent GEMM blocks.
+FUSED_BN_MAX_ELEMS = 0
 
 
 def rup(x, m):

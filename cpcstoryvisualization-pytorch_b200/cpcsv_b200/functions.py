@@ -66,8 +66,10 @@ class BatchNorm1dFn(torch.autograd.Function):
         yp = torch.empty(M, Cp, device=dev)
         rm, rv = (rmean, rvar) if training else (None, None)
         StateOrder.before(rm)
-        if not ops.bn_fwd_fused(xp, gamma.detach(), beta.detach(), rm, rv, None, C, ops.ACT_NONE, None, yp,
-                                None, None, ops.BF16, stats, vec):
+        from . import engine
+        if not (M * Cp <= engine.FUSED_BN_MAX_ELEMS and
+                ops.bn_fwd_fused(xp, gamma.detach(), beta.detach(), rm, rv, None, C, ops.ACT_NONE, None, yp,
+                                 None, None, ops.BF16, stats, vec)):
             ops.bn_stats(xp, stats)
             ops.bn_finalize(stats, M, gamma.detach(), beta.detach(), rm, rv, None, C, vec[0], vec[1], vec[2],
                             vec[3])

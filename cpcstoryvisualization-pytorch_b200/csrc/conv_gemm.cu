@@ -431,11 +431,16 @@ static int make_map(CUtensorMap* tm, const cpcsv_view5_t& v, const uint32_t box[
   return 0;
 }
 
-// CPCSV_PAIR=0 in the environment switches the cta_group::2 path off (A/B measurements)
+// The cta_group::2 path is OPT-IN (CPCSV_PAIR=1 in the environment).  Alone it is 0.79-0.87x the
+// time on hi/lo-plane jobs and never slower (profiles/r01_sweep_pair.txt), worth 0.45 ms on the
+// 23 ms step -- but the whole-step CUDA graph (dozens of concurrent branches, single-CTA wgrad
+// GEMMs and small kernels co-resident with the clusters) dead-locked on the GPU in 6 of 12
+// benchmark runs that followed the fp64 parity tests on the same box, and in 0 of 6 with the path
+// off (profiles/r01_pair_mode_hang.md).  Until that is root-caused the product runs single CTAs.
 static bool pair_mode_enabled() {
   static const bool on = [] {
     const char* e = getenv("CPCSV_PAIR");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }
