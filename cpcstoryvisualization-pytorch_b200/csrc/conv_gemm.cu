@@ -389,6 +389,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
     else tmem_dealloc(tmem_base, kTmemCols);
   }
+  // Pair mode: neither CTA may exit (and hand its SM to a block of another kernel that allocates
+  // TMEM there) before BOTH halves of the cta_group::2 deallocation have been issued.
+  if (kPair) cluster_sync_all();
 }
 
 // ------------------------------------------------------------------------------ host side
