@@ -46,300 +46,6 @@ static inline int grid_for(int64_t work_items, int threads, int max_blocks_per_s
   return static_cast<int>(blocks);
 }
 
-// ------------------------------------------------------------------------- bn_stats
-// block = 32 channel-quads x 8 row lanes; grid.x over 128-channel groups, grid.y over rows.
-__global__ void bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx,
-                                double* __restrict__ stats) {
-  const int cq = threadIdx.x & 31;
-  const int rl = threadIdx.x >> 5;
-  const int c = (blockIdx.x * 32 + cq) * 4;
-  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-  if (c < C) {
-    // 4 independent 16-byte loads in flight per thread; fp64 accumulation keeps the
-    // E[x^2] - mean^2 cancellation exact
-    const int64_t step = static_cast<int64_t>(gridDim.y) * 8;
-    int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + rl;
-    for (; r + 3 * step < rows; r += 4 * step) {
-      float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(x + (r + u * step) * ldx + c);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        s[0] += v[u].x; ss[0] += static_cast<double>(v[u].x) * v[u].x;
-        s[1] += v[u].y; ss[1] += static_cast<double>(v[u].y) * v[u].y;
-        s[2] += v[u].z; ss[2] += static_cast<double>(v[u].z) * v[u].z;
-        s[3] += v[u].w; ss[3] += static_cast<double>(v[u].w) * v[u].w;
-      }
-    }
-    for (; r < rows; r += step) {
-      const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
-      s[0] += v.x; ss[0] += static_cast<double>(v.x) * v.x;
-      s[1] += v.y; ss[1] += static_cast<double>(v.y) * v.y;
-      s[2] += v.z; ss[2] += static_cast<double>(v.z) * v.z;
-      s[3] += v.w; ss[3] += static_cast<double>(v.w) * v.w;
-    }
-  }
-  __shared__ double sh[8][32][8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sh[rl][cq][j] = s[j];
-    sh[rl][cq][4 + j] = ss[j];
-  }
-  __syncthreads();
-  if (rl == 0 && c < C) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      double t = 0;
-      for (int k = 0; k < 8; ++k) t += sh[k][cq][j];
-      // per-block partial (no atomics: hundreds of blocks hitting 2C addresses serialise in L2)
-      double* part = stats + static_cast<int64_t>(2 * C) * (1 + blockIdx.y);
-      if (j < 4) part[c + j] = t;
-      else part[C + c + (j - 4)] = t;
-    }
-  }
-}
-
-// out[i] = sum_p part[p][i] for i < n; partials start at out + n
-__global__ void sum_partials_kernel(double* __restrict__ out, int n, int parts) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double t = 0;
-  for (int p = 0; p < parts; ++p) t += out[static_cast<int64_t>(n) * (1 + p) + i];
-  out[i] = t;
-}
-
-// number of row-blocks (= partial slots) the reduction kernels use for a [rows, C] problem
-static inline int reduction_parts(int64_t rows, int C) {
-  const int64_t gx = ceil_div(C, 128);
-  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 4, gx);
-  const int64_t max_gy = ceil_div(rows, 8);
-  if (gy > max_gy) gy = max_gy;
-  return static_cast<int>(gy < 1 ? 1 : gy);
-}
-
-__global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t rows, int C,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* running_mean, float* running_var,
-                                   const int32_t* __restrict__ chan_map, int C_valid, float eps,
-                                   float momentum, float* mean, float* invstd, float* scale,
-                                   float* shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (c >= C_valid || (chan_map && chan_map[c] < 0)) {  // padding channel
-    mean[c] = 0.f; invstd[c] = 0.f; scale[c] = 0.f; shift[c] = 0.f;
-    return;
-  }
-  const double n = static_cast<double>(rows);
-  const double m = stats[c] / n;
-  double var = stats[C + c] / n - m * m;
-  if (var < 0) var = 0;
-  const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  const int p = chan_map ? chan_map[c] : c;
-  const float g = gamma[p], b = beta[p];
-  mean[c] = static_cast<float>(m);
-  invstd[c] = is;
-  scale[c] = g * is;
-  shift[c] = b - static_cast<float>(m) * g * is;
-  if (running_mean) {
-    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
-    running_mean[p] = (1.f - momentum) * running_mean[p] + momentum * static_cast<float>(m);
-    running_var[p] = (1.f - momentum) * running_var[p] + momentum * static_cast<float>(unbiased);
-  }
-}
-
-// ------------------------------------------------------------------------- bn_act_pack
-__global__ void bn_act_pack_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx,
-                                   const float* __restrict__ scale, const float* __restrict__ shift,
-                                   int act, const float* __restrict__ mod, int64_t ldmod,
-                                   float* __restrict__ y, int64_t ldy, uint16_t* __restrict__ hi,
-                                   uint16_t* __restrict__ lo, int64_t ldp, int dtype) {
-  const int cq = C >> 2;
-  const int64_t total = rows * cq;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / cq;
-    const int c = static_cast<int>(i - r * cq) * 4;
-    const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
-    float v[4] = {xv.x, xv.y, xv.z, xv.w};
-    if (scale) {
-      const float4 sc = *reinterpret_cast<const float4*>(scale + c);
-      const float4 sf = *reinterpret_cast<const float4*>(shift + c);
-      v[0] = fmaf(v[0], sc.x, sf.x); v[1] = fmaf(v[1], sc.y, sf.y);
-      v[2] = fmaf(v[2], sc.z, sf.z); v[3] = fmaf(v[3], sc.w, sf.w);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], act);
-    if (mod) {
-      const float4 mv = *reinterpret_cast<const float4*>(mod + r * ldmod + c);
-      v[0] *= 1.f + mv.x; v[1] *= 1.f + mv.y; v[2] *= 1.f + mv.z; v[3] *= 1.f + mv.w;
-    }
-    if (y) *reinterpret_cast<float4*>(y + r * ldy + c) = make_float4(v[0], v[1], v[2], v[3]);
-    if (hi) {
-      uint16_t h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) split16(v[j], dtype, h[j], l[j]);
-      uint2 hv, lv;
-      hv.x = h[0] | (static_cast<uint32_t>(h[1]) << 16);
-      hv.y = h[2] | (static_cast<uint32_t>(h[3]) << 16);
-      *reinterpret_cast<uint2*>(hi + r * ldp + c) = hv;
-      if (lo) {
-        lv.x = l[0] | (static_cast<uint32_t>(l[1]) << 16);
-        lv.y = l[2] | (static_cast<uint32_t>(l[3]) << 16);
-        *reinterpret_cast<uint2*>(lo + r * ldp + c) = lv;
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------- bn backward
-// shared by reduce and apply: g = dL/d(pre-activation) and xhat for 4 channels
-struct BwdElem {
-  float g[4], xhat[4], a[4];
-};
-__device__ __forceinline__ BwdElem bwd_elem(const float* __restrict__ x, const float* __restrict__ dy,
-                                            int64_t r, int c, int64_t ldx, int64_t lddy,
-                                            const float* __restrict__ scale,
-                                            const float* __restrict__ shift,
-                                            const float* __restrict__ mean,
-                                            const float* __restrict__ invstd, int act,
-                                            const float* __restrict__ mod, int64_t ldmod) {
-  BwdElem e;
-  const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
-  const float4 dv = *reinterpret_cast<const float4*>(dy + r * lddy + c);
-  const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-  const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
-  float ms[4] = {0.f, 0.f, 0.f, 0.f};
-  if (mod) {
-    const float4 mv = *reinterpret_cast<const float4*>(mod + r * ldmod + c);
-    ms[0] = mv.x; ms[1] = mv.y; ms[2] = mv.z; ms[3] = mv.w;
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float pre = xs[j];
-    if (scale) pre = fmaf(xs[j], scale[c + j], shift[c + j]);
-    e.a[j] = apply_act(pre, act);
-    const float da = ds[j] * (1.f + ms[j]);
-    e.g[j] = da * act_grad(pre, act);
-    e.xhat[j] = mean ? (xs[j] - mean[c + j]) * invstd[c + j] : 0.f;
-  }
-  return e;
-}
-
-__global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                     int64_t rows, int C, int64_t ldx, int64_t lddy,
-                                     const float* __restrict__ scale, const float* __restrict__ shift,
-                                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                                     int act, const float* __restrict__ mod, int64_t ldmod,
-                                     double* __restrict__ sums) {
-  const int cq = threadIdx.x & 31;
-  const int rl = threadIdx.x >> 5;
-  const int c = (blockIdx.x * 32 + cq) * 4;
-  double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
-  if (c < C) {
-    const int64_t step = static_cast<int64_t>(gridDim.y) * 8;
-    int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + rl;
-    for (; r + step < rows; r += 2 * step) {   // two rows in flight
-      const BwdElem e0 = bwd_elem(x, dy, r, c, ldx, lddy, scale, shift, mean, invstd, act, mod, ldmod);
-      const BwdElem e1 = bwd_elem(x, dy, r + step, c, ldx, lddy, scale, shift, mean, invstd, act, mod, ldmod);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s[j] += static_cast<double>(e0.g[j]) + e1.g[j];
-        sx[j] += static_cast<double>(e0.g[j]) * e0.xhat[j] + static_cast<double>(e1.g[j]) * e1.xhat[j];
-      }
-    }
-    for (; r < rows; r += step) {
-      const BwdElem e = bwd_elem(x, dy, r, c, ldx, lddy, scale, shift, mean, invstd, act, mod, ldmod);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s[j] += e.g[j];
-        sx[j] += static_cast<double>(e.g[j]) * e.xhat[j];
-      }
-    }
-  }
-  __shared__ double sh[8][32][8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sh[rl][cq][j] = s[j];
-    sh[rl][cq][4 + j] = sx[j];
-  }
-  __syncthreads();
-  if (rl == 0 && c < C) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      double t = 0;
-      for (int k = 0; k < 8; ++k) t += sh[k][cq][j];
-      double* part = sums + static_cast<int64_t>(2 * C) * (1 + blockIdx.y);
-      if (j < 4) part[c + j] = t;
-      else part[C + c + (j - 4)] = t;
-    }
-  }
-}
-
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                    int64_t rows, int C, int64_t ldx, int64_t lddy,
-                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ gamma,
-                                    const int32_t* __restrict__ chan_map, int C_valid, int act,
-                                    const float* __restrict__ mod, int64_t ldmod,
-                                    const double* __restrict__ sums, int has_bn,
-                                    float* __restrict__ dx, int64_t lddx, uint16_t* __restrict__ dx16,
-                                    int64_t ld16, float* __restrict__ dmod, int64_t lddmod,
-                                    uint16_t* __restrict__ dmod16, int64_t lddmod16,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int cq = C >> 2;
-  const int64_t total = rows * cq;
-  const float inv_rows = 1.f / static_cast<float>(rows);
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / cq;
-    const int c = static_cast<int>(i - r * cq) * 4;
-    const BwdElem e = bwd_elem(x, dy, r, c, ldx, lddy, scale, shift, has_bn ? mean : nullptr,
-                               invstd, act, mod, ldmod);
-    float d[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (has_bn) {
-        const float mg = static_cast<float>(sums[c + j]) * inv_rows;
-        const float mgx = static_cast<float>(sums[C + c + j]) * inv_rows;
-        // scale = gamma * invstd
-        d[j] = scale[c + j] * (e.g[j] - mg - e.xhat[j] * mgx);
-      } else {
-        d[j] = e.g[j];
-      }
-    }
-    if (dx) *reinterpret_cast<float4*>(dx + r * lddx + c) = make_float4(d[0], d[1], d[2], d[3]);
-    if (dx16) {
-      uint2 v;
-      v.x = to16(d[0], 1) | (static_cast<uint32_t>(to16(d[1], 1)) << 16);
-      v.y = to16(d[2], 1) | (static_cast<uint32_t>(to16(d[3], 1)) << 16);
-      *reinterpret_cast<uint2*>(dx16 + r * ld16 + c) = v;
-    }
-    if (dmod || dmod16) {
-      const float4 dv = *reinterpret_cast<const float4*>(dy + r * lddy + c);
-      const float m[4] = {dv.x * e.a[0], dv.y * e.a[1], dv.z * e.a[2], dv.w * e.a[3]};
-      if (dmod) *reinterpret_cast<float4*>(dmod + r * lddmod + c) = make_float4(m[0], m[1], m[2], m[3]);
-      if (dmod16) {
-        uint2 v;
-        v.x = to16(m[0], 1) | (static_cast<uint32_t>(to16(m[1], 1)) << 16);
-        v.y = to16(m[2], 1) | (static_cast<uint32_t>(to16(m[3], 1)) << 16);
-        *reinterpret_cast<uint2*>(dmod16 + r * lddmod16 + c) = v;
-      }
-    }
-    if (r == 0 && dgamma) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (c + j < C_valid) {
-          const int p = chan_map ? chan_map[c + j] : c + j;
-          if (p < 0) continue;
-          dgamma[p] = static_cast<float>(sums[C + c + j]);
-          dbeta[p] = static_cast<float>(sums[c + j]);
-        }
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------- pack_nchw
 __global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C, int H, int W, int64_t sn,
                                  int64_t sc, int64_t sh, int64_t sw, const float* __restrict__ bcast,
@@ -740,93 +446,7 @@ using namespace cpcsv;
 
 #define STREAM(s) static_cast<cudaStream_t>(s)
 
-#if 0  // the BatchNorm entry points moved to bn.cu (register-resident per-channel constants)
-extern "C" int cpcsv_bn_stats(const float* x, int64_t rows, int32_t C, int64_t ldx, double* stats,
-                              cpcsv_stream_t stream) {
-  CPCSV_REQUIRE(x && stats && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_stats: args");
-  const int parts = reduction_parts(rows, C);
-  dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), static_cast<unsigned>(parts));
-  bn_stats_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, rows, C, ldx, stats);
-  int rc = launched("bn_stats");
-  if (rc) return rc;
-  sum_partials_kernel<<<static_cast<unsigned>(ceil_div(2 * C, 256)), 256, 0, STREAM(stream)>>>(stats, 2 * C,
-                                                                                             parts);
-  return launched("bn_stats/sum");
-}
-
-extern "C" int64_t cpcsv_bn_workspace_doubles(int64_t rows, int32_t C) {
-  return static_cast<int64_t>(2 * C) * (1 + reduction_parts(rows, C));
-}
-
-extern "C" int cpcsv_bn_finalize(const double* stats, int64_t rows, int32_t C, const float* gamma,
-                                 const float* beta, float* running_mean, float* running_var,
-                                 const int32_t* chan_map, int32_t C_valid, float eps, float momentum,
-                                 float* mean, float* invstd, float* scale, float* shift,
-                                 cpcsv_stream_t stream) {
-  CPCSV_REQUIRE(stats && gamma && beta && mean && invstd && scale && shift && C > 0 && C_valid <= C,
-                "bn_finalize: args");
-  bn_finalize_kernel<<<static_cast<unsigned>(ceil_div(C, 256)), 256, 0, STREAM(stream)>>>(
-      stats, rows, C, gamma, beta, running_mean, running_var, chan_map, C_valid, eps, momentum, mean,
-      invstd, scale, shift);
-  return launched("bn_finalize");
-}
-
-extern "C" int cpcsv_bn_act_pack(const float* x, int64_t rows, int32_t C, int64_t ldx,
-                                 const float* scale, const float* shift, int32_t act,
-                                 const float* mod, int64_t ldmod, float* y, int64_t ldy, void* hi,
-                                 void* lo, int64_t ldp, int32_t dtype, cpcsv_stream_t stream) {
-  CPCSV_REQUIRE(x && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_act_pack: args");
-  CPCSV_REQUIRE((!mod || ldmod % 4 == 0) && (!y || ldy % 4 == 0) && (!hi || ldp % 4 == 0),
-                "bn_act_pack: pitches must be multiples of 4");
-  CPCSV_REQUIRE(hi || y, "bn_act_pack: no output");
-  CPCSV_REQUIRE(!lo || hi, "bn_act_pack: lo without hi");
-  const int64_t work = rows * (C / 4);
-  bn_act_pack_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
-      x, rows, C, ldx, scale, shift, act, mod, ldmod, y, ldy, static_cast<uint16_t*>(hi),
-      static_cast<uint16_t*>(lo), ldp, dtype);
-  return launched("bn_act_pack");
-}
-
-extern "C" int cpcsv_bn_bwd_reduce(const float* x, const float* dy, int64_t rows, int32_t C,
-                                   int64_t ldx, int64_t lddy, const float* scale, const float* shift,
-                                   const float* mean, const float* invstd, int32_t act,
-                                   const float* mod, int64_t ldmod, double* sums,
-                                   cpcsv_stream_t stream) {
-  CPCSV_REQUIRE(x && dy && sums && mean && invstd && rows > 0 && C > 0 && C % 4 == 0 &&
-                    ldx % 4 == 0 && lddy % 4 == 0,
-                "bn_bwd_reduce: args");
-  const int parts = reduction_parts(rows, C);
-  dim3 grid(static_cast<unsigned>(ceil_div(C, 128)), static_cast<unsigned>(parts));
-  bn_bwd_reduce_kernel<<<grid, 256, 0, STREAM(stream)>>>(x, dy, rows, C, ldx, lddy, scale, shift, mean,
-                                                         invstd, act, mod, ldmod, sums);
-  int rc = launched("bn_bwd_reduce");
-  if (rc) return rc;
-  sum_partials_kernel<<<static_cast<unsigned>(ceil_div(2 * C, 256)), 256, 0, STREAM(stream)>>>(sums, 2 * C,
-                                                                                             parts);
-  return launched("bn_bwd_reduce/sum");
-}
-
-extern "C" int cpcsv_bn_bwd_apply(const float* x, const float* dy, int64_t rows, int32_t C,
-                                  int64_t ldx, int64_t lddy, const float* scale, const float* shift,
-                                  const float* mean, const float* invstd, const float* gamma,
-                                  const int32_t* chan_map, int32_t C_valid, int32_t act,
-                                  const float* mod, int64_t ldmod, const double* sums, int32_t has_bn,
-                                  float* dx, int64_t lddx, void* dx16, int64_t ld16, float* dmod,
-                                  int64_t lddmod, void* dmod16, int64_t lddmod16, float* dgamma,
-                                  float* dbeta, cpcsv_stream_t stream) {
-  (void)gamma;
-  CPCSV_REQUIRE(x && dy && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0,
-                "bn_bwd_apply: args");
-  CPCSV_REQUIRE(!has_bn || (sums && scale && mean && invstd), "bn_bwd_apply: BN tensors missing");
-  const int64_t work = rows * (C / 4);
-  bn_bwd_apply_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
-      x, dy, rows, C, ldx, lddy, scale, shift, mean, invstd, gamma, chan_map, C_valid, act, mod, ldmod,
-      sums, has_bn, dx, lddx, static_cast<uint16_t*>(dx16), ld16, dmod, lddmod,
-      static_cast<uint16_t*>(dmod16), lddmod16, dgamma, dbeta);
-  return launched("bn_bwd_apply");
-}
-
-#endif
+// (the BatchNorm entry points live in bn.cu)
 
 extern "C" int cpcsv_pack_nchw(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t sn,
                                int64_t sc, int64_t sh, int64_t sw, const float* bcast, int32_t Cb,

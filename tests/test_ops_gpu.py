@@ -245,3 +245,68 @@ def test_head_conv_tanh_fwd(Co, C, dtype, two):
     ref = torch.tanh(torch.nn.functional.conv2d(
         (hi.double() + (lo.double() if two else 0)).permute(0, 3, 1, 2), w.double(), padding=1))
     assert close(g["y"], ref, 2e-6)
+
+
+def test_sgemm_split_k_paths():
+    """the conditioning-path SGEMM splits K over the grid (atomic partial sums into a kernel-zeroed
+    output, bias from split 0): CA_NET-sized K, all three operand layouts, with and without
+    accumulation into an existing output"""
+    x, w, bias = rnd(18, 1780, seed=31), rnd(248, 1780, seed=32, scale=0.05), rnd(248, seed=33)
+    (g, _), (c, _) = both("linear_f32", [x, w, bias], dict(y=torch.full((18, 248), 7.0)))
+    assert close(g["y"], c["y"], 2e-6)
+    (g, _), (c, _) = both("linear_f32", [x, w, bias], dict(y=torch.full((18, 248), 7.0)), accumulate=True)
+    assert close(g["y"], c["y"], 2e-6)
+    a, b = rnd(450, 124, seed=34), rnd(450, 372, seed=35)          # K = rows (5 steps x 90)
+    (g, _), (c, _) = both("linear_tn_f32", [a, b], dict(y=torch.zeros(124, 372)))
+    assert close(g["y"], c["y"], 2e-6)
+    dy, w2 = rnd(90, 1095, seed=36), rnd(1095, 465, seed=37, scale=0.05)
+    (g, _), (c, _) = both("linear_nn_f32", [dy, w2], dict(y=torch.zeros(90, 465)))
+    assert close(g["y"], c["y"], 2e-6)
+
+
+def test_gru_sequence_matches_torch_grucell():
+    """functions.GRUSeqFn (hoisted input projections, per-step recurrent GEMM + gate kernel) vs a
+    loop of torch.nn.GRUCell in fp64: outputs and every gradient (reference model.py:313-346)"""
+    from cpcsv_b200 import functions as Fx
+    T, B, I, H = 5, 18, 465, 365
+    cell = torch.nn.GRUCell(I, H).cuda()
+    x = rnd(T, B, I, seed=41).cuda().requires_grad_(True)
+    h0 = rnd(B, H, seed=42).cuda().requires_grad_(True)
+    gout = rnd(T, B, H, seed=43).cuda()
+    out = Fx.gru_sequence(x, h0, cell)
+    out.backward(gout)
+    got = [out.detach(), x.grad, h0.grad] + [p.grad for p in cell.parameters()]
+    ref_cell = torch.nn.GRUCell(I, H).double().cuda()
+    ref_cell.load_state_dict({k: v.double() for k, v in cell.state_dict().items()})
+    xr = x.detach().double().requires_grad_(True)
+    hr = h0.detach().double().requires_grad_(True)
+    h, outs = hr, []
+    for t in range(T):
+        h = ref_cell(xr[t], h)
+        outs.append(h)
+    ref = torch.stack(outs, 0)
+    ref.backward(gout.double())
+    want = [ref.detach(), xr.grad, hr.grad] + [p.grad for p in ref_cell.parameters()]
+    for a, b in zip(got, want):
+        assert close(a.cpu(), b.cpu(), 2e-5)
+
+
+def test_nested_forks_borrow_distinct_streams():
+    """streams.concurrently: the last piece of a fork runs on the parent stream and may fork again;
+    the nested fork must not be handed the side streams its siblings are running on"""
+    from cpcsv_b200 import streams
+    seen = {}
+
+    def leaf(tag):
+        seen[tag] = torch.cuda.current_stream().cuda_stream
+        return tag
+
+    def inner():
+        return streams.concurrently(lambda: leaf("in0"), lambda: leaf("in1"))
+
+    streams.concurrently(lambda: leaf("a"), lambda: leaf("b"), inner)
+    torch.cuda.synchronize()
+    main = torch.cuda.current_stream().cuda_stream
+    assert seen["in1"] == main                       # last piece of the nested fork: the parent
+    assert len({seen["a"], seen["b"], seen["in0"], main}) == 4
+    assert not any(streams._LENT.values())           # everything given back
