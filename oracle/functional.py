@@ -128,6 +128,69 @@ def _trunk(sd, zmc_all, use_segment=True):
     return img, seg
 
 
+def down_block(sd, name, x):
+    """downBlock: conv3x3 stride 2 pad 1 WITH bias -> BN -> ReLU (cascade_model.py:36-41)."""
+    x = F.conv2d(x, sd[name + ".0.weight"], sd[name + ".0.bias"], 2, 1)
+    return F.relu(batch_norm(sd, name + ".1", x))
+
+
+def seg_encoder(sd, seg):
+    """presample + downsample1..4_seg (cascade_model.py:312-320, 413-418): mask (n,1,64,64) ->
+    (g_seg1 (4x4), g_seg2 (8x8), g_seg3 (16x16), g_seg4 (32x32))."""
+    z = F.conv2d(seg, sd["presample.0.weight"], None, 1, 1)
+    z = F.relu(batch_norm(sd, "presample.1", z))
+    g4 = down_block(sd, "downsample1_seg", z)
+    g3 = down_block(sd, "downsample2_seg", g4)
+    g2 = down_block(sd, "downsample3_seg", g3)
+    g1 = down_block(sd, "downsample4_seg", g2)
+    return g1, g2, g3, g4
+
+
+def _trunk_cascade(sd, zmc_all):
+    """cascade_model.py:399-437 / 477-511: the segmentation trunk runs first, its mask is
+    re-encoded by presample + 4 downBlocks, and the image trunk is modulated by the
+    re-encoded features g_seg1 / g_seg2.  Returns (img, seg, latents) with latents =
+    ((zmc_seg, h_seg1, h_seg2, h_seg3), (g_seg1, g_seg2, g_seg3, g_seg4))."""
+    ngf = sd["upsample1.1.weight"].shape[1]
+    nseg = sd["upsample1_seg.1.weight"].shape[1]
+    zmc_img = F.relu(batch_norm(sd, "fc.1", F.linear(zmc_all, sd["fc.0.weight"]))).view(-1, ngf, 4, 4)
+    zmc_seg = F.relu(batch_norm(sd, "fc_seg.1", F.linear(zmc_all, sd["fc_seg.0.weight"]))).view(-1, nseg, 4, 4)
+    h1 = up_block(sd, "upsample1_seg", zmc_seg)
+    h2 = up_block(sd, "upsample2_seg", h1)
+    h3 = up_block(sd, "upsample3_seg", h2)
+    h4 = up_block(sd, "upsample4_seg", h3)
+    seg = torch.tanh(F.conv2d(h4, sd["img_seg.0.weight"], None, 1, 1))
+    g1, g2, g3, g4 = seg_encoder(sd, seg)
+    zmc_img = F.conv2d(g1, sd["seg_c.weight"], None, 1, 1) * zmc_img + zmc_img
+    h_img = up_block(sd, "upsample1", zmc_img)
+    h_img = F.conv2d(g2, sd["seg_c1.weight"], None, 1, 1) * h_img + h_img
+    for i in (2, 3, 4):
+        h_img = up_block(sd, "upsample%d" % i, h_img)
+    img = torch.tanh(F.conv2d(h_img, sd["img.0.weight"], None, 1, 1))
+    return img, seg, ((zmc_seg, h1, h2, h3), (g1, g2, g3, g4))
+
+
+def train_autoencoder(sd, real_segments):
+    """StoryGAN.train_autoencoder (cascade_model.py:528-540): mask -> encoder -> seg up-blocks
+    -> img_seg."""
+    g1, _g2, _g3, _g4 = seg_encoder(sd, real_segments)
+    h = g1
+    for i in (1, 2, 3, 4):
+        h = up_block(sd, "upsample%d_seg" % i, h)
+    return torch.tanh(F.conv2d(h, sd["img_seg.0.weight"], None, 1, 1))
+
+
+def is_cascade(sd):
+    return "presample.0.weight" in sd
+
+
+def _run_trunk(sd, zmc_all, use_segment):
+    if is_cascade(sd):
+        return _trunk_cascade(sd, zmc_all)
+    img, seg = _trunk(sd, zmc_all, use_segment)
+    return img, seg, None
+
+
 def _cond_to_latent(sd, motion_flat, crnn_code, zm_code, c_mu_rows):
     """model.py:371-378 / 436-443: image_net, filter_net, dynamic filter, concat."""
     zmc_code = torch.cat((zm_code, c_mu_rows), 1)
@@ -150,9 +213,9 @@ def sample_videos(sd, motion_input, content_input, noise, seg=False, use_segment
     m_flat = motion_input.reshape(B * V, -1)
     zm_code = sample_z_motion(sd, motion_input, V, noise)
     zmc_all = _cond_to_latent(sd, m_flat, crnn_code, zm_code, c_mu)
-    img, segm = _trunk(sd, zmc_all, use_segment)
+    img, segm, latents = _run_trunk(sd, zmc_all, use_segment)
     fake = img.view(B, V, 3, 64, 64).permute(0, 2, 1, 3, 4)
-    return None, fake, m_flat, m_flat, r_mu, r_logvar, (segm if seg else None)
+    return latents, fake, m_flat, m_flat, r_mu, r_logvar, (segm if seg else None)
 
 
 def sample_images(sd, motion_input, content_input, noise, seg=False, use_segment=True):
@@ -165,8 +228,8 @@ def sample_images(sd, motion_input, content_input, noise, seg=False, use_segment
     crnn_code = motion_content_rnn(sd, motion_input, c_mu)
     zm_code = sample_z_motion(sd, motion_input, 1, noise)
     zmc_all = _cond_to_latent(sd, motion_input, crnn_code, zm_code, c_mu)
-    img, segm = _trunk(sd, zmc_all, use_segment)
-    return None, img, motion_input, motion_input, c_mu, c_logvar, (segm if seg else None)
+    img, segm, latents = _run_trunk(sd, zmc_all, use_segment)
+    return latents, img, motion_input, motion_input, c_mu, c_logvar, (segm if seg else None)
 
 
 # ----------------------------------------------------------------------- discriminators
@@ -288,8 +351,9 @@ class OracleModel:
 
 
 def train_step(model, batch, noise, ratio=1.0, apply_optim=True):
-    """One iteration of GANTrainer.train (trainer.py:252-416), SEGMENT_LEARNING on,
-    CASCADE_MODEL off.  ``noise`` is a synth.NoiseFeed.  Returns a dict with the losses,
+    """One iteration of GANTrainer.train (trainer.py:252-416), SEGMENT_LEARNING on; with a
+    cascade generator state dict (CASCADE_MODEL, cascade_model.py) also the latent-MSE and
+    reconstruction losses of trainer.py:369-384, 412-413.  ``noise`` is a synth.NoiseFeed.  Returns a dict with the losses,
     the generated tensors of both generator passes and (via ``.grad``) all gradients."""
     p = model.p
     G, D_im, D_st, D_se = (model.nets[k] for k in ("G", "D_im", "D_st", "D_se"))
@@ -343,8 +407,22 @@ def train_step(model, batch, noise, ratio=1.0, apply_optim=True):
 
     # (4) generator update, trainer.py:365-416
     model.zero_grad("G")
-    _, st_fake, _, _, c_mu, c_logvar, _ = sample_videos(G, st_motion, st_content, noise)
-    _, im_fake, _, _, cim_mu, cim_logvar, se_fake = sample_images(G, im_motion, im_content, noise, seg=True)
+    video_latents, st_fake, _, _, c_mu, c_logvar, _ = sample_videos(G, st_motion, st_content, noise)
+    image_latents, im_fake, _, _, cim_mu, cim_logvar, se_fake = sample_images(G, im_motion, im_content, noise,
+                                                                              seg=True)
+    if video_latents is not None:
+        # trainer.py:370-380.  The reference unpacks the first tuple as (h_seg1..4) although it
+        # holds (zmc_seg, h_seg1, h_seg2, h_seg3): pairs are matched by position.
+        def latent_loss(latents):
+            hs, gs = latents
+            return sum(F.mse_loss(g, h) for g, h in zip(gs, hs))
+        video_latent_loss = latent_loss(video_latents)
+        image_latent_loss = latent_loss(image_latents)
+        rec_real = train_autoencoder(G, se_real)
+        rec_fake = train_autoencoder(G, se_fake)
+        reconstruct_loss = (F.mse_loss(rec_real, se_real) + F.mse_loss(rec_fake, se_fake)) / 2.0
+        out.update(video_latent_loss=video_latent_loss.detach(), image_latent_loss=image_latent_loss.detach(),
+                   reconstruct_loss=reconstruct_loss.detach())
     st_mu, im_mu = cond_vectors(c_mu, cim_mu)
     se_errG, _ = generator_loss(D_se, se_fake, im_ones, im_labels, im_mu)
     im_errG, _ = generator_loss(D_im, im_fake, im_ones, im_labels, im_mu)
@@ -354,6 +432,8 @@ def train_step(model, batch, noise, ratio=1.0, apply_optim=True):
     kl_w = p["KL"]
     total = im_errG + im_kl * kl_w + ratio * (se_errG * p["SEGMENT_RATIO"] + st_errG * p["IMAGE_RATIO"]
                                                 + st_kl * kl_w)
+    if video_latents is not None:
+        total = total + (video_latent_loss + reconstruct_loss) * p.get("RECONSTRUCT_LOSS", 1.0)   # trainer.py:412-413
     total.backward()
     if apply_optim:
         model.opt["G"].step()

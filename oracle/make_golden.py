@@ -1,6 +1,6 @@
 """Generate ``tests/golden/*.pt`` by running the REAL reference (build container only).
 
-    python -m oracle.make_golden [tiny small clevr]
+    python -m oracle.make_golden [tiny small clevr tiny_cascade small_cascade]
 
 For every preset: oracle-initialised weights (``oracle/params.py``, seed 0) are loaded into
 the reference's own modules (strict), the seeded synthetic batch (``oracle/synth.py``,
@@ -44,7 +44,7 @@ def run(name):
     gold = {"preset": p, "losses": losses, "seconds": dt, "torch": str(torch.__version__),
             "threads": torch.get_num_threads()}
     grads = dict(out["D_grads"], G=out["G_grads"])
-    if name == "tiny":
+    if name.startswith("tiny"):
         for k in ("p1_st_fake", "p1_im_fake", "p1_se_fake", "p3_st_fake", "p3_im_fake", "p3_se_fake"):
             gold[k] = out[k].contiguous().clone()
         gold["grads"] = grads

@@ -34,7 +34,8 @@ def _sn_conv(d, prefix, cout, cin, k, bias=False):
 
 
 def generator_inventory(p):
-    """reference model.py:214-311 (StoryGAN.__init__ / define_module)."""
+    """reference model.py:214-311 (StoryGAN.__init__ / define_module); with
+    ``p["CASCADE_MODEL"]`` also the mask re-encoder of cascade_model.py:36-41, 312-320."""
     V, T, L = p["VIDEO_LEN"], p["TEXT_DIM"], p["LABEL_NUM"]
     C, Z = p["CONDITION_DIM"], p["Z_DIM"]
     M = T + L
@@ -79,6 +80,16 @@ def generator_inventory(p):
     d["c_net.0.weight"] = ("w", (C, C))
     d["c_net.0.bias"] = ("zero", (C,))
     _bn(d, "c_net.1", C)
+    if p.get("CASCADE_MODEL"):
+        # cascade_model.py:312-320 (appended last so the non-cascade draws are unchanged)
+        d["presample.0.weight"] = ("w", (nseg // 16, 1, 3, 3))
+        _bn(d, "presample.1", nseg // 16)
+        c = nseg // 16
+        for i in range(1, 5):
+            d["downsample%d_seg.0.weight" % i] = ("w", (c * 2, c, 3, 3))
+            d["downsample%d_seg.0.bias" % i] = ("conv_b", (c * 2,), c * 9)
+            _bn(d, "downsample%d_seg.1" % i, c * 2)
+            c *= 2
     return d
 
 

@@ -6,7 +6,7 @@ Every preset is a flat dict of the ``cfg`` fields the model reads at constructio
 
 _COMMON = dict(
     CUDA=False, USE_SEQ_CONSISTENCY=False, SEGMENT_LEARNING=True, CASCADE_MODEL=False,
-    SEGMENT_RATIO=1.0, IMAGE_RATIO=5.0, KL=1.0,
+    SEGMENT_RATIO=1.0, IMAGE_RATIO=5.0, KL=1.0, RECONSTRUCT_LOSS=1.0,
     DISCRIMINATOR_LR=4e-4, GENERATOR_LR=1e-4,
 )
 
@@ -27,6 +27,9 @@ PRESETS = {
     "small": dict(_COMMON, VIDEO_LEN=3, TEXT_DIM=40, LABEL_NUM=5, ST_BATCH=4, IM_BATCH=8,
                   CONDITION_DIM=28, Z_DIM=16, DF_DIM=31, GF_DIM=32, GF_SEG_DIM=128),
 }
+# the cascade generator (cascade_model.py, cfg.CASCADE_MODEL)
+for _n in ("tiny", "small", "clevr", "pororo"):
+    PRESETS[_n + "_cascade"] = dict(PRESETS[_n], CASCADE_MODEL=True)
 
 
 def get(name, **overrides):
@@ -46,6 +49,7 @@ def apply_to_cfg(cfg, p):
     cfg.CASCADE_MODEL = p["CASCADE_MODEL"]
     cfg.SEGMENT_RATIO = p["SEGMENT_RATIO"]
     cfg.IMAGE_RATIO = p["IMAGE_RATIO"]
+    cfg.RECONSTRUCT_LOSS = p.get("RECONSTRUCT_LOSS", 1.0)
     cfg.Z_DIM = p["Z_DIM"]
     cfg.TRAIN.IM_BATCH_SIZE = p["IM_BATCH"]
     cfg.TRAIN.ST_BATCH_SIZE = p["ST_BATCH"]

@@ -57,7 +57,10 @@ def load_reference(p):
     from miscc.config import cfg
     presets.apply_to_cfg(cfg, p)
     cfg.CUDA = torch.cuda.is_available()
-    import model as ref_model
+    if p.get("CASCADE_MODEL"):
+        import cascade_model as ref_model       # trainer.py:83-84
+    else:
+        import model as ref_model
     import miscc.utils as ref_utils
     assert ref_model.__file__.startswith(REF), ref_model.__file__
     return ref_model, ref_utils, cfg
@@ -138,9 +141,22 @@ def reference_step(nets, ref_utils, cfg, batch, ratio=1.0, opts=None):
     out["D_grads"] = {k: {n: q.grad.detach().clone() for n, q in nets[k].named_parameters()}
                       for k in ("D_im", "D_st", "D_se")}
     netG.zero_grad()
-    _, st_fake, m_mu, m_logvar, c_mu, c_logvar, _ = netG.sample_videos(st_motion, st_content)
-    _, im_fake, im_mu, im_logvar, cim_mu, cim_logvar, se_fake = netG.sample_images(
+    video_latents, st_fake, m_mu, m_logvar, c_mu, c_logvar, _ = netG.sample_videos(st_motion, st_content)
+    image_latents, im_fake, im_mu, im_logvar, cim_mu, cim_logvar, se_fake = netG.sample_images(
         im_motion, im_content, seg=True)
+    if video_latents is not None:        # trainer.py:369-384, verbatim pairing
+        mse_loss = nn.MSELoss()
+        ((h_seg1, h_seg2, h_seg3, h_seg4), (g_seg1, g_seg2, g_seg3, g_seg4)) = video_latents
+        video_latent_loss = mse_loss(g_seg1, h_seg1) + mse_loss(g_seg2, h_seg2) + mse_loss(g_seg3, h_seg3) \
+            + mse_loss(g_seg4, h_seg4)
+        ((h_seg1, h_seg2, h_seg3, h_seg4), (g_seg1, g_seg2, g_seg3, g_seg4)) = image_latents
+        image_latent_loss = mse_loss(g_seg1, h_seg1) + mse_loss(g_seg2, h_seg2) + mse_loss(g_seg3, h_seg3) \
+            + mse_loss(g_seg4, h_seg4)
+        reconstruct_img = netG.train_autoencoder(se_real)
+        reconstruct_fake = netG.train_autoencoder(se_fake)
+        reconstruct_loss = (mse_loss(reconstruct_img, se_real) + mse_loss(reconstruct_fake, se_fake)) / 2.0
+        out.update(video_latent_loss=video_latent_loss.detach(), image_latent_loss=image_latent_loss.detach(),
+                   reconstruct_loss=reconstruct_loss.detach())
     characters_mu = (st_labels.mean(1) > 0).type(torch.FloatTensor)
     st_mu = torch.cat((c_mu, st_motion[:, :, :T].mean(1).squeeze(), characters_mu), 1)
     im_mu = torch.cat((im_motion, cim_mu), 1)
@@ -151,6 +167,8 @@ def reference_step(nets, ref_utils, cfg, batch, ratio=1.0, opts=None):
     st_kl = ref_utils.KL_loss(c_mu, c_logvar)
     total = im_errG + im_kl * cfg.TRAIN.COEFF.KL + ratio * (
         se_errG * cfg.SEGMENT_RATIO + st_errG * cfg.IMAGE_RATIO + st_kl * cfg.TRAIN.COEFF.KL)
+    if video_latents is not None:        # trainer.py:412-413
+        total = total + (video_latent_loss + reconstruct_loss) * cfg.RECONSTRUCT_LOSS
     total.backward()
     if opts:
         opts["G"].step()
