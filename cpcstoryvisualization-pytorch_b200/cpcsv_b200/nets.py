@@ -140,6 +140,8 @@ def prefetch_weights(modules, forward=True, backward=True, no_grad_forward=False
         gens = [m for m in mods if hasattr(m, "fc_seg")]
         if no_grad_forward:
             for G in gens:
+                if hasattr(G, "presample"):     # cascade generator: its no-grad call uses the split planes
+                    continue
                 _prefetch_fc(G, True, False, False)
                 for w, geom in _conv_weights(G):
                     engine.prefetch_conv_nograd(_CACHE, w, geom)
@@ -173,6 +175,9 @@ class TapeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, *tensors):
         ctx.runner = runner
+        # outputs nothing downstream uses (the mask of a sample_videos call, unused latents) come
+        # back as None, not as zero tensors: their branch of the backward pass is skipped
+        ctx.set_materialize_grads(False)
         outs = runner.run_forward(*tensors)
         return outs if isinstance(outs, tuple) else (outs,)
 
@@ -227,18 +232,12 @@ class TrunkRunner:
                         lambda: pack_fc_bwd(tape.cache, G, lin, C, Kp), name)
         return node, perm
 
-    # ---------------------------------------------------------------- forward
-    def run_forward(self, zmc_all, *plist):
-        G = self.G
-        _eval_bn_unsupported(G)
+    def _latent_planes(self, tape, zmc_all):
+        """latent [N, K] fp32 -> operand planes (zero padded to a multiple of 64 columns)"""
         dev = zmc_all.device
         N, K = zmc_all.shape
-        tape = Tape(_CACHE, training=G.training, need_grad=self.need_grad)
-        self.tape = tape
-        ngf, nseg = G.gf_dim, G.gf_dim_seg
         Kp = rup(K, 64)
         t16 = ops.TORCH16[tape.dtype]
-        # latent -> operand planes (zero padded to a multiple of 64 columns)
         x0 = T4(N, 1, 1, Kp)
         x0.hi = torch.zeros(N, 1, 1, Kp, device=dev, dtype=t16)
         x0.lo = torch.zeros(N, 1, 1, Kp, device=dev, dtype=t16) if tape.planes == 2 else None
@@ -248,6 +247,17 @@ class TrunkRunner:
                         dtype=tape.dtype)
         x0.needs_grad = self.need_grad
         self.x0, self.K = x0, K
+        return x0
+
+    # ---------------------------------------------------------------- forward
+    def run_forward(self, zmc_all, *plist):
+        G = self.G
+        _eval_bn_unsupported(G)
+        N, K = zmc_all.shape
+        tape = Tape(_CACHE, training=G.training, need_grad=self.need_grad)
+        self.tape = tape
+        ngf, nseg = G.gf_dim, G.gf_dim_seg
+        x0 = self._latent_planes(tape, zmc_all)
 
         nodes = {}
 

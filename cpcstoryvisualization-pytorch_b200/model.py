@@ -225,7 +225,7 @@ class StoryGAN(nn.Module):
         need_grad = torch.is_grad_enabled() and (
             zmc_all.requires_grad or any(p.requires_grad for p in self.parameters()))
         img, segm = nets.TrunkRunner(self, need_grad, seg).apply(zmc_all)
-        return img, segm
+        return None, img, segm      # no latents (the cascade variant returns them, cascade_model.py)
 
     # ---- public sampling API -------------------------------------------------------------
     def sample_videos(self, motion_input, content_input, seg=False):
@@ -238,10 +238,10 @@ class StoryGAN(nn.Module):
         c_mu = r_mu.repeat(self.video_len, 1)
         m_flat = motion_input.reshape(-1, motion_input.shape[2])
         zmc_all = self._conditioning(motion_input, m_flat, r_code, c_mu, self.video_len)
-        img, segm = self._trunk(zmc_all, seg)
+        latents, img, segm = self._trunk(zmc_all, seg)
         fake = img.view(B, self.video_len, self.n_channels, self.segment_size, self.segment_size)
         fake = fake.permute(0, 2, 1, 3, 4)
-        return None, fake, m_flat, m_flat, r_mu, r_logvar, (segm if seg else None)
+        return latents, fake, m_flat, m_flat, r_mu, r_logvar, (segm if seg else None)
 
     def sample_images(self, motion_input, content_input, seg=False):
         """motion_input (N, text+label), content_input (N, V, text).  The context GRU is seeded
@@ -250,8 +250,8 @@ class StoryGAN(nn.Module):
         content = content_input.reshape(N, cfg.VIDEO_LEN * content_input.shape[2])
         _c_code, c_mu, c_logvar = self.ca_net(content)
         zmc_all = self._conditioning(motion_input, motion_input, c_mu, c_mu, 1)
-        img, segm = self._trunk(zmc_all, seg)
-        return None, img, motion_input, motion_input, c_mu, c_logvar, (segm if seg else None)
+        latents, img, segm = self._trunk(zmc_all, seg)
+        return latents, img, motion_input, motion_input, c_mu, c_logvar, (segm if seg else None)
 
 
 # --------------------------------------------------------------------------- discriminators

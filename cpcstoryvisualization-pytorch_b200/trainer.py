@@ -71,10 +71,10 @@ class GradSync:
 
 def build_networks(video_len=None):
     """StoryGAN + the three discriminators, initialised like reference trainer.py:87-97."""
-    from model import StoryGAN, STAGE1_D_IMG, STAGE1_D_STY_V2, STAGE1_D_SEG
-    if cfg.CASCADE_MODEL:
-        raise NotImplementedError("CASCADE_MODEL=True (cascade_model.py) is outside the accelerated path; "
-                                  "cfg/final.yml:17 sets it to False")
+    if cfg.CASCADE_MODEL:      # reference trainer.py:83-86
+        from cascade_model import StoryGAN, STAGE1_D_IMG, STAGE1_D_STY_V2, STAGE1_D_SEG
+    else:
+        from model import StoryGAN, STAGE1_D_IMG, STAGE1_D_STY_V2, STAGE1_D_SEG
     nets = {"G": StoryGAN(video_len if video_len is not None else cfg.VIDEO_LEN),
             "D_im": STAGE1_D_IMG(), "D_st": STAGE1_D_STY_V2(), "D_se": STAGE1_D_SEG()}
     for n in nets.values():
@@ -120,6 +120,12 @@ def _cond_vectors(x, c_mu, cim_mu):
     st_mu = torch.cat((c_mu, x["st_motion"][:, :, :T].mean(1).squeeze(), chars), 1)
     im_mu = torch.cat((x["im_motion"], cim_mu), 1)
     return st_mu, im_mu
+
+
+def _latent_loss(latents):
+    """sum of MSE(g_seg_k, h_k) over the four (decoder, re-encoder) pairs, reference trainer.py:371-375"""
+    hs, gs = latents
+    return sum(torch.nn.functional.mse_loss(g, h) for g, h in zip(gs, hs))
 
 
 D_NETS = ("D_se", "D_im", "D_st")
@@ -233,8 +239,18 @@ def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True, forward=None)
                 lambda: netG.sample_videos(x["st_motion"], x["st_content"]),
                 lambda: netG.sample_images(x["im_motion"], x["im_content"], seg=True),
                 enabled=CONCURRENT_G)
-        (_, st_fake, _, _, c_mu, c_logvar, _), (_, im_fake, _, _, cim_mu, cim_logvar, se_fake) = g_vid, g_img
+        (video_latents, st_fake, _, _, c_mu, c_logvar, _) = g_vid
+        (image_latents, im_fake, _, _, cim_mu, cim_logvar, se_fake) = g_img
         st_mu, im_mu = _cond_vectors(x, c_mu, cim_mu)
+        if video_latents is not None:
+            # cascade generator, reference trainer.py:369-384 (the tuples are paired by position)
+            video_latent_loss, image_latent_loss = _latent_loss(video_latents), _latent_loss(image_latents)
+            rec_real = netG.train_autoencoder(x["se_real"])
+            rec_fake = netG.train_autoencoder(se_fake)
+            reconstruct_loss = (torch.nn.functional.mse_loss(rec_real, x["se_real"])
+                                + torch.nn.functional.mse_loss(rec_fake, se_fake)) / 2.0
+            out.update(video_latent_loss=video_latent_loss.detach(), image_latent_loss=image_latent_loss.detach(),
+                       reconstruct_loss=reconstruct_loss.detach())
         se_errG, im_errG, st_errG = _concurrently(
             lambda: compute_generator_loss(netD_se, se_fake, x["se_real"], im_ones, x["im_labels"], im_mu, gpus)[0],
             lambda: compute_generator_loss(netD_im, im_fake, x["im_real"], im_ones, x["im_labels"], im_mu, gpus)[0],
@@ -244,6 +260,8 @@ def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True, forward=None)
         kl_w = cfg.TRAIN.COEFF.KL
         total = im_errG + im_kl * kl_w + ratio * (se_errG * cfg.SEGMENT_RATIO + st_errG * cfg.IMAGE_RATIO
                                                   + st_kl * kl_w)
+        if video_latents is not None:      # reference trainer.py:412-413
+            total = total + (video_latent_loss + reconstruct_loss) * cfg.RECONSTRUCT_LOSS
         total.backward()
     finally:
         if skip_d_wgrad:

@@ -5,8 +5,12 @@ import torch
 from oracle import functional as Fn
 from oracle import params, presets, synth
 
-ZERO_GRAD = ("filter_net.0.bias", "image_net.0.bias", "m_net.0.bias", "c_net.0.bias")
+ZERO_GRAD = ("filter_net.0.bias", "image_net.0.bias", "m_net.0.bias", "c_net.0.bias",
+             # cascade downBlocks: conv bias directly followed by BatchNorm (cascade_model.py:36-41)
+             "downsample1_seg.0.bias", "downsample2_seg.0.bias", "downsample3_seg.0.bias",
+             "downsample4_seg.0.bias")
 LOSS_KEYS = ("se_errD", "im_errD", "st_errD", "se_errG", "im_errG", "st_errG", "im_kl", "st_kl")
+CASCADE_LOSS_KEYS = ("video_latent_loss", "image_latent_loss", "reconstruct_loss")
 IMG_KEYS = ("p1_st_fake", "p1_im_fake", "p1_se_fake", "p3_st_fake", "p3_im_fake", "p3_se_fake")
 
 
@@ -14,7 +18,10 @@ def build_product(p, states, device):
     from miscc.config import cfg
     presets.apply_to_cfg(cfg, p)
     cfg.CUDA = device.type == "cuda"
-    import model
+    if p.get("CASCADE_MODEL"):
+        import cascade_model as model      # reference trainer.py:83-84
+    else:
+        import model
     nets = {"G": model.StoryGAN(p["VIDEO_LEN"]), "D_im": model.STAGE1_D_IMG(),
             "D_st": model.STAGE1_D_STY_V2(), "D_se": model.STAGE1_D_SEG()}
     for k, net in nets.items():
@@ -81,7 +88,7 @@ def rel_l2(a, b):
 def compare(out, grads, ref_out, ref_grads, verbose=False):
     """returns dict of worst-case metrics against the reference results"""
     res = {"loss_rel": 0.0, "img_rel": 0.0, "cos_min": 1.0, "cos_min_name": None, "cos_net": {}}
-    for k in LOSS_KEYS:
+    for k in LOSS_KEYS + tuple(k for k in CASCADE_LOSS_KEYS if k in ref_out):
         r = abs(float(out[k]) - float(ref_out[k])) / abs(float(ref_out[k]))
         res["loss_rel"] = max(res["loss_rel"], r)
         if verbose:

@@ -59,13 +59,43 @@ def test_small_step_emulated(monkeypatch):
     _check(harness.compare(out, grads, ref_out, ref_grads))
 
 
-def test_tiny_step_emulated_vs_reference_golden(monkeypatch):
-    """phase-1 images, discriminator losses and discriminator gradients of the REAL reference
-    (tests/golden/step_tiny.pt); these do not depend on the optimiser coupling."""
+@pytest.mark.parametrize("name", ["tiny_cascade", "small_cascade"])
+def test_cascade_step_emulated(monkeypatch, name):
+    """the cascade generator (cascade_model.py) with the latent-MSE and
+    reconstruction losses of reference trainer.py:369-384, product host logic on the emulator vs
+    the fp64 oracle."""
     emulator.install(monkeypatch)
-    gold = torch.load(os.path.join(GOLD, "step_tiny.pt"))
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    p = presets.get(name)
+    _, out, grads, ref_out, ref_grads = _step_pair(p, torch.device("cpu"))
+    res = harness.compare(out, grads, ref_out, ref_grads, verbose=True)
+    print(name, res)
+    _check(res, small_tensor_cos=0.99 if name.startswith("tiny") else None)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_cascade"])
+def test_tiny_step_emulated_vs_reference_golden(monkeypatch, name):
+    """phase-1 images, discriminator losses and discriminator gradients of the REAL reference
+    (tests/golden/step_tiny*.pt); these do not depend on the optimiser coupling.  Also the
+    generator's BatchNorm running statistics after the step (they depend on the generator's
+    weights, inputs and noise only): call order, momentum, and -- cascade -- the conv bias folded
+    into the running mean."""
+    emulator.install(monkeypatch)
+    gold = torch.load(os.path.join(GOLD, "step_%s.pt" % name))
     nets, out, grads = harness.run_product_step(gold["preset"], torch.device("cpu"))
     _check_against_golden(gold, out, grads)
+    _check_generator_buffers(gold, nets)
+
+
+def _check_generator_buffers(gold, nets):
+    sd = nets["G"].state_dict()
+    for n, t in gold["post_buffers"]["G"].items():
+        mine = sd[n].detach().cpu()
+        if n.endswith("num_batches_tracked"):
+            assert int(mine) == int(t), n
+        else:
+            assert torch.allclose(mine.float(), t.float(), atol=2e-3, rtol=2e-3), (
+                n, float((mine.float() - t.float()).abs().max()))
 
 
 def _check_against_golden(gold, out, grads):
@@ -103,6 +133,7 @@ def test_tiny_step_gpu_vs_reference_golden():
     gold = torch.load(os.path.join(GOLD, "step_tiny.pt"))
     nets, out, grads = harness.run_product_step(gold["preset"], torch.device("cuda"))
     _check_against_golden(gold, out, grads)
+    _check_generator_buffers(gold, nets)
 
 
 @pytest.mark.gpu
