@@ -214,6 +214,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
       }
+      if (kPair) {
+        // Producer tail (pair mode): the commits that release the last `stages` ring slots are
+        // multicast arrives into BOTH CTAs' shared memory and nobody waits for them in the main
+        // loop.  Drain them before this CTA may exit, so that none of them can land in the
+        // barriers of whatever block is scheduled on this SM next.  (Slots that were never
+        // filled pass immediately: a fresh barrier is complete for the preceding parity.)
+        for (int i = 0; i < P.stages; ++i) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (++stage == P.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
