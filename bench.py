@@ -169,16 +169,16 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------- product arm
 class StepEngine:
-    """The public train_step API around static device buffers, optionally as one CUDA graph."""
+    """Networks, optimisers and a pinned synthetic host batch around the product's own
+    ``trainer.GraphedStep`` (the public train_step API on static device buffers, replayed as one
+    CUDA graph; three graphs with the NCCL exchanges between them when N > 1)."""
 
     def __init__(self, p, device, use_graph, grad_sync, segmented=False):
         self.segmented = segmented
         from miscc.config import cfg
         apply_cfg(cfg, p)
-        import miscc.utils as mu
         import trainer
         from cpcsv_b200 import nets as knets
-        mu.SYNC_ACCURACY = False            # no host round trip inside the step
         self.trainer, self.knets = trainer, knets
         self.p, self.device = p, device
         torch.manual_seed(1234 + int(os.environ.get("RANK", "0")))
@@ -200,78 +200,24 @@ class StepEngine:
         self.h2d_bytes = sum(v.numel() * v.element_size() for d in (st, im) for v in d.values())
         self.grad_sync = grad_sync
         self.use_graph = use_graph
-        self.graph = None
-        self.loss_keys = ("se_errD", "im_errD", "st_errD", "se_errG", "im_errG", "st_errG", "im_kl", "st_kl",
-                          "errG_total")
-        self.loss_dev = torch.zeros(len(self.loss_keys), device=device)
-        self.loss_host = torch.zeros(len(self.loss_keys)).pin_memory()
+        self.gs = trainer.GraphedStep(self.nets, self.opts, self.labels, self.dev_st, self.dev_im,
+                                      grad_sync=grad_sync, ratio=1.0, use_graph=use_graph, segmented=segmented)
+        self.loss_keys, self.loss_dev, self.loss_host = self.gs.loss_keys, self.gs.loss_dev, self.gs.loss_host
 
     def _step_body(self):
-        x = self.trainer.prepare_inputs(self.dev_st, self.dev_im)
-        out = self.trainer.train_step(self.nets, self.opts, x, self.labels, 1.0, self.grad_sync)
-        self.loss_dev.copy_(torch.stack([out[k].reshape(()) for k in self.loss_keys]))
-
-    # --- the step in three segments, with the NCCL gradient exchange between them ------------
-    def _seg_d(self):
-        self._x = self.trainer.prepare_inputs(self.dev_st, self.dev_im)
-        self._out = self.trainer.stage_discriminators(self.nets, self._x, self.labels,
-                                                      early_generator=self.trainer.EARLY_G)
-        if "early_generator" in self._out:
-            self._out["early_generator"].join()      # every branch joins before the segment ends
-
-    def _seg_g(self):
-        for k in self.trainer.D_NETS:
-            self.opts[k].step()
-        self._out.update(self.trainer.stage_generator(self.nets, self._x, self.labels, 1.0,
-                                                      forward=self._out.pop("early_generator", None)))
-
-    def _seg_opt(self):
-        self.opts["G"].step()
-        self.loss_dev.copy_(torch.stack([self._out[k].reshape(()) for k in self.loss_keys]))
+        self.gs._step_body()
 
     def capture(self):
-        """The whole step is ONE CUDA graph; with N > 1 the two NCCL gradient all-reduces are
-        captured inside it.  ``--segmented``: three graphs with the all-reduces issued eagerly
-        between them (collectives kept out of the capture)."""
-        self.knets.invalidate_weight_cache()
-        if not self.segmented:
-            self.graph = torch.cuda.CUDAGraph()
-            kw = {}
-            if self.grad_sync is not None and self.grad_sync.enabled:
-                kw["capture_error_mode"] = "thread_local"   # the NCCL watchdog thread keeps running
-            with torch.cuda.graph(self.graph, stream=self.trainer.step_stream(self.device), **kw):
-                self._step_body()
-            return
-        self.graphs = []
-        pool = None
-        for seg in (self._seg_d, self._seg_g, self._seg_opt):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool, stream=self.trainer.step_stream(self.device)):
-                seg()
-            pool = g.pool()
-            self.graphs.append(g)
-        self.graph = True
+        self.gs.capture()
 
     def step(self):
-        if self.graph is None:
-            self._step_body()
-        elif not self.segmented:
-            self.graph.replay()
-        else:
-            self.graphs[0].replay()
-            self.trainer.sync_grads(self.nets, self.trainer.D_NETS, self.grad_sync)
-            self.graphs[1].replay()
-            self.trainer.sync_grads(self.nets, ("G",), self.grad_sync)
-            self.graphs[2].replay()
+        self.gs.step()
 
     def upload(self):
-        for k, v in self.host_st.items():
-            self.dev_st[k].copy_(v, non_blocking=True)
-        for k, v in self.host_im.items():
-            self.dev_im[k].copy_(v, non_blocking=True)
+        self.gs.load(self.host_st, self.host_im)
 
     def download(self):
-        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+        self.gs.download()
 
 
 def job_flops(job):

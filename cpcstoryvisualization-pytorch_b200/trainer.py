@@ -299,6 +299,150 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
     return out
 
 
+LOSS_KEYS = ("se_errD", "im_errD", "st_errD", "se_errG", "im_errG", "st_errG", "im_kl", "st_kl", "errG_total")
+
+
+def build_capturable_optimizers(nets, device):
+    """``build_optimizers`` for a step that is replayed as a CUDA graph: fused, capturable Adam with
+    the learning rate held in a device tensor, so the halving schedule (reference trainer.py:447-456)
+    acts on later replays (``set_lr``) instead of being frozen into the captured launches."""
+    opts = {}
+    for k, net in nets.items():
+        lr = cfg.TRAIN.GENERATOR_LR if k == "G" else cfg.TRAIN.DISCRIMINATOR_LR
+        opts[k] = optim.Adam([p for p in net.parameters() if p.requires_grad],
+                             lr=torch.tensor(float(lr), device=device), betas=(0.5, 0.999), fused=True,
+                             capturable=True)
+    return opts
+
+
+def set_lr(opt, lr):
+    """works for float and for device-tensor learning rates (capturable optimisers)"""
+    for g in opt.param_groups:
+        if torch.is_tensor(g["lr"]):
+            g["lr"].fill_(lr)
+        else:
+            g["lr"] = lr
+
+
+class GraphedStep:
+    """``train_step`` on STATIC device buffers, replayed as CUDA graphs: ~1500 kernel launches on a
+    dozen streams per step become one graph launch (reference hot loop trainer.py:290-416; SURVEY.md
+    section 8 row f1).
+
+    One process / one GPU: the whole step is ONE graph.  With a gradient exchange (``grad_sync``
+    enabled, N > 1) the step is three graphs -- discriminator stage | discriminator Adam steps +
+    generator stage | generator Adam step -- with the two NCCL all-reduces issued eagerly between
+    them (collectives captured inside the one-graph step hung on a 2-GPU box; ``segmented=False``
+    keeps that variant reachable).
+
+    ``dev_st`` / ``dev_im``: dicts of device tensors with the batch-dict contract of the reference's
+    loaders (``images``, ``description``, ``labels`` [, ``content``, ``images_seg``]); ``load`` copies
+    a new batch into them.  The optimisers must be capturable (``build_capturable_optimizers``) and
+    must have taken at least one eager step (state allocated) before ``capture``."""
+
+    def __init__(self, nets, opts, labels, dev_st, dev_im, grad_sync=None, ratio=1.0, use_graph=True,
+                 segmented=None):
+        import miscc.utils as mu
+        mu.SYNC_ACCURACY = False            # no host round trip inside the step
+        self.nets, self.opts, self.labels, self.ratio = nets, opts, labels, ratio
+        self.dev_st, self.dev_im = dev_st, dev_im
+        self.device = labels[0].device
+        self.grad_sync = grad_sync
+        exchange = grad_sync is not None and getattr(grad_sync, "enabled", True)
+        self.segmented = exchange if segmented is None else segmented
+        self.use_graph = use_graph
+        self.graph = None
+        self.graphs = []
+        self.loss_keys = LOSS_KEYS
+        self.loss_dev = torch.zeros(len(LOSS_KEYS), device=self.device)
+        self.loss_host = torch.zeros(len(LOSS_KEYS))
+        if self.device.type == "cuda":
+            self.loss_host = self.loss_host.pin_memory()
+
+    # --- static buffers ----------------------------------------------------------------------
+    def fits(self, st_batch, im_batch):
+        """True when the batch has the shapes of the static buffers (loaders use drop_last)"""
+        for dst, src in ((self.dev_st, st_batch), (self.dev_im, im_batch)):
+            for k, t in dst.items():
+                if k not in src or tuple(src[k].shape) != tuple(t.shape):
+                    return False
+        return True
+
+    def load(self, st_batch, im_batch):
+        """host (pinned) or device batch dicts -> static device buffers, on the current stream"""
+        for dst, src in ((self.dev_st, st_batch), (self.dev_im, im_batch)):
+            for k, t in dst.items():
+                t.copy_(src[k], non_blocking=True)
+
+    def download(self):
+        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+
+    def losses(self):
+        """dict of the step's losses as Python floats (host sync)"""
+        self.download()
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        return {k: float(v) for k, v in zip(self.loss_keys, self.loss_host)}
+
+    # --- the step ------------------------------------------------------------------------------
+    def _record(self, out):
+        self.loss_dev.copy_(torch.stack([out[k].reshape(()) for k in self.loss_keys]))
+
+    def _step_body(self):
+        x = prepare_inputs(self.dev_st, self.dev_im)
+        self._record(train_step(self.nets, self.opts, x, self.labels, self.ratio, self.grad_sync))
+
+    # the step in three segments, with the NCCL gradient exchange between them
+    def _seg_d(self):
+        self._x = prepare_inputs(self.dev_st, self.dev_im)
+        self._out = stage_discriminators(self.nets, self._x, self.labels, early_generator=EARLY_G)
+        if "early_generator" in self._out:
+            self._out["early_generator"].join()      # every branch joins before the segment ends
+
+    def _seg_g(self):
+        for k in D_NETS:
+            self.opts[k].step()
+        self._out.update(stage_generator(self.nets, self._x, self.labels, self.ratio,
+                                         forward=self._out.pop("early_generator", None)))
+
+    def _seg_opt(self):
+        self.opts["G"].step()
+        self._record(self._out)
+
+    def capture(self):
+        knets.invalidate_weight_cache()
+        stream = step_stream(self.device)
+        if not self.segmented:
+            self.graph = torch.cuda.CUDAGraph()
+            kw = {}
+            if self.grad_sync is not None and getattr(self.grad_sync, "enabled", False):
+                kw["capture_error_mode"] = "thread_local"   # the NCCL watchdog thread keeps running
+            with torch.cuda.graph(self.graph, stream=stream, **kw):
+                self._step_body()
+            return
+        self.graphs = []
+        pool = None
+        for seg in (self._seg_d, self._seg_g, self._seg_opt):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, stream=stream):
+                seg()
+            pool = g.pool()
+            self.graphs.append(g)
+        self.graph = True
+
+    def step(self):
+        if self.graph is None:
+            self._step_body()
+        elif not self.segmented:
+            self.graph.replay()
+        else:
+            self.graphs[0].replay()
+            sync_grads(self.nets, D_NETS, self.grad_sync)
+            self.graphs[1].replay()
+            sync_grads(self.nets, ("G",), self.grad_sync)
+            self.graphs[2].replay()
+
+
 class GANTrainer(object):
     def __init__(self, output_dir, args, ratio=1.0):
         if cfg.TRAIN.FLAG:
@@ -344,50 +488,84 @@ class GANTrainer(object):
             n.to(self.device)
         return nets["G"], nets["D_im"], nets["D_st"], nets["D_se"]
 
-    def sample_real_image_batch(self):
+    def sample_real_image_batch(self, to_device=True):
         if self.imagedataset is None:
             self.imagedataset = enumerate(self.imageloader)
         batch_idx, batch = next(self.imagedataset)
-        batch = {k: (v if k == "text" else v.to(self.device, non_blocking=True)) for k, v in batch.items()}
+        if to_device:
+            batch = {k: (v if k == "text" else v.to(self.device, non_blocking=True)) for k, v in batch.items()}
         if batch_idx == len(self.imageloader) - 1:
             self.imagedataset = enumerate(self.imageloader)
         return batch
 
+    GRAPH_WARMUP_STEPS = 3      # eager steps (optimiser state, weight caches, NCCL) before the capture
+
     def train(self, imageloader, storyloader, testloader, stage=1):
+        """reference trainer.py:187-485.  On a GPU the step runs through ``GraphedStep``: batches are
+        copied into static device buffers and, after ``GRAPH_WARMUP_STEPS`` eager iterations, every
+        iteration is one CUDA-graph replay (``CPCSV_GRAPH=0`` keeps the eager step).  Losses stay on
+        the device; they are read back only when a logger is attached, every 20 iterations."""
         self.imageloader, self.imagedataset = imageloader, None
         netG, netD_im, netD_st, netD_se = self.load_network_stageI()
         nets = {"G": netG, "D_im": netD_im, "D_st": netD_st, "D_se": netD_se}
-        opts = build_optimizers(nets)
         dev = self.device
+        use_graph = dev.type == "cuda" and os.environ.get("CPCSV_GRAPH", "1") != "0"
+        opts = build_capturable_optimizers(nets, dev) if use_graph else build_optimizers(nets)
         labels = (torch.ones(self.imbatch_size, device=dev), torch.zeros(self.imbatch_size, device=dev),
                   torch.ones(self.stbatch_size, device=dev), torch.zeros(self.stbatch_size, device=dev))
         grad_sync = GradSync()
+        graphed, eager_steps = None, 0
         generator_lr, discriminator_lr = cfg.TRAIN.GENERATOR_LR, cfg.TRAIN.DISCRIMINATOR_LR
         lr_decay_step = cfg.TRAIN.LR_DECAY_EPOCH
         start_epoch = int(self.con_ckpt) if self.con_ckpt else 0
         c_time = time.time()
+
+        def tensors(batch):
+            return {k: v for k, v in batch.items() if torch.is_tensor(v)}
+
         for epoch in range(start_epoch, self.max_epoch):
             start_t = time.time()
             num_step = len(storyloader)
             for i, data in enumerate(storyloader):
-                im_batch = self.sample_real_image_batch()
-                st_batch = {k: (v if k == "text" else v.to(dev, non_blocking=True)) for k, v in data.items()}
-                x = prepare_inputs(st_batch, im_batch)
-                stats = train_step(nets, opts, x, labels, self.ratio, grad_sync)
-                if self._logger is not None and i % 20 == 0:
+                st_batch, im_batch = tensors(data), tensors(self.sample_real_image_batch(to_device=False))
+                want_log = self._logger is not None and i % 20 == 0
+                stats = None
+                if use_graph and graphed is None:
+                    graphed = GraphedStep(nets, opts, labels, {k: v.to(dev) for k, v in st_batch.items()},
+                                          {k: v.to(dev) for k, v in im_batch.items()}, grad_sync, self.ratio)
+                if use_graph and graphed.fits(st_batch, im_batch):
+                    graphed.load(st_batch, im_batch)
+                    if graphed.graph is None:
+                        if eager_steps >= self.GRAPH_WARMUP_STEPS:
+                            graphed.capture()
+                        else:
+                            eager_steps += 1
+                    graphed.step()
+                    if want_log:
+                        stats = graphed.losses()
+                else:
+                    # the eager step on the same kernels: CPCSV_GRAPH=0, or a batch of another size
+                    # (a loader without drop_last)
+                    st_dev = {k: v.to(dev, non_blocking=True) for k, v in st_batch.items()}
+                    im_dev = {k: v.to(dev, non_blocking=True) for k, v in im_batch.items()}
+                    n_st, n_im = st_dev["images"].shape[0], im_dev["images"].shape[0]
+                    lab = labels if (n_im, n_st) == (self.imbatch_size, self.stbatch_size) else (
+                        torch.ones(n_im, device=dev), torch.zeros(n_im, device=dev),
+                        torch.ones(n_st, device=dev), torch.zeros(n_st, device=dev))
+                    out = train_step(nets, opts, prepare_inputs(st_dev, im_dev), lab, self.ratio, grad_sync)
+                    if want_log:
+                        stats = {k: float(out[k]) for k in LOSS_KEYS}
+                if stats is not None:
                     step = i + num_step * epoch
-                    for key in ("se_errD", "im_errD", "st_errD", "se_errG", "im_errG", "st_errG", "im_kl",
-                                "st_kl", "errG_total"):
-                        self._logger.add_scalar(key, float(stats[key]), step)
+                    for key, val in stats.items():
+                        self._logger.add_scalar(key, val, step)
             # learning-rate halving, reference trainer.py:447-456
             if epoch % lr_decay_step == 0 and epoch > 0:
                 generator_lr *= 0.5
                 discriminator_lr *= 0.5
-                for g in opts["G"].param_groups:
-                    g["lr"] = generator_lr
+                set_lr(opts["G"], generator_lr)
                 for k in ("D_st", "D_im"):
-                    for g in opts[k].param_groups:
-                        g["lr"] = discriminator_lr
+                    set_lr(opts[k], discriminator_lr)
                 lr_decay_step *= 2
             print("----[{}/{}] epoch {:.1f} min, total {:.1f} h----".format(
                 epoch, self.max_epoch, (time.time() - start_t) / 60, (time.time() - c_time) / 3600))
@@ -403,5 +581,5 @@ def story_rate(ms_per_step, n_gpus=1):
     return cfg.TRAIN.ST_BATCH_SIZE * n_gpus / (ms_per_step * 1e-3)
 
 
-__all__ = ["GANTrainer", "train_step", "build_networks", "build_optimizers", "prepare_inputs", "GradSync",
-           "story_rate", "np"]
+__all__ = ["GANTrainer", "GraphedStep", "train_step", "build_networks", "build_optimizers",
+           "build_capturable_optimizers", "set_lr", "prepare_inputs", "GradSync", "story_rate", "LOSS_KEYS", "np"]

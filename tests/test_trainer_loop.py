@@ -1,0 +1,100 @@
+"""Host logic of the product's training loop (trainer.GANTrainer.train, trainer.GraphedStep;
+reference trainer.py:187-485) on the kernel-contract emulator:
+loader plumbing, static-buffer loading, the three-segment step used for multi-GPU runs, the
+learning-rate halving and the checkpoint files.  The CUDA-graph capture itself is covered by the
+``-m gpu`` case in tests/test_zz_cascade.py and by bench.py."""
+import copy
+import os
+import types
+
+import torch
+
+import emulator
+import harness
+from oracle import params, presets, synth
+
+
+def _setup(monkeypatch, name="tiny"):
+    emulator.install(monkeypatch)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    p = presets.get(name)
+    dev = torch.device("cpu")
+    nets = harness.build_product(p, params.init_all(p, 0), dev)
+    batch = synth.make_batch(p, 1)
+    st = {"images": batch["st_real"], "description": batch["st_desc"], "labels": batch["st_labels"]}
+    im = {"images": batch["im_real"], "description": batch["im_desc"], "content": batch["im_content"],
+          "labels": batch["im_labels"], "images_seg": batch["se_real"]}
+    N, B = p["IM_BATCH"], p["ST_BATCH"]
+    labels = (torch.ones(N), torch.zeros(N), torch.ones(B), torch.zeros(B))
+    return p, nets, st, im, labels
+
+
+def test_graphed_step_segments_match_whole_step(monkeypatch):
+    """the 3-segment step (discriminator stage | D Adam + generator stage | G Adam) that multi-GPU
+    runs replay around the NCCL exchanges computes what the one-piece step computes"""
+    import trainer
+    p, nets, st, im, labels = _setup(monkeypatch)
+    nets2 = copy.deepcopy(nets)
+    noise = synth.make_noise(p, 2)
+    results = []
+    for which, nn_ in (("whole", nets), ("segments", nets2)):
+        harness.inject_noise(nn_["G"], synth.NoiseFeed(noise))
+        opts = trainer.build_optimizers(nn_, fused=False)
+        gs = trainer.GraphedStep(nn_, opts, labels, {k: v.clone() for k, v in st.items()},
+                                 {k: v.clone() for k, v in im.items()}, grad_sync=None, use_graph=False)
+        assert gs.fits(st, im) and not gs.fits({k: v[:1] for k, v in st.items()}, im)
+        gs.load(st, im)
+        if which == "whole":
+            gs.step()
+        else:
+            gs._seg_d()
+            gs._seg_g()
+            gs._seg_opt()
+        results.append((gs.losses(), {k: [q.detach().clone() for q in n.parameters()] for k, n in nn_.items()}))
+    (l1, w1), (l2, w2) = results
+    assert set(l1) == set(trainer.LOSS_KEYS)
+    for k in l1:
+        assert abs(l1[k] - l2[k]) <= 1e-5 * abs(l1[k]) + 1e-7, (k, l1[k], l2[k])
+    for k in w1:
+        for a, b in zip(w1[k], w2[k]):
+            # Adam's first step is lr * sign(g)-like: identical unless a gradient element flips sign
+            assert float((a - b).abs().max()) <= 2.5 * 4e-4, k
+
+
+def test_gan_trainer_loop(monkeypatch, tmp_path):
+    """GANTrainer.train with list 'loaders': two epochs of one iteration, LR halving after epoch 1,
+    checkpoints written with the reference's file names (miscc/utils.py:323-338)"""
+    import trainer
+    from miscc.config import cfg
+    p, nets, st, im, labels = _setup(monkeypatch)
+    cfg.TRAIN.MAX_EPOCH, cfg.TRAIN.SNAPSHOT_INTERVAL, cfg.TRAIN.LR_DECAY_EPOCH = 2, 1, 1
+    cfg.NET_G = ""
+    t = trainer.GANTrainer.__new__(trainer.GANTrainer)      # __init__ binds a CUDA device
+    t.model_dir = str(tmp_path)
+    t.video_len, t.max_epoch, t.snapshot_interval = p["VIDEO_LEN"], 2, 1
+    t.imbatch_size, t.stbatch_size, t.ratio = p["IM_BATCH"], p["ST_BATCH"], 1.0
+    t.con_ckpt, t.device = None, torch.device("cpu")
+    logged = []
+    t._logger = types.SimpleNamespace(add_scalar=lambda k, v, s: logged.append((k, v, s)))
+    captured = {}
+    orig = trainer.build_optimizers
+
+    def spy(nets_, fused=None):
+        captured["opts"] = orig(nets_, fused=False)
+        return captured["opts"]
+    monkeypatch.setattr(trainer, "build_optimizers", spy)
+    st_loader = [dict(st, text=["a story"])]
+    im_loader = [dict(im, text=["an image"])]
+    out_nets = t.train(im_loader, st_loader, None)
+    assert set(out_nets) == {"G", "D_im", "D_st", "D_se"}
+    # halved once (after epoch 1) for G, D_st, D_im; the reference never halves D_se (trainer.py:452-455)
+    lr = {k: o.param_groups[0]["lr"] for k, o in captured["opts"].items()}
+    assert abs(lr["G"] - 0.5 * p["GENERATOR_LR"]) < 1e-12
+    assert abs(lr["D_im"] - 0.5 * p["DISCRIMINATOR_LR"]) < 1e-12 and abs(lr["D_st"] - lr["D_im"]) < 1e-12
+    assert abs(lr["D_se"] - p["DISCRIMINATOR_LR"]) < 1e-12
+    files = set(os.listdir(tmp_path))
+    assert {"netG_epoch_0.pth", "netG_epoch_1.pth", "netG_epoch_2.pth", "netD_im_epoch_last.pth",
+            "netD_st_epoch_last.pth", "netD_se_epoch_last.pth"} <= files, files
+    assert {k for k, _, _ in logged} == set(trainer.LOSS_KEYS) and len(logged) == 2 * len(trainer.LOSS_KEYS)
+    sd = torch.load(os.path.join(tmp_path, "netG_epoch_2.pth"))
+    assert set(sd) == set(out_nets["G"].state_dict())

@@ -136,3 +136,44 @@ def test_tiny_cascade_step_gpu_vs_reference_golden():
     nets, out, grads = harness.run_product_step(gold["preset"], torch.device("cuda"))
     _check_against_golden(gold, out, grads)
     _check_generator_buffers(gold, nets)
+
+
+# ------------------------------------------------------------------------------ CUDA-graph step (f1)
+@pytest.mark.gpu
+def test_graphed_step_replay_matches_eager_gpu():
+    """trainer.GraphedStep (the step GANTrainer.train and bench.py replay as ONE CUDA graph): three
+    steps as eager-eager-capture+replay give the losses of three eager steps.  Noise is injected
+    (static tensors), so both runs see identical inputs; split-K red.add ordering is the only
+    source of difference."""
+    import copy
+    import trainer
+    from oracle import params, synth
+    p = presets.get("small")
+    dev = torch.device("cuda")
+    base = harness.build_product(p, params.init_all(p, 0), dev)
+    noise = synth.make_noise(p, 2, device=dev)
+    batch = synth.make_batch(p, 1, device=dev)
+    st = {"images": batch["st_real"], "description": batch["st_desc"], "labels": batch["st_labels"]}
+    im = {"images": batch["im_real"], "description": batch["im_desc"], "content": batch["im_content"],
+          "labels": batch["im_labels"], "images_seg": batch["se_real"]}
+    N, B = p["IM_BATCH"], p["ST_BATCH"]
+    labels = (torch.ones(N, device=dev), torch.zeros(N, device=dev), torch.ones(B, device=dev),
+              torch.zeros(B, device=dev))
+    losses = {}
+    for mode in ("eager", "graph"):
+        nets = copy.deepcopy(base)
+        opts = trainer.build_capturable_optimizers(nets, dev)
+        gs = trainer.GraphedStep(nets, opts, labels, {k: v.clone() for k, v in st.items()},
+                                 {k: v.clone() for k, v in im.items()}, grad_sync=None)
+        for i in range(3):
+            harness.inject_noise(nets["G"], synth.NoiseFeed(noise))
+            gs.load(st, im)
+            if mode == "graph" and i == 2:
+                gs.capture()
+            gs.step()
+        losses[mode] = gs.losses()
+        torch.cuda.synchronize()
+    for k, v in losses["eager"].items():
+        assert abs(v - losses["graph"][k]) <= 2e-3 * abs(v) + 1e-6, (k, v, losses["graph"][k])
+    trainer.set_lr(opts["G"], 5e-5)
+    assert float(opts["G"].param_groups[0]["lr"]) == pytest.approx(5e-5)
