@@ -213,8 +213,13 @@ class StepEngine:
     def step(self):
         self.gs.step()
 
+    overlap_io = False      # --overlap-io: stage the next batch on a copy stream (GraphedStep.load_async)
+
     def upload(self):
-        self.gs.load(self.host_st, self.host_im)
+        if self.overlap_io:
+            self.gs.load_async(self.host_st, self.host_im)
+        else:
+            self.gs.load(self.host_st, self.host_im)
 
     def download(self):
         self.gs.download()
@@ -288,6 +293,9 @@ def main():
     ap.add_argument("--impl", default="cpcsv_b200")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap-io", action="store_true",
+                    help="e2e loop: copy the next batch on a copy stream while the current step replays "
+                         "(trainer.GraphedStep.load_async; opt-in until measured on a GPU)")
     ap.add_argument("--whole-graph", action="store_true",
                     help="N > 1: capture the NCCL all-reduces inside ONE step graph (experimental)")
     ap.add_argument("--segmented", action="store_true",
@@ -319,6 +327,7 @@ def main():
     if args.segmented and world == 1:
         grad_sync = trainer.GradSync(enabled=False)
     eng = StepEngine(p, device, use_graph=not args.no_graph, grad_sync=grad_sync, segmented=args.segmented)
+    eng.overlap_io = args.overlap_io
 
     # warm-up (eager: builds caches, sets kernel attributes), then capture
     side = torch.cuda.Stream()

@@ -284,7 +284,6 @@ class TrunkRunner:
             up_s = getattr(G, "upsample%d_seg" % i)
             cs = ConvNode(tape, "up", a_seg, up_s[1].weight, "upsample%d_seg" % i)
             z_s = tape.add(cs)
-            last_seg = (i == 4)
             bs = BnActNode(tape, z_s, _bn_tuple(up_s[2]), ops.ACT_RELU, "upsample%d_seg.bn" % i,
                            want_planes=True)
             a_seg = tape.add(bs)
@@ -299,7 +298,6 @@ class TrunkRunner:
             bi = BnActNode(tape, z_i, _bn_tuple(up_i[2]), ops.ACT_RELU, "upsample%d.bn" % i, mod=mod)
             a_img = tape.add(bi)
             nodes.update({cs.name: cs, bs.name: bs, ci.name: ci, bi.name: bi})
-            del last_seg
         self.nodes = nodes
         self.a_img, self.a_seg = a_img, a_seg
         img = self._head_fwd(a_img, G.img[0].weight, 3, "img")

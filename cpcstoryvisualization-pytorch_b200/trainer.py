@@ -358,6 +358,8 @@ class GraphedStep:
         self.loss_host = torch.zeros(len(LOSS_KEYS))
         if self.device.type == "cuda":
             self.loss_host = self.loss_host.pin_memory()
+        self._copy_stream = self._staging = None
+        self._pending = False
 
     # --- static buffers ----------------------------------------------------------------------
     def fits(self, st_batch, im_batch):
@@ -373,6 +375,32 @@ class GraphedStep:
         for dst, src in ((self.dev_st, st_batch), (self.dev_im, im_batch)):
             for k, t in dst.items():
                 t.copy_(src[k], non_blocking=True)
+
+    def load_async(self, st_batch, im_batch):
+        """Pipelined ``load``: the host-to-device copy goes to a staging set of buffers on a copy
+        stream, so the copy of step k+1's inputs overlaps the replay of step k; the next ``step``
+        waits for it and moves staging -> static buffers with one multi-tensor device copy.
+        (Not yet exercised on a GPU -- bench.py ``--overlap-io``; ``load`` is the default.)"""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging = [{k: torch.empty_like(t) for k, t in d.items()} for d in (self.dev_st, self.dev_im)]
+            self._ready, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed)      # staging free again (no-op the first time)
+            for dst, src in zip(self._staging, (st_batch, im_batch)):
+                for k, t in dst.items():
+                    t.copy_(src[k], non_blocking=True)
+            self._ready.record(self._copy_stream)
+        self._pending = True
+
+    def _consume_staging(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready)
+        dsts = [t for d in (self.dev_st, self.dev_im) for t in d.values()]
+        srcs = [s[k] for d, s in zip((self.dev_st, self.dev_im), self._staging) for k in d]
+        torch._foreach_copy_(dsts, srcs)
+        self._consumed.record(cur)
+        self._pending = False
 
     def download(self):
         self.loss_host.copy_(self.loss_dev, non_blocking=True)
@@ -431,6 +459,8 @@ class GraphedStep:
         self.graph = True
 
     def step(self):
+        if self._pending:
+            self._consume_staging()
         if self.graph is None:
             self._step_body()
         elif not self.segmented:
