@@ -437,12 +437,16 @@ class GraphedStep:
         self.opts["G"].step()
         self._record(self._out)
 
-    def capture(self):
+    def capture(self, capture_error_mode=None):
+        """``capture_error_mode="thread_local"`` when other host threads keep making CUDA calls
+        during the capture (DataLoader pin-memory thread, NCCL watchdog)"""
         knets.invalidate_weight_cache()
         stream = step_stream(self.device)
+        kw = {}
+        if capture_error_mode is not None:
+            kw["capture_error_mode"] = capture_error_mode
         if not self.segmented:
             self.graph = torch.cuda.CUDAGraph()
-            kw = {}
             if self.grad_sync is not None and getattr(self.grad_sync, "enabled", False):
                 kw["capture_error_mode"] = "thread_local"   # the NCCL watchdog thread keeps running
             with torch.cuda.graph(self.graph, stream=stream, **kw):
@@ -452,7 +456,7 @@ class GraphedStep:
         pool = None
         for seg in (self._seg_d, self._seg_g, self._seg_opt):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool, stream=stream):
+            with torch.cuda.graph(g, pool=pool, stream=stream, **kw):
                 seg()
             pool = g.pool()
             self.graphs.append(g)
@@ -567,7 +571,7 @@ class GANTrainer(object):
                     graphed.load(st_batch, im_batch)
                     if graphed.graph is None:
                         if eager_steps >= self.GRAPH_WARMUP_STEPS:
-                            graphed.capture()
+                            graphed.capture(capture_error_mode="thread_local")   # loader threads
                         else:
                             eager_steps += 1
                     graphed.step()

@@ -98,3 +98,93 @@ def test_gan_trainer_loop(monkeypatch, tmp_path):
     assert {k for k, _, _ in logged} == set(trainer.LOSS_KEYS) and len(logged) == 2 * len(trainer.LOSS_KEYS)
     sd = torch.load(os.path.join(tmp_path, "netG_epoch_2.pth"))
     assert set(sd) == set(out_nets["G"].state_dict())
+
+
+class _FakeGraph:
+    """stand-in for torch.cuda.CUDAGraph on a box without a GPU: 'capturing' runs the body once and
+    keeps it, 'replay' runs it again -- enough to drive the host logic of GraphedStep.capture / step"""
+
+    def __init__(self):
+        self.body = None
+
+    def pool(self):
+        return "pool"
+
+    def replay(self):
+        self.body()
+
+
+class _FakeCapture:
+    def __init__(self, graph, pool=None, stream=None, **kw):
+        self.graph = graph
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def test_graphed_step_capture_paths_host_logic(monkeypatch, tmp_path):
+    """capture() + step() of the one-graph and of the three-graph (gradient exchange) variants with
+    a fake CUDAGraph: every attribute / call the real capture goes through exists and the segmented
+    replay issues the two exchanges between the segments"""
+    import torch.distributed as dist
+    import trainer
+    p, nets, st, im, labels = _setup(monkeypatch)
+    dist.init_process_group("gloo", init_method="file://%s" % (tmp_path / "pg"), rank=0, world_size=1)
+    try:
+        _capture_paths(monkeypatch, trainer, p, nets, st, im, labels)
+    finally:
+        dist.destroy_process_group()
+
+
+def _capture_paths(monkeypatch, trainer, p, nets, st, im, labels):
+    monkeypatch.setattr(trainer, "step_stream", lambda device=None: None)
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", _FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", _FakeCapture)
+    noise = synth.make_noise(p, 2)
+    for exchange in (False, True):
+        nn_ = copy.deepcopy(nets)
+        opts = trainer.build_optimizers(nn_, fused=False)
+        calls = []
+        sync = trainer.GradSync(enabled=exchange)
+        orig_call = sync.__call__
+
+        class Spy:
+            enabled = exchange
+
+            def __call__(self, params):
+                calls.append(len(list(params)))
+                return orig_call(params)
+        gs = trainer.GraphedStep(nn_, opts, labels, {k: v.clone() for k, v in st.items()},
+                                 {k: v.clone() for k, v in im.items()}, grad_sync=Spy() if exchange else None)
+        assert gs.segmented == exchange
+        bodies = []
+
+        def run_capture():
+            # the fake context cannot intercept the body: record it by wrapping the segment functions
+            if gs.segmented:
+                for name in ("_seg_d", "_seg_g", "_seg_opt"):
+                    fn = getattr(gs, name)
+                    bodies.append(fn)
+            else:
+                bodies.append(gs._step_body)
+            harness.inject_noise(nn_["G"], synth.NoiseFeed(noise))
+            gs.capture()
+        run_capture()
+        if gs.segmented:
+            assert len(gs.graphs) == 3
+            for g, fn in zip(gs.graphs, bodies):
+                g.body = fn
+        else:
+            gs.graph.body = bodies[0]
+        harness.inject_noise(nn_["G"], synth.NoiseFeed(noise))
+        calls.clear()
+        gs.load(st, im)
+        gs.step()
+        losses = gs.losses()
+        assert all(v == v for v in losses.values())          # finite, not NaN
+        if exchange:
+            # D_se, D_im, D_st after the discriminator stage, G after the generator stage
+            assert len(calls) == 4, calls
