@@ -167,6 +167,47 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def run_stock_cuda_arm(args, dev=None, p=None):
+    """BASELINE.md "second bar" (not part of the driver's contract; run by hand):
+    ``bench.py --impl stock-cuda``.  The same oracle port of the reference step, full cfg/final.yml
+    batch, on cuda:0 through STOCK PyTorch (cuDNN / cuBLAS / ATen, eager, the reference's own
+    execution model), fp32 with TF32 off and on.  Device-timed with CUDA events."""
+    import torch.backends.cudnn as cudnn
+    from oracle import functional as Fn
+    from oracle import params, synth
+    dev = dev if dev is not None else torch.device("cuda", 0)
+    if p is None:
+        p = preset_dict()
+        p["CUDA"] = True
+    out = {}
+    for tf32 in (False, True):
+        cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        cudnn.benchmark = True
+        model = Fn.OracleModel(params.init_all(p, 0), p, device=dev)
+        batch = synth.make_batch(p, 1, device=dev)
+        noise = [synth.make_noise(p, 2 + i, device=dev) for i in range(args.warmup + args.steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                torch.cuda.synchronize()
+                e0.record()
+            Fn.train_step(model, batch, synth.NoiseFeed(noise[i]))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out["tf32_on" if tf32 else "tf32_off"] = {"ms_per_step": ms, "stories_per_s": p["ST_BATCH"] / (ms * 1e-3)}
+        del model
+        torch.cuda.empty_cache()
+    line = {"impl": "stock-cuda", "metric": "train stories/s", "unit": "stories/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "value": out["tf32_off"]["stories_per_s"],
+            "ms_per_step": out["tf32_off"]["ms_per_step"], "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "execution": "oracle port of the reference step, eager stock PyTorch "
+                       "(cuDNN benchmark mode), no per-step host syncs"},
+            "tf32_off": out["tf32_off"], "tf32_on": out["tf32_on"]}
+    print(json.dumps(line), flush=True)
+
+
 # ----------------------------------------------------------------------------- product arm
 class StepEngine:
     """Networks, optimisers and a pinned synthetic host batch around the product's own
@@ -304,6 +345,9 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.impl == "stock-cuda":
+        run_stock_cuda_arm(args)
         return
     args.warmup = max(args.warmup, 3)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.whole_graph:
