@@ -464,6 +464,9 @@ def main():
         "gpu_launches_per_step": launches_per_step,
         "roofline": {"bound": "tensor", "achieved": prof["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
                      "frac": prof["achieved_tflops"] / peak, "traffic": None,
+                     "traffic_note": "no per-launch average over the 219 launch shapes; ncu --set full of four "
+                                     "GEMM classes in profiles/r01_ncu_full_v2_head_and_gemm_classes.txt (up3 "
+                                     "forward: 77 MB read + 56 MB written = its operands and output once)",
                      "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM)", "peak_source": peak_src,
                      "executed_gflop_per_step": prof["executed_gflop_per_step"],
                      "gemm_launches_per_step": prof["launches_per_step"],
