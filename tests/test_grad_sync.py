@@ -46,3 +46,64 @@ def test_grad_sync_world2():
         assert torch.allclose(g0, torch.full((5, 3), 1.5))
         assert torch.allclose(g1, torch.arange(7.0) * 1.5)
         assert g2 is None
+
+
+class _Patch:
+    """minimal stand-in for pytest's monkeypatch inside a spawned worker"""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p_ in (root, os.path.join(root, "cpcstoryvisualization-pytorch_b200"), os.path.join(root, "tests")):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import emulator
+    import harness
+    import trainer
+    from oracle import params, presets, synth
+    emulator.install(_Patch)
+    p = presets.get("tiny")
+    dev = torch.device("cpu")
+    N, B = p["IM_BATCH"], p["ST_BATCH"]
+    labels = (torch.ones(N), torch.zeros(N), torch.ones(B), torch.zeros(B))
+    x = harness.product_inputs(synth.make_batch(p, 10 + rank))          # this rank's shard of the job
+    noise = synth.make_noise(p, 20 + rank)
+    grads = {}
+    for mode, sync in (("local", None), ("synced", trainer.GradSync())):
+        nets = harness.build_product(p, params.init_all(p, 0), dev)     # identical weights on every rank
+        harness.inject_noise(nets["G"], synth.NoiseFeed(noise))
+        opts = trainer.build_optimizers(nets, fused=False)
+        trainer.train_step(nets, opts, x, labels, 1.0, grad_sync=sync, apply_optim=(mode == "synced"))
+        grads[mode] = torch.cat([q.grad.flatten() for k in ("D_im", "G") for q in nets[k].parameters()
+                                 if q.grad is not None])
+        if mode == "synced":
+            weights = torch.cat([q.detach().flatten() for n in nets.values() for q in n.parameters()])
+    # D gradients do not depend on the optimiser coupling: synced == mean over ranks of the local ones
+    n_d = sum(q.numel() for q in nets["D_im"].parameters())
+    local = [torch.zeros(n_d) for _ in range(world)]
+    dist.all_gather(local, grads["local"][:n_d].contiguous())
+    out[rank] = (float((grads["synced"][:n_d] - sum(local) / world).abs().max()),
+                 float(grads["synced"][:n_d].abs().max()), weights)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_step_world2():
+    """SURVEY.md section 8e on two gloo ranks (kernel-contract emulator): each rank runs train_step on
+    its own shard; after the one exchange per optimiser step the discriminator gradients are the
+    mean of the per-rank gradients and every rank ends the step with identical weights."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for rank in range(world):
+        err, scale, _ = out[rank]
+        assert err <= 1e-6 * max(scale, 1.0), (rank, err, scale)
+    assert torch.equal(out[0][2], out[1][2])
