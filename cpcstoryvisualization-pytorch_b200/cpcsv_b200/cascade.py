@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import conv, ops
 from .engine import T4, BnActNode, ConvNode, StateOrder, Tape, rup, _e
-from .nets import _CACHE, TapeFn, TrunkRunner, _alias, _bn_tuple, _eval_bn_unsupported, _row_pad_map
+from .nets import _CACHE, TapeFn, TrunkRunner, _alias, _bn_tuple, _eval_needs_no_grad, _row_pad_map
 
 BN_MOMENTUM = 0.1
 
@@ -150,7 +150,7 @@ class SegEncoder:
             cn = DownConvNode(tape, a, blk[0].weight, "downsample%d_seg" % i)
             zc = tape.add(cn)
             bn = BnActNode(tape, zc, _bn_tuple(blk[1]), ops.ACT_RELU, "downsample%d_seg.bn" % i,
-                           want_f32=want_f32)
+                           want_f32=want_f32, pre_bias=blk[0].bias)
             a = tape.add(bn)
             if tape.training:
                 # the conv bias only shifts the batch mean BatchNorm subtracts again
@@ -227,7 +227,7 @@ class CascadeTrunkRunner(TrunkRunner):
 
     def run_forward(self, zmc_all, *plist):
         G = self.G
-        _eval_bn_unsupported(G)
+        _eval_needs_no_grad(G, self.need_grad)
         N = zmc_all.shape[0]
         # Split bf16 operands (3 MMAs) also for the no-grad call: the image depends on the mask
         # through tanh -> re-encoder -> modulation, twice the depth of the plain generator, and
@@ -384,7 +384,7 @@ class AutoencoderRunner(TrunkRunner):
 
     def run_forward(self, mask, *plist):
         G = self.G
-        _eval_bn_unsupported(G)
+        _eval_needs_no_grad(G, self.need_grad)
         tape = Tape(_CACHE, training=G.training, need_grad=self.need_grad)
         self.tape = tape
         enc = SegEncoder(tape, G)

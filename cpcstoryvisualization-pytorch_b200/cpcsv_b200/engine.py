@@ -368,12 +368,31 @@ class GemmNode:
 
 
 # ------------------------------------------------------------------------------ BN / act node
+def eval_affine(bn, C, chan_map, c_valid, eps=1e-5):
+    """per-channel (scale, shift) of an eval-mode BatchNorm over the C (padded / re-ordered) channels
+    of a kernel tensor: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale;
+    channels beyond c_valid or mapped to -1 (padding) get 0 / 0, like cpcsv_bn_finalize."""
+    gamma, beta, rmean, rvar, _ = bn
+    dev = gamma.device
+    sc = gamma.detach() / torch.sqrt(rvar + eps)
+    sh = beta.detach() - rmean * sc
+    pos = torch.arange(C, device=dev)
+    idx = chan_map.long() if chan_map is not None else pos
+    valid = (pos < c_valid) & (idx >= 0)
+    src = idx.clamp(0, sc.numel() - 1)
+    zero = torch.zeros((), device=dev)
+    return (torch.where(valid, sc[src], zero).contiguous(), torch.where(valid, sh[src], zero).contiguous())
+
+
 class BnActNode:
     """[BatchNorm (batch statistics)] -> activation -> [* (1 + mod)] -> operand planes / fp32."""
 
     def __init__(self, tape, z, bn, act, name, mod=None, want_f32=False, want_planes=True,
-                 chan_map=None, c_valid=None):
+                 chan_map=None, c_valid=None, pre_bias=None):
         self.tape, self.z, self.bn, self.act, self.name, self.mod = tape, z, bn, act, name, mod
+        # bias of the producing conv that was NOT added to z (a batch-statistics BatchNorm removes it;
+        # only the eval-mode normalisation with running statistics has to account for it)
+        self.pre_bias = pre_bias
         self.want_f32, self.want_planes, self.chan_map = want_f32, want_planes, chan_map
         self.c_valid = c_valid if c_valid is not None else (bn[0].numel() if bn else z.C)
         self.out = T4(z.N, z.H, z.W, z.C)
@@ -395,7 +414,18 @@ class BnActNode:
         him = z.mat(out.hi) if out.hi is not None else None
         lom = z.mat(out.lo) if out.lo is not None else None
         scale = shift = None
-        if self.bn is not None:
+        if self.bn is not None and not t.training:
+            # eval mode (reference inference.py:88, trainer.py:161,177 call netG.eval() for the FID / SSIM
+            # loops): normalise with the running statistics, no batch statistics, no state update
+            if t.need_grad:
+                raise NotImplementedError("cpcsv_b200: backward through eval-mode BatchNorm is not implemented "
+                                          "(the reference only evaluates under torch.no_grad())")
+            scale, shift = eval_affine(self.bn, z.C, self.chan_map, self.c_valid)
+            if self.pre_bias is not None:
+                b = torch.zeros(z.C, device=dev)
+                b[:self.pre_bias.numel()].copy_(self.pre_bias.detach())
+                shift = shift + scale * b
+        elif self.bn is not None:
             gamma, beta, rmean, rvar, nbt = self.bn
             if t.training and nbt is not None:
                 t.counters.append(nbt)

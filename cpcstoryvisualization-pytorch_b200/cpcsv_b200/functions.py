@@ -64,6 +64,21 @@ class BatchNorm1dFn(torch.autograd.Function):
         stats = ops.bn_workspace(M, Cp, dev)
         vec = torch.empty(4, Cp, device=dev)
         yp = torch.empty(M, Cp, device=dev)
+        if not training:
+            # eval mode: running statistics, no state update (reference inference.py:88 netG.eval())
+            sc = gamma.detach() / torch.sqrt(rvar + 1e-5)
+            scale = torch.zeros(Cp, device=dev)
+            shift = torch.zeros(Cp, device=dev)
+            scale[:C].copy_(sc)
+            shift[:C].copy_(beta.detach() - rmean * sc)
+            ops.bn_act_pack(xp, scale, shift, ops.ACT_NONE, y=yp)
+            out = yp
+            if act_tanh:
+                out = torch.empty_like(yp)
+                ops.tanh_fwd(yp, out)
+            ctx.eval_mode = True
+            return out[:, :C]
+        ctx.eval_mode = False
         rm, rv = (rmean, rvar) if training else (None, None)
         StateOrder.before(rm)
         from . import engine
@@ -88,6 +103,9 @@ class BatchNorm1dFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        if ctx.eval_mode:
+            raise NotImplementedError("cpcsv_b200: backward through eval-mode BatchNorm1d is not implemented "
+                                      "(the reference only evaluates under torch.no_grad())")
         xp, vec, tout = ctx.saved_tensors
         M, Cp = xp.shape
         C = ctx.C

@@ -193,10 +193,18 @@ def _bn_tuple(bn):
 
 
 def _eval_bn_unsupported(mod):
+    """discriminators: the reference never calls .eval() on them (only on netG, for the FID / SSIM loops)"""
     if not mod.training:
-        raise RuntimeError("cpcsv_b200: eval-mode BatchNorm (running statistics) is not part of the "
-                           "accelerated path; the reference never leaves train mode on this path "
-                           "(SURVEY.md section 3.3)")
+        raise RuntimeError("cpcsv_b200: eval-mode discriminators (running statistics, frozen spectral-norm "
+                           "vectors) are not part of the accelerated path; the reference only ever calls "
+                           ".eval() on the generator (inference.py:88, trainer.py:161,177)")
+
+
+def _eval_needs_no_grad(G, need_grad):
+    """generator in eval mode (running statistics): forward only"""
+    if not G.training and need_grad:
+        raise RuntimeError("cpcsv_b200: the eval-mode generator runs under torch.no_grad() only "
+                           "(reference inference.py:88-89, trainer.py:161-162)")
 
 
 # =============================================================================== generator trunk
@@ -252,7 +260,7 @@ class TrunkRunner:
     # ---------------------------------------------------------------- forward
     def run_forward(self, zmc_all, *plist):
         G = self.G
-        _eval_bn_unsupported(G)
+        _eval_needs_no_grad(G, self.need_grad)
         N, K = zmc_all.shape
         tape = Tape(_CACHE, training=G.training, need_grad=self.need_grad)
         self.tape = tape

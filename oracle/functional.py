@@ -18,8 +18,28 @@ FILTER_SIZE = 21   # model.py:228
 
 
 # --------------------------------------------------------------------------- primitives
+_TRAINING = [True]
+
+
+class eval_mode:
+    """``with eval_mode():`` -- what ``netG.eval()`` changes (reference inference.py:88,
+    trainer.py:161,177): every BatchNorm normalises with its running statistics and leaves them
+    untouched.  (The generator has no other mode-dependent layer.)"""
+
+    def __enter__(self):
+        self.prev = _TRAINING[0]
+        _TRAINING[0] = False
+
+    def __exit__(self, *exc):
+        _TRAINING[0] = self.prev
+        return False
+
+
 def batch_norm(sd, prefix, x):
     """nn.BatchNorm1d/2d in train mode, eps 1e-5, momentum 0.1 (model.py:32,252,...)."""
+    if not _TRAINING[0]:
+        return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"],
+                            sd[prefix + ".weight"], sd[prefix + ".bias"], training=False, eps=1e-5)
     sd[prefix + ".num_batches_tracked"] += 1
     return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"],
                         sd[prefix + ".weight"], sd[prefix + ".bias"],

@@ -1,6 +1,7 @@
 """Generate ``tests/golden/*.pt`` by running the REAL reference (build container only).
 
     python -m oracle.make_golden [tiny small clevr tiny_cascade small_cascade]
+    python -m oracle.make_golden --eval [tiny tiny_cascade]      (eval-mode generator, see run_eval)
 
 For every preset: oracle-initialised weights (``oracle/params.py``, seed 0) are loaded into
 the reference's own modules (strict), the seeded synthetic batch (``oracle/synth.py``,
@@ -66,7 +67,44 @@ def run(name):
           "%.2f MB" % (os.path.getsize(path) / 1e6))
 
 
+def run_eval(name):
+    """eval-mode generator (reference inference.py:88-89 / trainer.py:161-162: ``netG.eval()`` under
+    no_grad): one train-mode no-grad pass first, so the running statistics are no longer their
+    initial 0 / 1, then ``sample_videos`` / ``sample_images`` with ``seg=True`` in eval mode.
+    Writes tests/golden/eval_<name>.pt."""
+    torch.manual_seed(1234)
+    p = presets.get(name)
+    ref_model, _ref_utils, cfg = load_reference(p)
+    states = params.init_all(p, seed=0)
+    netG = build_reference_nets(ref_model, p, states)["G"]
+    feed = synth.NoiseFeed(synth.make_noise(p, seed=2))
+    inject_noise(netG, feed)
+    batch = synth.make_batch(p, seed=1)
+    T = cfg.TEXT.DIMENSION
+    im_motion = torch.cat((batch["im_desc"][:, :T], batch["im_labels"]), 1)
+    im_content = batch["im_content"][:, :, :T]
+    st_motion = torch.cat((batch["st_desc"][:, :, :T], batch["st_labels"]), 2)
+    st_content = batch["st_desc"][:, :, :T]
+    with torch.no_grad():
+        netG.train()
+        netG.sample_videos(st_motion, st_content)
+        netG.sample_images(im_motion, im_content, seg=True)
+        netG.eval()
+        _, st_fake, _, _, _, _, st_seg = netG.sample_videos(st_motion, st_content, seg=True)
+        _, im_fake, _, _, _, _, im_seg = netG.sample_images(im_motion, im_content, seg=True)
+    assert feed.pos == len(feed.tensors)
+    gold = {"preset": p, "torch": str(torch.__version__),
+            "st_fake": st_fake.contiguous().clone(), "st_seg": st_seg.contiguous().clone(),
+            "im_fake": im_fake.contiguous().clone(), "im_seg": im_seg.contiguous().clone()}
+    path = os.path.join(OUT, "eval_%s.pt" % name)
+    torch.save(gold, path)
+    print("eval", name, "%.2f MB" % (os.path.getsize(path) / 1e6))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) == 3 and sys.argv[1] == "--eval":
+        run_eval(sys.argv[2])
+        sys.exit(0)
     # one preset per process: the reference reads cfg at import/construction time
     names = sys.argv[1:] or ["tiny"]
     assert len(names) == 1, "run one preset per process"

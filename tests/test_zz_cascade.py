@@ -182,3 +182,13 @@ def test_graphed_step_replay_matches_eager_gpu():
         assert abs(v - losses["graph"][k]) <= 1e-3 * abs(v) + 1e-6, (k, v, losses["graph"][k])
     trainer.set_lr(opts["G"], 5e-5)
     assert float(opts["G"].param_groups[0]["lr"]) == pytest.approx(5e-5)
+
+
+# ------------------------------------------------------------------------------ eval-mode generator
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny", "tiny_cascade"])
+def test_product_eval_mode_gpu(name):
+    """netG.eval() under no_grad (reference inference.py:88-89) on the real kernels vs the golden
+    outputs of the REAL reference"""
+    from test_eval_mode import run_product_eval
+    run_product_eval(name, torch.device("cuda"))
