@@ -1,7 +1,9 @@
 """Loss / bookkeeping helpers with the reference's names and call signatures
 (``miscc/utils.py`` of the reference: compute_discriminator_loss l.48-123,
 compute_generator_loss l.126-171, KL_loss l.184-188, weights_init l.191-201, get_multi_acc
-l.313-321, save_model l.323-338, count_param l.431-435).
+l.313-321, save_model l.323-338, count_param l.431-435); the consumers of the generator's outputs
+(image sheets, PNG / npy writers, sampling loops) live in ``miscc/outputs.py`` and are re-exported here
+under the reference's names.
 
 Differences that do not change results: the discriminators are called directly instead of
 through ``nn.parallel.data_parallel`` (one process drives one GPU here, where data_parallel
@@ -15,6 +17,11 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from miscc.config import cfg  # noqa: F401
+
+from miscc.outputs import (check_is_order, compute_cyc_loss_img, compute_cyc_loss_txt,  # noqa: F401,E402
+                           create_random_shuffle, images_to_numpy, inference_samples, save_all_img,
+                           save_image_results, save_img_results, save_story_results, save_test_samples,
+                           save_train_samples)
 
 SYNC_ACCURACY = True   # reference behaviour: .cpu().numpy() round trip per call (host sync)
 PARALLEL_PASSES = True  # real / fake (/ wrong-pair) passes of one discriminator on parallel CUDA streams

@@ -26,7 +26,7 @@ import torch.optim as optim
 
 from miscc.config import cfg
 from miscc.utils import (KL_loss, compute_discriminator_loss, compute_generator_loss, count_param,
-                         mkdir_p, save_model, weights_init)
+                         mkdir_p, save_image_results, save_model, save_story_results, weights_init)
 from cpcsv_b200 import nets as knets
 from cpcsv_b200 import streams
 
@@ -560,6 +560,7 @@ class GANTrainer(object):
         for epoch in range(start_epoch, self.max_epoch):
             start_t = time.time()
             num_step = len(storyloader)
+            last = None
             for i, data in enumerate(storyloader):
                 st_batch, im_batch = tensors(data), tensors(self.sample_real_image_batch(to_device=False))
                 want_log = self._logger is not None and i % 20 == 0
@@ -593,6 +594,23 @@ class GANTrainer(object):
                     step = i + num_step * epoch
                     for key, val in stats.items():
                         self._logger.add_scalar(key, val, step)
+                last = (data, st_batch, i)
+            # end-of-epoch sample sheet from the last story batch (reference trainer.py:437-444): one more
+            # train-mode no-grad generator call (it moves the BatchNorm running statistics, as there)
+            if last is not None:
+                data, st_batch, i = last
+                st_dev = {k: v.to(dev, non_blocking=True) for k, v in st_batch.items()}
+                T = cfg.TEXT.DIMENSION
+                st_content = st_dev["description"][:, :, :T]
+                st_motion = torch.cat((st_content, st_dev["labels"]), 2)
+                with torch.no_grad():
+                    _, fake, _, _, _, _, se_fake = netG.sample_videos(st_motion, st_content, seg=True)
+                st_result = save_story_results(st_batch["images"].cpu(), fake, data.get("text"), epoch,
+                                               self.image_dir, i)
+                se_result = save_image_results(None, se_fake)
+                if self._logger is not None and hasattr(self._logger, "add_image"):
+                    self._logger.add_image("pororo", st_result.transpose(2, 0, 1) / 255, epoch)
+                    self._logger.add_image("segment", se_result.transpose(2, 0, 1) / 255, epoch)
             # learning-rate halving, reference trainer.py:447-456
             if epoch % lr_decay_step == 0 and epoch > 0:
                 generator_lr *= 0.5

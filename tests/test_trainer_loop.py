@@ -71,11 +71,15 @@ def test_gan_trainer_loop(monkeypatch, tmp_path):
     cfg.NET_G = ""
     t = trainer.GANTrainer.__new__(trainer.GANTrainer)      # __init__ binds a CUDA device
     t.model_dir = str(tmp_path)
+    t.image_dir = str(tmp_path / "Image")
+    os.makedirs(t.image_dir)
     t.video_len, t.max_epoch, t.snapshot_interval = p["VIDEO_LEN"], 2, 1
     t.imbatch_size, t.stbatch_size, t.ratio = p["IM_BATCH"], p["ST_BATCH"], 1.0
     t.con_ckpt, t.device = None, torch.device("cpu")
     logged = []
-    t._logger = types.SimpleNamespace(add_scalar=lambda k, v, s: logged.append((k, v, s)))
+    sheets = []
+    t._logger = types.SimpleNamespace(add_scalar=lambda k, v, s: logged.append((k, v, s)),
+                                      add_image=lambda tag, img, ep: sheets.append((tag, img.shape, ep)))
     captured = {}
     orig = trainer.build_optimizers
 
@@ -83,7 +87,8 @@ def test_gan_trainer_loop(monkeypatch, tmp_path):
         captured["opts"] = orig(nets_, fused=False)
         return captured["opts"]
     monkeypatch.setattr(trainer, "build_optimizers", spy)
-    st_loader = [dict(st, text=["a story"])]
+    B, V = p["ST_BATCH"], p["VIDEO_LEN"]
+    st_loader = [dict(st, text=[["frame %d of story %d" % (f, b) for b in range(B)] for f in range(V)])]
     im_loader = [dict(im, text=["an image"])]
     out_nets = t.train(im_loader, st_loader, None)
     assert set(out_nets) == {"G", "D_im", "D_st", "D_se"}
@@ -96,6 +101,11 @@ def test_gan_trainer_loop(monkeypatch, tmp_path):
     assert {"netG_epoch_0.pth", "netG_epoch_1.pth", "netG_epoch_2.pth", "netD_im_epoch_last.pth",
             "netD_st_epoch_last.pth", "netD_se_epoch_last.pth"} <= files, files
     assert {k for k, _, _ in logged} == set(trainer.LOSS_KEYS) and len(logged) == 2 * len(trainer.LOSS_KEYS)
+    # end-of-epoch sample sheets (reference trainer.py:437-444): stories next to the ground truth, masks
+    assert [tag for tag, _, _ in sheets] == ["pororo", "segment"] * 2
+    h, w = B * (68 + 2) + 2, (V * 66 + 2) + 4      # make_grid of per-story rows, 2-pixel gutters twice
+    assert sheets[0][1] == (3, h, 2 * w) and sheets[1][1] == (3, h, w)
+    assert os.path.exists(os.path.join(t.image_dir, "fake_samples_1.txt"))
     sd = torch.load(os.path.join(tmp_path, "netG_epoch_2.pth"))
     assert set(sd) == set(out_nets["G"].state_dict())
 
