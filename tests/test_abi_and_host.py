@@ -49,3 +49,21 @@ def test_gemm_struct_layout_matches_header():
     assert C.sizeof(_lib.Tap) == 40
     # 19 int32 fields (incl. cta_pair) padded to 20 x 4 bytes before the int64 members
     assert C.sizeof(_lib.Gemm) == 20 * 4 + 4 * 8 + 2 * 8 + 4 * 88 + 16 * 40
+
+
+def test_miscc_package_falls_through_to_the_reference_for_modules_it_does_not_replace(tmp_path):
+    """with this package first on sys.path, ``from miscc.datasets import ...`` (reference
+    main_pororo.py:23, inference.py:26) still finds the reference's own miscc/datasets.py"""
+    import subprocess
+    import sys
+    ref = tmp_path / "ref" / "miscc"
+    ref.mkdir(parents=True)
+    (ref / "__init__.py").write_text("")
+    (ref / "datasets.py").write_text("class TextDataset:\n    origin = 'reference'\n")
+    (ref / "utils.py").write_text("raise RuntimeError('the reference utils must stay shadowed')\n")
+    pkg = os.path.join(ROOT, "cpcstoryvisualization-pytorch_b200")
+    code = ("import sys; sys.path[:0] = [%r, %r]; from miscc.datasets import TextDataset; import miscc.utils as u; "
+            "print(TextDataset.origin, hasattr(u, 'compute_discriminator_loss'))" % (pkg, str(tmp_path / "ref")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.split()[-2:] == ["reference", "True"]
