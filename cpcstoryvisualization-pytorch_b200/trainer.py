@@ -477,6 +477,22 @@ class GraphedStep:
             self.graphs[2].replay()
 
 
+def snapshot_sources(output_dir, cfg_file=None):
+    """reference trainer.py:55-61: keep the settings and the model / trainer sources next to the run
+    (``inference.py:61-68`` later re-imports ``<output_dir>/model.py`` under another name; the copy
+    finds ``cpcsv_b200`` through ``sys.path`` or ``CPCSV_B200_HOME``).  With ``cfg.CASCADE_MODEL`` the
+    cascade file is the one stored as ``model.py``, as in the reference."""
+    from shutil import copyfile
+    here = os.path.dirname(os.path.abspath(__file__))
+    if os.path.exists(os.path.join(output_dir, "Model", "model.py")):      # the reference's (never true) guard
+        return
+    if cfg_file and os.path.exists(cfg_file):
+        copyfile(cfg_file, os.path.join(output_dir, "setting.yml"))
+    copyfile(os.path.join(here, "cascade_model.py" if cfg.CASCADE_MODEL else "model.py"),
+             os.path.join(output_dir, "model.py"))
+    copyfile(os.path.join(here, "trainer.py"), os.path.join(output_dir, "trainer.py"))
+
+
 class GANTrainer(object):
     def __init__(self, output_dir, args, ratio=1.0):
         if cfg.TRAIN.FLAG:
@@ -487,6 +503,7 @@ class GANTrainer(object):
             self.test_dir = os.path.join(output_dir, "Test")
             for d in (self.model_dir, self.image_dir, self.log_dir, self.test_dir):
                 mkdir_p(d)
+            snapshot_sources(output_dir, getattr(args, "cfg_file", None))
         self.video_len = cfg.VIDEO_LEN
         self.max_epoch = cfg.TRAIN.MAX_EPOCH
         self.snapshot_interval = cfg.TRAIN.SNAPSHOT_INTERVAL

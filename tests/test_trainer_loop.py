@@ -198,3 +198,34 @@ def _capture_paths(monkeypatch, trainer, p, nets, st, im, labels):
         if exchange:
             # D_se, D_im, D_st after the discriminator stage, G after the generator stage
             assert len(calls) == 4, calls
+
+
+def test_snapshot_model_copy_is_importable_under_another_name(tmp_path):
+    """reference trainer.py:55-61 + inference.py:61-68: the run directory gets model.py (the cascade
+    file when cfg.CASCADE_MODEL) and a copy imported under another module name still builds the generator"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "cpcstoryvisualization-pytorch_b200")
+    code = r'''
+import importlib, os, shutil, sys
+sys.path[:0] = [%r, %r]
+from miscc.config import cfg
+from oracle import presets
+import trainer
+for cascade in (False, True):
+    presets.apply_to_cfg(cfg, presets.get("tiny_cascade" if cascade else "tiny"))
+    out = os.path.join(%r, "run%%d" %% cascade)
+    os.makedirs(out)
+    trainer.snapshot_sources(out)
+    assert sorted(os.listdir(out)) == ["model.py", "trainer.py"]
+    name = "model_saved_%%d" %% cascade
+    shutil.copyfile(os.path.join(out, "model.py"), os.path.join(%r, name + ".py"))
+    sys.path.insert(0, %r)
+    mod = importlib.import_module(name)
+    G = mod.StoryGAN(cfg.VIDEO_LEN)
+    assert hasattr(G, "presample") == cascade and hasattr(G, "sample_videos")
+print("ok")
+''' % (pkg, root, str(tmp_path), str(tmp_path), str(tmp_path))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-3000:]
