@@ -549,6 +549,33 @@ class GANTrainer(object):
             self.imagedataset = enumerate(self.imageloader)
         return batch
 
+    def calculate_vfid(self, netG, epoch, testloader):
+        """reference trainer.py:160-174: FID / video-FID of generated test stories with the generator in
+        EVAL mode (running BatchNorm statistics; supported by the kernel path under no_grad).  The
+        metric code (``fid/`` of the reference: InceptionV3 / R(2+1)D features + Frechet distance) is
+        evaluation plumbing outside this package and is imported from the reference tree."""
+        try:
+            from fid.fid_score_v import fid_score
+            from fid.utils import IgnoreLabelDataset, StoryGANDataset
+            from fid.vfid_score import fid_score as vfid_score
+        except ImportError as e:
+            raise RuntimeError("cfg.EVALUATE_FID_SCORE needs the reference's fid/ package on sys.path") from e
+        netG.eval()
+        try:
+            with torch.no_grad():
+                generated = StoryGANDataset(netG, len(testloader), testloader.dataset)
+                real = IgnoreLabelDataset(testloader.dataset)
+                vfid_value = vfid_score(real, generated, cuda=True, normalize=True,
+                                        r_cache=".cache/seg_story_vfid_reference_score.npz")
+                fid_value = fid_score(real, generated, cuda=True, normalize=True,
+                                      r_cache=".cache/seg_story_fid_reference_score.npz")
+        finally:
+            netG.train()
+        if self._logger is not None:
+            self._logger.add_scalar("Evaluation/vfid", vfid_value, epoch)
+            self._logger.add_scalar("Evaluation/fid", fid_value, epoch)
+        return vfid_value, fid_value
+
     GRAPH_WARMUP_STEPS = 3      # eager steps (optimiser state, weight caches, NCCL) before the capture
 
     def train(self, imageloader, storyloader, testloader, stage=1):
@@ -636,6 +663,8 @@ class GANTrainer(object):
                 for k in ("D_st", "D_im"):
                     set_lr(opts[k], discriminator_lr)
                 lr_decay_step *= 2
+            if cfg.EVALUATE_FID_SCORE:
+                self.calculate_vfid(netG, epoch, testloader)
             print("----[{}/{}] epoch {:.1f} min, total {:.1f} h----".format(
                 epoch, self.max_epoch, (time.time() - start_t) / 60, (time.time() - c_time) / 3600))
             if epoch % self.snapshot_interval == 0 and int(os.environ.get("RANK", "0")) == 0:
