@@ -222,10 +222,11 @@ class StepEngine:
         from cpcsv_b200 import nets as knets
         self.trainer, self.knets = trainer, knets
         self.p, self.device = p, device
-        torch.manual_seed(1234 + int(os.environ.get("RANK", "0")))
+        torch.manual_seed(1234)             # identical initial weights on every rank (data parallel)
         self.nets = trainer.build_networks(p["VIDEO_LEN"])
         for n in self.nets.values():
             n.to(device).train()
+        torch.manual_seed(1234 + int(os.environ.get("RANK", "0")))     # independent noise per rank
         self.opts = {}
         for k, net in self.nets.items():
             lr = p["GENERATOR_LR"] if k == "G" else p["DISCRIMINATOR_LR"]

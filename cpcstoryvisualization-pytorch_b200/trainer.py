@@ -69,6 +69,16 @@ class GradSync:
             p.grad = v
 
 
+def broadcast_initial_state(nets, src=0):
+    """data parallel: every rank starts from rank `src`'s parameters and buffers (the reference has one
+    process and one set of weights; with one process per GPU the initialisation RNG may differ per rank)"""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    for net in nets.values():
+        for t in list(net.parameters()) + list(net.buffers()):
+            dist.broadcast(t.data, src)
+
+
 def build_networks(video_len=None):
     """StoryGAN + the three discriminators, initialised like reference trainer.py:87-97."""
     if cfg.CASCADE_MODEL:      # reference trainer.py:83-86
@@ -586,6 +596,7 @@ class GANTrainer(object):
         self.imageloader, self.imagedataset = imageloader, None
         netG, netD_im, netD_st, netD_se = self.load_network_stageI()
         nets = {"G": netG, "D_im": netD_im, "D_st": netD_st, "D_se": netD_se}
+        broadcast_initial_state(nets)
         dev = self.device
         use_graph = dev.type == "cuda" and os.environ.get("CPCSV_GRAPH", "1") != "0"
         opts = build_capturable_optimizers(nets, dev) if use_graph else build_optimizers(nets)
@@ -680,4 +691,4 @@ def story_rate(ms_per_step, n_gpus=1):
 
 
 __all__ = ["GANTrainer", "GraphedStep", "train_step", "build_networks", "build_optimizers",
-           "build_capturable_optimizers", "set_lr", "prepare_inputs", "GradSync", "story_rate", "LOSS_KEYS", "np"]
+           "build_capturable_optimizers", "set_lr", "prepare_inputs", "GradSync", "broadcast_initial_state", "story_rate", "LOSS_KEYS", "np"]

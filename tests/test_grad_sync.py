@@ -33,6 +33,14 @@ def _worker(rank, world, port, out):
     assert sync.enabled and sync.world == world
     sync(params)
     out[rank] = [p.grad.clone() if p.grad is not None else None for p in params]
+    # every rank starts from rank 0's parameters and buffers
+    torch.manual_seed(100 + rank)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))
+    net[1].running_mean.fill_(float(rank))
+    trainer.broadcast_initial_state({"net": net})
+    torch.manual_seed(100)
+    ref = torch.nn.Linear(4, 3)
+    assert torch.equal(net[0].weight.data, ref.weight.data) and float(net[1].running_mean.sum()) == 0.0
     dist.destroy_process_group()
 
 
