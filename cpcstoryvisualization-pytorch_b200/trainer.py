@@ -45,7 +45,11 @@ class GradSync:
         self.world = dist.get_world_size() if self.enabled else 1
         self.avg_in_collective = self.enabled and dist.is_initialized() and dist.get_backend() == "nccl"
 
-    def __call__(self, params):
+    def __call__(self, params, inplace=False):
+        """``inplace``: write the averaged values back into the existing ``.grad`` tensors instead of
+        re-pointing ``.grad`` at the reduced buffer.  Required when the optimiser step that follows is a
+        REPLAYED CUDA graph: it reads the gradient memory it saw at capture time (the addresses the
+        replayed backward pass writes), not whatever ``.grad`` points at afterwards."""
         if not self.enabled:
             return
         owners = [p for p in params if p.grad is not None]
@@ -65,6 +69,9 @@ class GradSync:
             else:
                 dist.all_reduce(flat)
                 flat.div_(self.world)
+        if inplace:
+            torch._foreach_copy_(grads, views)
+            return
         for p, v in zip(owners, views):
             p.grad = v
 
@@ -284,11 +291,14 @@ def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True, forward=None)
     return out
 
 
-def sync_grads(nets, names, grad_sync):
+def sync_grads(nets, names, grad_sync, inplace=False):
     """the one exchange step of the data-parallel job: average gradients across ranks"""
     if grad_sync:
         for k in names:
-            grad_sync(list(nets[k].parameters()))
+            if inplace:
+                grad_sync(list(nets[k].parameters()), inplace=True)
+            else:
+                grad_sync(list(nets[k].parameters()))
 
 
 def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=True, skip_d_wgrad=True):
@@ -480,10 +490,11 @@ class GraphedStep:
         elif not self.segmented:
             self.graph.replay()
         else:
+            # in place: the captured Adam steps read the gradient memory of the captured backward pass
             self.graphs[0].replay()
-            sync_grads(self.nets, D_NETS, self.grad_sync)
+            sync_grads(self.nets, D_NETS, self.grad_sync, inplace=True)
             self.graphs[1].replay()
-            sync_grads(self.nets, ("G",), self.grad_sync)
+            sync_grads(self.nets, ("G",), self.grad_sync, inplace=True)
             self.graphs[2].replay()
 
 

@@ -33,6 +33,12 @@ def _worker(rank, world, port, out):
     assert sync.enabled and sync.world == world
     sync(params)
     out[rank] = [p.grad.clone() if p.grad is not None else None for p in params]
+    # in-place variant (replayed CUDA-graph optimiser steps read the original gradient memory)
+    q = torch.nn.Parameter(torch.zeros(4))
+    q.grad = torch.full((4,), float(rank + 1))
+    ptr = q.grad.data_ptr()
+    sync([q], inplace=True)
+    assert q.grad.data_ptr() == ptr and torch.allclose(q.grad, torch.full((4,), 1.5))
     # every rank starts from rank 0's parameters and buffers
     torch.manual_seed(100 + rank)
     net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))

@@ -164,9 +164,9 @@ def _capture_paths(monkeypatch, trainer, p, nets, st, im, labels):
         class Spy:
             enabled = exchange
 
-            def __call__(self, params):
-                calls.append(len(list(params)))
-                return orig_call(params)
+            def __call__(self, params, inplace=False):
+                calls.append((len(list(params)), inplace))
+                return orig_call(params, inplace=inplace)
         gs = trainer.GraphedStep(nn_, opts, labels, {k: v.clone() for k, v in st.items()},
                                  {k: v.clone() for k, v in im.items()}, grad_sync=Spy() if exchange else None)
         assert gs.segmented == exchange
@@ -198,6 +198,8 @@ def _capture_paths(monkeypatch, trainer, p, nets, st, im, labels):
         if exchange:
             # D_se, D_im, D_st after the discriminator stage, G after the generator stage
             assert len(calls) == 4, calls
+            # replayed optimiser steps read the captured gradient memory: the exchange must be in place
+            assert all(inplace for _, inplace in calls), calls
 
 
 def test_snapshot_model_copy_is_importable_under_another_name(tmp_path):
