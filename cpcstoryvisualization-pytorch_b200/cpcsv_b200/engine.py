@@ -7,6 +7,8 @@ Precision recipe: forward convolutions whose result feeds
 pass run with hi/lo split bf16 operands (3 MMAs, ~16-bit significand); backward GEMMs (dgrad,
 wgrad) are single-pass bf16; statistics, normalisation and all gradients are fp32.
 """
+import weakref
+
 import torch
 
 from . import conv, ops
@@ -65,7 +67,7 @@ class WeightCache:
         streams that were joined (None: every stream)"""
         for key, ent in list(self.d.items()):
             if ent[2] is not None and (streams is None or ent[2] in streams):
-                self.d[key] = (ent[0], ent[1], None, None)
+                self.d[key] = (ent[0], ent[1], None, None, ent[4])
 
     def get(self, key, param, build):
         """Entries remember the stream that packed them and an event recorded after the pack
@@ -79,7 +81,9 @@ class WeightCache:
         tag = (param._version, param.data_ptr(), self.epoch, capturing)
         ent = self.d.get(key)
         cur = torch.cuda.current_stream() if on_gpu else None
-        if ent is not None and ent[0] == tag:
+        # keys carry id(param): an entry only counts while THAT parameter object is alive (a freed
+        # parameter's id, address and version can all be recycled by a later one)
+        if ent is not None and ent[0] == tag and ent[4]() is param:
             if on_gpu and ent[2] is not None and ent[2] != cur:
                 cur.wait_event(ent[3])
                 for tns in (ent[1] if isinstance(ent[1], (list, tuple)) else [ent[1]]):
@@ -91,7 +95,8 @@ class WeightCache:
         if on_gpu:
             ev = torch.cuda.Event()
             ev.record(cur)
-        self.d[key] = (tag, val, cur, ev)
+        # the entry (and the operand planes it keeps alive) goes away with the parameter
+        self.d[key] = (tag, val, cur, ev, weakref.ref(param, lambda _r, k=key, d=self.d: d.pop(k, None)))
         return val
 
 

@@ -67,3 +67,34 @@ def test_miscc_package_falls_through_to_the_reference_for_modules_it_does_not_re
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.split()[-2:] == ["reference", "True"]
+
+
+def test_weight_cache_entries_die_with_their_parameter():
+    """keys carry id(param): a recycled id / address / version of a freed parameter must not hit the
+    old entry, and the packed planes must not outlive the parameter"""
+    import gc
+    from cpcsv_b200 import engine
+    cache = engine.WeightCache()
+    built = []
+
+    def get(p):
+        return cache.get((id(p), "k"), p, lambda: built.append(1) or torch.zeros(3))
+    a = torch.nn.Parameter(torch.zeros(4))
+    get(a)
+    get(a)
+    assert len(built) == 1 and len(cache.d) == 1
+    key = next(iter(cache.d))
+    del a
+    gc.collect()
+    assert len(cache.d) == 0
+    # an impostor with the same key and tag (what id / address recycling would produce) is rebuilt
+    b = torch.nn.Parameter(torch.zeros(4))
+    get(b)
+    ent = cache.d[(id(b), "k")]
+    c = torch.nn.Parameter(torch.zeros(4))
+    import weakref
+    cache.d[(id(b), "k")] = (ent[0], ent[1], ent[2], ent[3], weakref.ref(c))
+    n = len(built)
+    get(b)
+    assert len(built) == n + 1
+    del key
