@@ -12,6 +12,7 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "timeout: per-test limit (pytest-timeout; a no-op without the plugin)")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -140,6 +140,7 @@ def test_tiny_cascade_step_gpu_vs_reference_golden():
 
 # ------------------------------------------------------------------------------ CUDA-graph step (f1)
 @pytest.mark.gpu
+@pytest.mark.timeout(300)
 def test_graphed_step_replay_matches_eager_gpu():
     """trainer.GraphedStep (the step GANTrainer.train and bench.py replay as ONE CUDA graph): three
     steps as eager-eager-capture+replay give the losses of three eager steps.  Noise is injected
@@ -186,6 +187,7 @@ def test_graphed_step_replay_matches_eager_gpu():
 
 # ------------------------------------------------------------------------------ eval-mode generator
 @pytest.mark.gpu
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize("name", ["tiny", "tiny_cascade"])
 def test_product_eval_mode_gpu(name):
     """netG.eval() under no_grad (reference inference.py:88-89) on the real kernels vs the golden
