@@ -227,11 +227,9 @@ class StepEngine:
         for n in self.nets.values():
             n.to(device).train()
         torch.manual_seed(1234 + int(os.environ.get("RANK", "0")))     # independent noise per rank
-        self.opts = {}
-        for k, net in self.nets.items():
-            lr = p["GENERATOR_LR"] if k == "G" else p["DISCRIMINATOR_LR"]
-            self.opts[k] = torch.optim.Adam(net.parameters(), lr=lr, betas=(0.5, 0.999), fused=True,
-                                            capturable=use_graph)
+        # the product's optimiser: PackedAdam (Adam fused with the weight re-layout), lr in a device tensor
+        self.opts = trainer.build_capturable_optimizers(self.nets, device) if use_graph else \
+            trainer.build_optimizers(self.nets, fused=True)
         N, B = p["IM_BATCH"], p["ST_BATCH"]
         self.labels = (torch.ones(N, device=device), torch.zeros(N, device=device),
                        torch.ones(B, device=device), torch.zeros(B, device=device))

@@ -36,6 +36,23 @@ class Gemm(C.Structure):
     ]
 
 
+MAX_PLANES = 6
+
+
+class AdamHyper(C.Structure):
+    _fields_ = [("lr", C.c_void_p), ("bc", C.c_void_p), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float)]
+
+
+class AdamTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64)]
+
+
+class Plane(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("dtype", C.c_int32), ("rows_pad", C.c_int32), ("cols_pad", C.c_int32),
+                ("hi", C.c_void_p), ("lo", C.c_void_p)]
+
+
 _i32, _i64, _f32, _p = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 # name -> argument ctypes (every function returns int unless noted)
@@ -78,6 +95,12 @@ SIGNATURES = {
     "cpcsv_affine_sigmoid_bwd": [_p, _p, _p, _p, _p, _i64, _p],
     "cpcsv_spectral_sigma": [_p, _i32, _i32, _p, _p, _i32, _f32, _p, _p, _p, _p],
     "cpcsv_spectral_bwd": [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p],
+    "cpcsv_adam_tick": [_p, _f32, _f32, _p, _p],
+    "cpcsv_adam_multi": [C.POINTER(AdamTensor), _i32, C.POINTER(AdamHyper), _p],
+    "cpcsv_adam_pack_conv": [_p, _p, _p, _p, _i32, _i32, _i32, _i32, C.POINTER(AdamHyper), C.POINTER(Plane),
+                             _i32, _p],
+    "cpcsv_adam_pack_fc": [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, C.POINTER(AdamHyper), _p, _p, _p, _p,
+                           _p],
 }
 OTHER_SYMBOLS = ("cpcsv_version", "cpcsv_last_error_string", "cpcsv_launch_count",
                  "cpcsv_bn_workspace_doubles")

@@ -46,8 +46,31 @@ class T4:
         return [self.hi, self.lo if n == 2 else None]
 
 
+class CacheEntry:
+    """one packed form of a parameter: ``val`` (operand planes), the validity ``tag``, the stream / event
+    of the kernel that last wrote it, a weak reference to the parameter, and -- for planes that live in
+    PERSISTENT buffers kept current by the optimiser -- their ``spec`` and the ``fill`` closure that
+    re-packs them in place"""
+
+    __slots__ = ("tag", "val", "stream", "event", "ref", "spec", "fill")
+
+    def __init__(self, tag, val, stream, event, ref, spec=None, fill=None):
+        self.tag, self.val, self.stream, self.event, self.ref, self.spec, self.fill = \
+            tag, val, stream, event, ref, spec, fill
+
+
 class WeightCache:
-    """16-bit operand planes of parameters, re-packed only when the parameter changed."""
+    """16-bit operand planes of parameters.
+
+    Two kinds of entries:
+      * MAINTAINED (``spec`` given): the planes of the tensor-core convolutions and of fc / fc_seg live in
+        persistent buffers.  ``optim.PackedAdam`` rewrites them in the same kernel that updates the fp32
+        weight, so they are always current -- inside replayed CUDA graphs too -- and nothing is re-packed
+        between an optimiser step and the next forward pass.  A parameter changed in any other way
+        (``load_state_dict``, another optimiser, ``invalidate``) is re-packed IN PLACE at its next use.
+      * plain: small derived forms (first discriminator layer, head gradients); rebuilt when the parameter
+        changed (``_version``), after every optimiser step (global post-step hook in nets.py, because fused
+        optimisers do not bump ``_version``) or when the capture state differs."""
 
     def __init__(self):
         self.d = {}
@@ -56,47 +79,80 @@ class WeightCache:
     def invalidate(self):
         self.epoch += 1
 
-    def invalidate_params(self, param_ids):
-        """drop the entries of the given parameters (keys are (id(param), kind, planes))"""
+    def invalidate_params(self, param_ids, keep_maintained=False):
+        """drop the entries of the given parameters (keys start with id(param)); maintained planes are
+        marked stale (re-packed into the same buffers at the next use) unless the optimiser that
+        just stepped keeps them current itself"""
         for key in [k for k in self.d if k[0] in param_ids]:
-            del self.d[key]
+            ent = self.d[key]
+            if ent.spec is None:
+                del self.d[key]
+            elif not keep_maintained:
+                ent.tag = None
+
+    def maintained(self, param):
+        """[(key, entry)] of the persistent planes of `param`"""
+        pid = id(param)
+        return [(k, e) for k, e in self.d.items() if k[0] == pid and e.spec is not None and e.ref() is param]
+
+    def refreshed(self, ent, param):
+        """the optimiser has just rewritten the planes of `ent` on the current stream; every later
+        consumer is ordered after it by the step's fork / join structure"""
+        ent.tag = self._tag(param, True, False)
+        ent.stream = ent.event = None
 
     def mark_synced(self, streams=None):
         """after packing streams have been joined into the current one: later consumers need no
         event wait (and must not wait on an event of an earlier graph capture).  `streams` = the
         streams that were joined (None: every stream)"""
-        for key, ent in list(self.d.items()):
-            if ent[2] is not None and (streams is None or ent[2] in streams):
-                self.d[key] = (ent[0], ent[1], None, None, ent[4])
+        for ent in self.d.values():
+            if ent.stream is not None and (streams is None or ent.stream in streams):
+                ent.stream = ent.event = None
 
-    def get(self, key, param, build):
+    def _tag(self, param, maintained, capturing):
+        # planes packed while a CUDA graph is being captured only exist once that graph replays,
+        # and planes packed eagerly must not be waited on from inside a capture: for plain entries
+        # the capture state is part of the validity tag.  Maintained planes sit in persistent buffers
+        # that the (captured or eager) optimiser step keeps current: valid in both states.
+        return (param._version, param.data_ptr(), self.epoch) + (() if maintained else (capturing,))
+
+    def get(self, key, param, build, spec=None, fill=None):
         """Entries remember the stream that packed them and an event recorded after the pack
         kernel: a consumer on another stream (concurrent network calls, pack prefetching) waits
-        on the event instead of racing with the pack."""
+        on the event instead of racing with the pack.  ``spec`` / ``fill(val)``: maintained entry
+        (``build`` allocates AND fills; ``fill`` re-packs into the existing buffers)."""
         on_gpu = param.is_cuda
-        # planes packed while a CUDA graph is being captured only exist once that graph replays,
-        # and planes packed eagerly must not be waited on from inside a capture: the capture
-        # state is part of the validity tag
         capturing = on_gpu and torch.cuda.is_current_stream_capturing()
-        tag = (param._version, param.data_ptr(), self.epoch, capturing)
+        tag = self._tag(param, spec is not None, capturing)
         ent = self.d.get(key)
         cur = torch.cuda.current_stream() if on_gpu else None
         # keys carry id(param): an entry only counts while THAT parameter object is alive (a freed
         # parameter's id, address and version can all be recycled by a later one)
-        if ent is not None and ent[0] == tag and ent[4]() is param:
-            if on_gpu and ent[2] is not None and ent[2] != cur:
-                cur.wait_event(ent[3])
-                for tns in (ent[1] if isinstance(ent[1], (list, tuple)) else [ent[1]]):
-                    if tns is not None:
-                        tns.record_stream(cur)     # keep the allocator from recycling it early
-            return ent[1]
-        val = build()
+        alive = ent is not None and ent.ref() is param
+        if alive and ent.tag == tag:
+            if on_gpu and ent.stream is not None and ent.stream != cur:
+                cur.wait_event(ent.event)
+                if ent.spec is None:
+                    for tns in (ent.val if isinstance(ent.val, (list, tuple)) else [ent.val]):
+                        if tns is not None:
+                            tns.record_stream(cur)     # keep the allocator from recycling it early
+            return ent.val
+        if alive and spec is not None and ent.spec == spec:
+            # stale persistent planes (the parameter was modified outside PackedAdam): re-pack in place.
+            # Earlier readers of the old contents may still be running on other streams.
+            if on_gpu and not capturing:
+                torch.cuda.synchronize(param.device)
+            fill(ent.val)
+            val = ent.val
+        else:
+            val = build()
         ev = None
         if on_gpu:
             ev = torch.cuda.Event()
             ev.record(cur)
         # the entry (and the operand planes it keeps alive) goes away with the parameter
-        self.d[key] = (tag, val, cur, ev, weakref.ref(param, lambda _r, k=key, d=self.d: d.pop(k, None)))
+        self.d[key] = CacheEntry(tag, val, cur, ev, weakref.ref(param, lambda _r, k=key, d=self.d: d.pop(k, None)),
+                                 spec, fill)
         return val
 
 
@@ -191,17 +247,22 @@ CONV_GEOM = {
 
 
 def pack_conv(cache, w, geom, kindcode, rows_pad, cols_pad, planes, dtype=BF16):
-    """(cached) tap-major 16-bit operand planes of a conv weight; see cpcsv_pack_conv_weight"""
+    """(cached, persistent) tap-major 16-bit operand planes of a conv weight; kinds as
+    cpcsv_pack_conv_weight.  Filled here at first use, afterwards kept current by optim.PackedAdam."""
     ntap = CONV_GEOM[geom][3]
+
+    def fill(val):
+        ops.adam_pack_conv(w.detach(), None, None, None, [(kindcode, dtype, rows_pad, cols_pad, val[0], val[1])])
 
     def build():
         dev = w.device
         t16 = ops.TORCH16[dtype]
         hi = _e((ntap * rows_pad, cols_pad), dev, t16)
         lo = _e((ntap * rows_pad, cols_pad), dev, t16) if planes == 2 else None
-        ops.pack_conv_weight(w.detach(), kindcode, rows_pad, cols_pad, hi, lo, dtype)
+        fill([hi, lo])
         return [hi, lo]
-    return cache.get((id(w), kindcode, planes, dtype), w, build)
+    return cache.get((id(w), kindcode, planes, dtype), w, build,
+                     spec=("conv", kindcode, dtype, rows_pad, cols_pad, planes), fill=fill)
 
 
 def prefetch_conv(cache, w, geom, forward=True, backward=True):

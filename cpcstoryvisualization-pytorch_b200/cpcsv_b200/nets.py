@@ -23,11 +23,12 @@ def weight_cache():
 
 
 def invalidate_weight_cache():
-    """Drop every packed operand plane.  The cache validates entries against
-    ``Tensor._version``, but fused optimisers (``Adam(fused=True)``) update parameters without
-    bumping it, so every ``torch.optim`` step also invalidates the cache through the global
-    post-step hook registered below.  Call this by hand after modifying parameters through
-    any other path that bypasses the version counter."""
+    """Mark every packed operand plane stale (re-packed at its next use).  The cache validates
+    entries against ``Tensor._version``; ``optim.PackedAdam`` keeps the planes current itself, and
+    every other ``torch.optim`` step (fused optimisers do not bump ``_version``) invalidates the
+    stepped parameters through the global post-step hook registered below.  Call this by hand after
+    modifying parameters through any other path that bypasses the version counter (``.data``
+    edits; ``miscc.utils.weights_init`` does it for you)."""
     _CACHE.invalidate()
 
 
@@ -38,7 +39,8 @@ def _install_optimizer_hook():
         raise RuntimeError("cpcsv_b200 needs torch.optim global step hooks (torch >= 2.0)") from e
     def hook(opt, args, kwargs):
         ids = {id(p) for g in opt.param_groups for p in g["params"]}
-        _CACHE.invalidate_params(ids)
+        # optim.PackedAdam has just rewritten the persistent planes itself
+        _CACHE.invalidate_params(ids, keep_maintained=getattr(opt, "maintains_planes", False))
 
     register_optimizer_step_post_hook(hook)
 
@@ -77,33 +79,48 @@ def fc_maps(G, C, dev):
 
 
 def pack_fc_fwd(cache, G, lin, C, Kp, planes, dtype):
-    """(cached) operand planes [16*Cp, Kp] of fc / fc_seg for the forward GEMM (rows re-ordered to NHWC)"""
+    """(cached) operand planes [16*Cp, Kp] of fc / fc_seg for the forward GEMM (rows re-ordered to NHWC).
+    The two forms the step uses -- single-plane fp16 (no-grad pass) and bf16 hi/lo -- are persistent and
+    kept current by optim.PackedAdam (cpcsv_adam_pack_fc)."""
     w = lin.weight
     K, Cp = w.shape[1], rup(C, 64)
+    t16 = ops.TORCH16[dtype]
+    if (planes, dtype) in ((1, ops.FP16), (2, ops.BF16)):
+        def fill(val):
+            if planes == 1:
+                ops.adam_pack_fc(w.detach(), None, None, None, C, 16, Cp, Kp, fwd16=val[0])
+            else:
+                ops.adam_pack_fc(w.detach(), None, None, None, C, 16, Cp, Kp, fwd_hi=val[0], fwd_lo=val[1])
+
+        def build():
+            val = [_e((16 * Cp, Kp), w.device, t16), _e((16 * Cp, Kp), w.device, t16) if planes == 2 else None]
+            fill(val)
+            return val
+        return cache.get((id(w), "fc_fwd", planes, dtype), w, build,
+                         spec=("fc", "fwd16" if planes == 1 else "fwd", C, Cp, Kp), fill=fill)
     perm = fc_maps(G, C, w.device)
 
-    def build():
-        t16 = ops.TORCH16[dtype]
+    def build_generic():
         hi = _e((16 * Cp, Kp), w.device, t16)
         lo = _e((16 * Cp, Kp), w.device, t16) if planes == 2 else None
         ops.pack_matrix(w.detach(), 16 * Cp, Kp, K, K, 1, perm, hi, lo, dtype)
         return [hi, lo]
-    return cache.get((id(w), "fc_fwd", planes, dtype), w, build)
+    return cache.get((id(w), "fc_fwd", planes, dtype), w, build_generic)
 
 
 def pack_fc_bwd(cache, G, lin, C, Kp):
-    """(cached) transposed bf16 plane [Kp, 16*Cp] for the data-gradient GEMM"""
+    """(cached, persistent) transposed bf16 plane [Kp, 16*Cp] for the data-gradient GEMM"""
     w = lin.weight
-    K, Cp = w.shape[1], rup(C, 64)
-    perm = fc_maps(G, C, w.device)
+    Cp = rup(C, 64)
+
+    def fill(val):
+        ops.adam_pack_fc(w.detach(), None, None, None, C, 16, Cp, Kp, bwd=val)
 
     def build():
         hi = _e((Kp, 16 * Cp), w.device, torch.bfloat16)
-        # out[r = k, c = j'] = w[perm[j'], k]
-        ops.pack_matrix(w.detach(), Kp, 16 * Cp, 16 * Cp, 1, K, _row_pad_map(K, Kp, w.device), hi, None,
-                        col_map=perm)
+        fill(hi)
         return hi
-    return cache.get((id(w), "fc_bwd", 1), w, build)
+    return cache.get((id(w), "fc_bwd", 1), w, build, spec=("fc", "bwd", C, Cp, Kp), fill=fill)
 
 
 def _prefetch_fc(G, no_grad_forward, forward, backward):

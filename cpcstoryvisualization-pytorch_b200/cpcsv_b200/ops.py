@@ -14,6 +14,7 @@ from . import _lib
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 FP16, BF16 = 0, 1
 TORCH16 = {FP16: torch.float16, BF16: torch.bfloat16}
+MAX_PLANES = _lib.MAX_PLANES
 
 
 def _stream():
@@ -395,3 +396,70 @@ def spectral_bwd(g2d, w2d, u, v, sigma, dw2d, scratch):
     _lib.check(_lib.load().cpcsv_spectral_bwd(
         _ptr(g2d, torch.float32), _ptr(w2d, torch.float32), _ptr(u), _ptr(v), _ptr(sigma), R, Cc,
         _ptr(dw2d, torch.float32), _ptr(scratch), _stream()), "cpcsv_spectral_bwd")
+
+
+# ------------------------------------------------------------------ optimiser (Adam fused with the re-layout)
+class AdamHyper:
+    """device-resident hyper-parameters of one optimiser: lr [1], bc [2] (bias corrections written
+    by ``adam_tick``), and the host constants"""
+
+    def __init__(self, lr, bc, beta1, beta2, eps):
+        self.lr, self.bc, self.beta1, self.beta2, self.eps = lr, bc, float(beta1), float(beta2), float(eps)
+
+    def to_c(self):
+        h = _lib.AdamHyper()
+        h.lr, h.bc = _ptr(self.lr, torch.float32).value, _ptr(self.bc, torch.float32).value
+        h.beta1, h.beta2, h.eps = self.beta1, self.beta2, self.eps
+        return h
+
+
+def adam_tick(step, beta1, beta2, bc):
+    """step += 1; bc = [1 / (1 - beta1^step), 1 / sqrt(1 - beta2^step)]"""
+    _lib.check(_lib.load().cpcsv_adam_tick(_ptr(step, torch.float32), beta1, beta2, _ptr(bc, torch.float32),
+                                           _stream()), "cpcsv_adam_tick")
+
+
+def adam_multi(tensors, hyper):
+    """Adam step on a list of (p, g, m, v) fp32 tensors (contiguous, same numel each)"""
+    n = len(tensors)
+    if n == 0:
+        return
+    arr = (_lib.AdamTensor * n)()
+    for i, (p, g, m, v) in enumerate(tensors):
+        assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+        assert g.numel() == p.numel() == m.numel() == v.numel()
+        arr[i].p, arr[i].g = _ptr(p, torch.float32).value, _ptr(g, torch.float32).value
+        arr[i].m, arr[i].v = _ptr(m, torch.float32).value, _ptr(v, torch.float32).value
+        arr[i].n = p.numel()
+    h = hyper.to_c()
+    _lib.check(_lib.load().cpcsv_adam_multi(arr, n, C.byref(h), _stream()), "cpcsv_adam_multi")
+
+
+def adam_pack_conv(w, g, m, v, planes, hyper=None):
+    """[Adam step on the conv weight w [Cout, Cin, kh, kw] (g None: no step), then] every plane of
+    ``planes`` = [(kind, dtype, rows_pad, cols_pad, hi, lo-or-None)] rewritten from w"""
+    Cout, Cin, kh, kw = w.shape
+    assert w.is_contiguous() and (g is None or g.is_contiguous())
+    n = len(planes)
+    arr = (_lib.Plane * max(n, 1))()
+    for i, (kind, dtype, rows_pad, cols_pad, hi, lo) in enumerate(planes):
+        arr[i].kind, arr[i].dtype, arr[i].rows_pad, arr[i].cols_pad = kind, dtype, rows_pad, cols_pad
+        arr[i].hi, arr[i].lo = _ptr(hi, TORCH16[dtype]).value, (_ptr(lo, TORCH16[dtype]).value if lo is not None else None)
+    h = hyper.to_c() if g is not None else None
+    _lib.check(_lib.load().cpcsv_adam_pack_conv(
+        _ptr(w, torch.float32), _ptr(g, torch.float32), _ptr(m, torch.float32), _ptr(v, torch.float32), Cout, Cin,
+        kh, kw, C.byref(h) if h is not None else None, arr, n, _stream()), "cpcsv_adam_pack_conv")
+
+
+def adam_pack_fc(w, g, m, v, C_, P, Cp, Kp, fwd16=None, fwd_hi=None, fwd_lo=None, bwd=None, hyper=None):
+    """fc / fc_seg weight w [C*P, K]: [Adam step, then] the NHWC-ordered planes fwd16 fp16 [P*Cp, Kp],
+    fwd_hi / fwd_lo bf16 [P*Cp, Kp], bwd bf16 [Kp, P*Cp]"""
+    rows, K = w.shape
+    assert rows == C_ * P and w.is_contiguous() and (g is None or g.is_contiguous())
+    for t, shape in ((fwd16, (P * Cp, Kp)), (fwd_hi, (P * Cp, Kp)), (fwd_lo, (P * Cp, Kp)), (bwd, (Kp, P * Cp))):
+        assert t is None or (tuple(t.shape) == shape and t.is_contiguous()), (shape, None if t is None else t.shape)
+    h = hyper.to_c() if g is not None else None
+    _lib.check(_lib.load().cpcsv_adam_pack_fc(
+        _ptr(w, torch.float32), _ptr(g, torch.float32), _ptr(m, torch.float32), _ptr(v, torch.float32), C_, K, P,
+        Cp, Kp, C.byref(h) if h is not None else None, _ptr(fwd16, torch.float16), _ptr(fwd_hi, torch.bfloat16),
+        _ptr(fwd_lo, torch.bfloat16), _ptr(bwd, torch.bfloat16), _stream()), "cpcsv_adam_pack_fc")

@@ -1,0 +1,109 @@
+"""``PackedAdam``: the reference's ``optim.Adam(lr, betas=(0.5, 0.999))`` (trainer.py:212-220, stepped
+at trainer.py:345-346 and 416) as hand-written multi-tensor kernels fused with the weight re-layout.
+
+One optimiser step =
+  * ``cpcsv_adam_tick``        step count += 1 and the two bias corrections (device side);
+  * ``cpcsv_adam_pack_conv``   per tensor-core conv weight: Adam update + every persistent 16-bit
+                               operand plane of that weight (forward fp16 / bf16 hi+lo, transposed
+                               data-gradient plane, sub-pixel merged taps) in the same pass;
+  * ``cpcsv_adam_pack_fc``     fc / fc_seg likewise (rows re-ordered to NHWC, transposed plane);
+  * ``cpcsv_adam_multi``       everything else (BatchNorm affine, biases, GRUs, small Linears).
+No pack kernel runs between an optimiser step and the next forward pass, and the planes are current
+after a replayed CUDA graph as well (the step count and the learning rate are device tensors).
+
+Arithmetic and state layout follow ``torch.optim.Adam`` (no weight decay / amsgrad / maximize):
+``state[p] = {"step", "exp_avg", "exp_avg_sq"}``.  Difference: all parameters of one optimiser share
+ONE step counter (``state[p]["step"]`` is the same device tensor for every p), i.e. a parameter that
+had no gradient in some step still advances its bias correction -- on this path every parameter gets
+a gradient in every step.
+"""
+import torch
+
+from . import ops
+
+
+class PackedAdam(torch.optim.Optimizer):
+    maintains_planes = True        # read by the weight cache's optimiser hook (nets.py)
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, cache=None):
+        if weight_decay != 0:
+            raise ValueError("PackedAdam: weight decay is not implemented (the reference uses none)")
+        if not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
+            raise ValueError("PackedAdam: betas %r" % (betas,))
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0))
+        if cache is None:
+            from . import nets
+            cache = nets.weight_cache()
+        self.cache = cache
+        self._dev = {}          # per group index: device-side step / bc / lr
+
+    # ---- device-side scalars ----------------------------------------------------------------
+    def _group_state(self, gi, group, device):
+        st = self._dev.get(gi)
+        if st is None:
+            st = self._dev[gi] = {"step": torch.zeros(1, device=device), "bc": torch.zeros(2, device=device),
+                                  "lr": None, "lr_host": None}
+        lr = group["lr"]
+        if torch.is_tensor(lr):
+            if lr.device != device or lr.dtype != torch.float32:
+                raise ValueError("PackedAdam: a tensor learning rate must be an fp32 tensor on the parameters' device")
+            st["lr"] = lr.reshape(1)
+        elif st["lr"] is None or st["lr_host"] != lr:
+            # a Python-float learning rate: mirrored into a device scalar (not capturable: inside a
+            # CUDA graph use a tensor learning rate, trainer.build_capturable_optimizers)
+            if st["lr"] is None or st["lr_host"] is None:
+                st["lr"] = torch.zeros(1, device=device)
+            st["lr"].fill_(float(lr))
+            st["lr_host"] = lr
+        return st
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            params = [p for p in group["params"] if p.grad is not None]
+            if not params:
+                continue
+            device = params[0].device
+            st = self._group_state(gi, group, device)
+            beta1, beta2 = group["betas"]
+            hyper = ops.AdamHyper(st["lr"], st["bc"], beta1, beta2, group["eps"])
+            ops.adam_tick(st["step"], beta1, beta2, st["bc"])
+            plain, touched = [], []
+            for p in params:
+                if p.grad.is_sparse:
+                    raise RuntimeError("PackedAdam does not support sparse gradients")
+                state = self.state[p]
+                if len(state) == 0:
+                    state["step"] = st["step"]
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                m, v = state["exp_avg"], state["exp_avg_sq"]
+                ents = self.cache.maintained(p) if p.is_contiguous() else []
+                conv = [(k, e) for k, e in ents if e.spec[0] == "conv"]
+                fc = [(k, e) for k, e in ents if e.spec[0] == "fc"]
+                if conv and p.dim() == 4 and len(conv) <= ops.MAX_PLANES:
+                    planes = [(e.spec[1], e.spec[2], e.spec[3], e.spec[4], e.val[0], e.val[1]) for _, e in conv]
+                    ops.adam_pack_conv(p, g, m, v, planes, hyper)
+                    touched += [(e, p) for _, e in conv]
+                elif fc and p.dim() == 2:
+                    geo = {e.spec[2:] for _, e in fc}
+                    assert len(geo) == 1, geo
+                    C_, Cp, Kp = geo.pop()
+                    by = {e.spec[1]: e for _, e in fc}
+                    ops.adam_pack_fc(p, g, m, v, C_, p.shape[0] // C_, Cp, Kp,
+                                     fwd16=by["fwd16"].val[0] if "fwd16" in by else None,
+                                     fwd_hi=by["fwd"].val[0] if "fwd" in by else None,
+                                     fwd_lo=by["fwd"].val[1] if "fwd" in by else None,
+                                     bwd=by["bwd"].val if "bwd" in by else None, hyper=hyper)
+                    touched += [(e, p) for _, e in fc]
+                else:
+                    plain.append((p, g, m, v))
+            ops.adam_multi(plain, hyper)
+            for ent, p in touched:
+                self.cache.refreshed(ent, p)
+        return loss

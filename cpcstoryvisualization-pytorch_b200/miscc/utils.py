@@ -97,6 +97,10 @@ def weights_init(m):
     """N(0, 0.02) for Conv / Linear weights, N(1, 0.02) for BatchNorm scale, zero biases;
     dispatch on the class name like the reference."""
     name = m.__class__.__name__
+    if any(k in name for k in ("Conv", "BatchNorm", "Linear")):
+        # `.data` writes bypass Tensor._version: tell the packed-operand cache (no-op before first use)
+        from cpcsv_b200 import nets as _knets
+        _knets.invalidate_weight_cache()
     if "Conv" in name:
         m.weight.data.normal_(0.0, 0.02)
     elif "BatchNorm" in name:

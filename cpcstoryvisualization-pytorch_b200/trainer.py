@@ -99,16 +99,24 @@ def build_networks(video_len=None):
     return nets
 
 
-def build_optimizers(nets, fused=None):
-    """Adam(betas=(0.5, 0.999)); lr from cfg (reference trainer.py:212-220)."""
+def build_optimizers(nets, fused=None, lr_tensor_device=None):
+    """Adam(betas=(0.5, 0.999)); lr from cfg (reference trainer.py:212-220).  On a GPU (``fused``) this is
+    ``cpcsv_b200.optim.PackedAdam``: the same arithmetic as ``torch.optim.Adam`` in hand-written
+    multi-tensor kernels that also rewrite the 16-bit operand planes of the updated weights.
+    ``fused=False``: stock ``torch.optim.Adam`` (CPU tests of the host logic).  ``lr_tensor_device``: hold the
+    learning rate in a device tensor (CUDA-graph replays see later changes, ``set_lr``)."""
     fused = torch.cuda.is_available() if fused is None else fused
-    kw = dict(betas=(0.5, 0.999))
-    if fused:
-        kw["fused"] = True
     opts = {}
     for k, net in nets.items():
         lr = cfg.TRAIN.GENERATOR_LR if k == "G" else cfg.TRAIN.DISCRIMINATOR_LR
-        opts[k] = optim.Adam([p for p in net.parameters() if p.requires_grad], lr=lr, **kw)
+        params = [p for p in net.parameters() if p.requires_grad]
+        if fused:
+            from cpcsv_b200.optim import PackedAdam
+            if lr_tensor_device is not None:
+                lr = torch.tensor(float(lr), device=lr_tensor_device)
+            opts[k] = PackedAdam(params, lr=lr, betas=(0.5, 0.999))
+        else:
+            opts[k] = optim.Adam(params, lr=lr, betas=(0.5, 0.999))
     return opts
 
 
@@ -323,16 +331,10 @@ LOSS_KEYS = ("se_errD", "im_errD", "st_errD", "se_errG", "im_errG", "st_errG", "
 
 
 def build_capturable_optimizers(nets, device):
-    """``build_optimizers`` for a step that is replayed as a CUDA graph: fused, capturable Adam with
-    the learning rate held in a device tensor, so the halving schedule (reference trainer.py:447-456)
-    acts on later replays (``set_lr``) instead of being frozen into the captured launches."""
-    opts = {}
-    for k, net in nets.items():
-        lr = cfg.TRAIN.GENERATOR_LR if k == "G" else cfg.TRAIN.DISCRIMINATOR_LR
-        opts[k] = optim.Adam([p for p in net.parameters() if p.requires_grad],
-                             lr=torch.tensor(float(lr), device=device), betas=(0.5, 0.999), fused=True,
-                             capturable=True)
-    return opts
+    """``build_optimizers`` for a step that is replayed as a CUDA graph: ``PackedAdam`` (step count on the
+    device) with the learning rate held in a device tensor, so the halving schedule (reference
+    trainer.py:447-456) acts on later replays (``set_lr``) instead of being frozen into the captured launches."""
+    return build_optimizers(nets, fused=True, lr_tensor_device=device)
 
 
 def set_lr(opt, lr):
@@ -460,7 +462,11 @@ class GraphedStep:
     def capture(self, capture_error_mode=None):
         """``capture_error_mode="thread_local"`` when other host threads keep making CUDA calls
         during the capture (DataLoader pin-memory thread, NCCL watchdog)"""
-        knets.invalidate_weight_cache()
+        # everything issued so far has to be complete: planes packed eagerly are read inside the capture
+        # without event waits (an event recorded outside a capture cannot be waited on inside it)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        knets.sync_point(None)
         stream = step_stream(self.device)
         kw = {}
         if capture_error_mode is not None:

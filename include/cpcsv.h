@@ -274,6 +274,53 @@ int cpcsv_spectral_bwd(const float* G, const float* W, const float* u, const flo
                        const float* sigma, int32_t R, int32_t C, float* dW, float* scratch,
                        cpcsv_stream_t stream);
 
+/* ------------------------------------------------------------------ optimiser (Adam)
+ * optim.Adam(lr, betas=(0.5, 0.999)) of reference trainer.py:212-220, stepped at trainer.py:345-346
+ * (discriminators) and trainer.py:416 (generator): fp32 Adam without weight decay, as multi-tensor
+ * kernels FUSED with the re-layout of the updated weights into the 16-bit GEMM operand planes
+ * (what cpcsv_pack_conv_weight / cpcsv_pack_matrix would otherwise redo after every step).
+ * `step` (device float) counts optimiser steps; cpcsv_adam_tick advances it and writes
+ * bc = { 1 / (1 - beta1^t), 1 / sqrt(1 - beta2^t) }; `lr` is a device scalar so a schedule
+ * (trainer.py:447-456) acts on replayed CUDA graphs. */
+typedef struct {
+  const float* lr; /* device scalar */
+  const float* bc; /* device [2], from cpcsv_adam_tick */
+  float beta1, beta2, eps;
+} cpcsv_adam_t;
+
+typedef struct {
+  float* p;
+  const float* g;
+  float* m; /* exp_avg */
+  float* v; /* exp_avg_sq */
+  int64_t n;
+} cpcsv_adam_tensor_t;
+
+/* one packed operand plane (pair) of a conv weight; kinds as cpcsv_pack_conv_weight */
+typedef struct {
+  int32_t kind, dtype, rows_pad, cols_pad;
+  void* hi;
+  void* lo; /* may be NULL */
+} cpcsv_plane_t;
+
+#define CPCSV_MAX_PLANES 6
+
+int cpcsv_adam_tick(float* step, float beta1, float beta2, float* bc, cpcsv_stream_t stream);
+/* plain parameters (BatchNorm affine, biases, GRU / Linear weights of the conditioning path) */
+int cpcsv_adam_multi(const cpcsv_adam_tensor_t* tensors, int32_t count, const cpcsv_adam_t* hyper,
+                     cpcsv_stream_t stream);
+/* conv weight [Cout, Cin, kh, kw] (kh*kw <= 16): Adam step (skipped when g == NULL: pack only) and
+ * every plane of `planes` rewritten from the updated values, padding included */
+int cpcsv_adam_pack_conv(float* p, const float* g, float* m, float* v, int32_t Cout, int32_t Cin,
+                         int32_t kh, int32_t kw, const cpcsv_adam_t* hyper, const cpcsv_plane_t* planes,
+                         int32_t n_planes, cpcsv_stream_t stream);
+/* fc / fc_seg weight [C*P, K] (model.py:260-263,285-288; P = 16 positions of the 4x4 map):
+ * Adam step (g == NULL: pack only) + the NHWC-ordered planes: fwd16 fp16 [P*Cp, Kp], fwd_hi/lo
+ * bf16 [P*Cp, Kp], bwd bf16 [Kp, P*Cp] (row j = c*P + pos -> j' = pos*Cp + c); any may be NULL */
+int cpcsv_adam_pack_fc(float* p, const float* g, float* m, float* v, int32_t C, int32_t K, int32_t P,
+                       int32_t Cp, int32_t Kp, const cpcsv_adam_t* hyper, void* fwd16, void* fwd_hi,
+                       void* fwd_lo, void* bwd, cpcsv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

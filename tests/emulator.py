@@ -19,7 +19,7 @@ def install(monkeypatch):
     import cpcsv_b200.ops as ops
     for name, fn in list(globals().items()):
         if callable(fn) and not name.startswith("_") and hasattr(ops, name) and name not in (
-                "View", "GemmJob", "install"):
+                "View", "GemmJob", "install", "AdamHyper"):
             monkeypatch.setattr(ops, name, fn)
     monkeypatch.setattr(ops, "_ptr", lambda t, dtype=None: None)
 
@@ -516,3 +516,52 @@ def spectral_bwd(g2d, w2d, u, v, sigma, dw2d, scratch):
     s = float(sigma)
     gw = float((g2d * w2d).sum())
     dw2d.copy_((g2d - (gw / s) * torch.outer(u, v)) / s)
+
+
+# ------------------------------------------------------------------------------ optimiser
+def adam_tick(step, beta1, beta2, bc):
+    step += 1
+    t = float(step)
+    bc[0] = 1.0 / (1.0 - beta1 ** t)
+    bc[1] = 1.0 / (1.0 - beta2 ** t) ** 0.5
+
+
+def _adam(p, g, m, v, hyper):
+    m.add_((g - m) * (1.0 - hyper.beta1))
+    v.mul_(hyper.beta2).add_(g * g * (1.0 - hyper.beta2))
+    step_size = float(hyper.lr) * float(hyper.bc[0])
+    denom = v.sqrt() * float(hyper.bc[1]) + hyper.eps
+    p.sub_(step_size * (m / denom))
+
+
+def adam_multi(tensors, hyper):
+    with torch.no_grad():
+        for p, g, m, v in tensors:
+            _adam(p, g, m, v, hyper)
+
+
+def adam_pack_conv(w, g, m, v, planes, hyper=None):
+    with torch.no_grad():
+        if g is not None:
+            _adam(w, g, m, v, hyper)
+        for kind, dtype, rows_pad, cols_pad, hi, lo in planes:
+            pack_conv_weight(w.detach(), kind, rows_pad, cols_pad, hi, lo, dtype)
+
+
+def adam_pack_fc(w, g, m, v, C_, P, Cp, Kp, fwd16=None, fwd_hi=None, fwd_lo=None, bwd=None, hyper=None):
+    with torch.no_grad():
+        if g is not None:
+            _adam(w, g, m, v, hyper)
+        K = w.shape[1]
+        full = torch.zeros(P, Cp, Kp)
+        full[:, :C_, :K] = w.detach().reshape(C_, P, K).permute(1, 0, 2)        # [pos, c, k]
+        full = full.reshape(P * Cp, Kp)
+        if fwd16 is not None:
+            fwd16.copy_(full.to(torch.float16))
+        if fwd_hi is not None:
+            h, l = _split16(full, 1)
+            fwd_hi.copy_(h)
+            if fwd_lo is not None:
+                fwd_lo.copy_(l)
+        if bwd is not None:
+            bwd.copy_(full.t().to(torch.bfloat16))

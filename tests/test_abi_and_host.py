@@ -93,7 +93,7 @@ def test_weight_cache_entries_die_with_their_parameter():
     ent = cache.d[(id(b), "k")]
     c = torch.nn.Parameter(torch.zeros(4))
     import weakref
-    cache.d[(id(b), "k")] = (ent[0], ent[1], ent[2], ent[3], weakref.ref(c))
+    cache.d[(id(b), "k")] = engine.CacheEntry(ent.tag, ent.val, ent.stream, ent.event, weakref.ref(c))
     n = len(built)
     get(b)
     assert len(built) == n + 1

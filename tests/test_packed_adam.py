@@ -1,0 +1,156 @@
+"""optim.PackedAdam (hand-written multi-tensor Adam fused with the weight re-layout) against
+``torch.optim.Adam`` -- the optimiser the reference builds at trainer.py:212-220 -- and its persistent
+operand planes against a fresh re-layout of the updated weights.
+
+Every case runs with the CPU emulator of the kernel contract (host logic: grouping of parameters,
+plane bookkeeping in the weight cache) and, marked ``gpu``, through libcpcsv.so.
+"""
+import pytest
+import torch
+
+import emulator
+from cpcsv_b200 import engine, nets, ops
+from cpcsv_b200.optim import PackedAdam
+
+
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def dev(request, monkeypatch):
+    if request.param == "emu":
+        emulator.install(monkeypatch)
+        return torch.device("cpu")
+    return torch.device("cuda")
+
+
+def _params(dev, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    shapes = {"up": (20, 72, 3, 3), "s1": (24, 40, 3, 3), "s2": (12, 8, 4, 4), "fc": (16 * 10, 37),
+              "bn_w": (33,), "gru": (45, 17), "bias": (1,), "big": (9000,)}
+    return {k: torch.nn.Parameter((torch.randn(*s, generator=g) * 0.05).to(dev)) for k, s in shapes.items()}
+
+
+class _FakeG:
+    def __init__(self):
+        self._cpcsv_maps = {}
+
+
+def _register_planes(cache, P):
+    """what the first forward / backward passes of a step would ask the cache for"""
+    rup = engine.rup
+    got = {}
+    for name, geom in (("up", "up"), ("s1", "s1"), ("s2", "s2")):
+        w = P[name]
+        Co_pad, Ci_pad = rup(w.shape[0], 64), rup(w.shape[1], 64)
+        _k, fkind, bkind, _nt, _uk = engine.CONV_GEOM[geom]
+        got[name] = [engine.pack_conv(cache, w, geom, fkind, Co_pad, Ci_pad, 2, ops.BF16),
+                     engine.pack_conv(cache, w, geom, bkind, Ci_pad, Co_pad, 1, ops.BF16)]
+        if geom != "s2":
+            got[name].append(engine.pack_conv(cache, w, geom, fkind, Co_pad, Ci_pad, 1, ops.FP16))
+
+    class Lin:
+        weight = P["fc"]
+    G = _FakeG()
+    Kp = rup(P["fc"].shape[1], 64)
+    got["fc"] = [nets.pack_fc_fwd(cache, G, Lin, 10, Kp, 1, ops.FP16), nets.pack_fc_fwd(cache, G, Lin, 10, Kp, 2, ops.BF16),
+                 nets.pack_fc_bwd(cache, G, Lin, 10, Kp)]
+    return got
+
+
+def _flat(planes):
+    out = []
+    for v in planes:
+        for t in (v if isinstance(v, (list, tuple)) else [v]):
+            if t is not None:
+                out.append(t.detach().float().cpu().clone())
+    return out
+
+
+def test_packed_adam_matches_torch_adam_and_keeps_planes_current(dev):
+    P = _params(dev)
+    Q = {k: torch.nn.Parameter(v.detach().clone()) for k, v in P.items()}
+    cache = engine.WeightCache()
+    planes = _register_planes(cache, P)
+    lr = torch.tensor(3e-3, device=dev)
+    opt = PackedAdam(list(P.values()), lr=lr, betas=(0.5, 0.999), cache=cache)
+    ref = torch.optim.Adam(list(Q.values()), lr=3e-3, betas=(0.5, 0.999))
+    gen = torch.Generator().manual_seed(11)
+    for step in range(3):
+        for k in P:
+            g = torch.randn(P[k].shape, generator=gen) * (0.3 if k != "bias" else 1e-3)
+            P[k].grad = g.to(dev)
+            Q[k].grad = g.to(dev).clone()
+        if step == 2:
+            lr.fill_(1e-3)                      # a schedule acting through the device tensor
+            ref.param_groups[0]["lr"] = 1e-3
+        opt.step()
+        ref.step()
+        for k in P:
+            a, b = P[k].detach().double().cpu(), Q[k].detach().double().cpu()
+            assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(b.abs().max())), (k, step)
+        # state layout of torch.optim.Adam
+        assert set(opt.state[P["up"]]) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(opt.state[P["up"]]["step"]) == step + 1
+        for k in ("up", "fc", "gru"):
+            a, b = opt.state[P[k]]["exp_avg_sq"].double().cpu(), ref.state[Q[k]]["exp_avg_sq"].double().cpu()
+            assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())
+    # the persistent planes hold the UPDATED weights: identical to a fresh re-layout of them
+    kept = {k: _flat(v) for k, v in planes.items()}
+    again = _register_planes(cache, P)
+    for k in planes:      # cache hits: the very same buffers, nothing re-packed
+        for a, b in zip(planes[k], again[k]):
+            ta = a[0] if isinstance(a, (list, tuple)) else a
+            tb = b[0] if isinstance(b, (list, tuple)) else b
+            assert ta.data_ptr() == tb.data_ptr()
+    fresh = _register_planes(engine.WeightCache(), P)
+    for k in planes:
+        for a, b in zip(kept[k], _flat(fresh[k])):
+            assert torch.equal(a, b), k
+
+
+def test_foreign_optimizer_and_invalidate_repack_in_place(dev):
+    """another optimiser (the global post-step hook) or invalidate_weight_cache() marks the persistent
+    planes stale; the next use re-packs them into the same buffers"""
+    P = _params(dev, seed=3)
+    cache = nets.weight_cache()      # the hook acts on the global cache
+    planes = _register_planes(cache, P)
+    before = _flat(planes["s1"])
+    opt = torch.optim.Adam(list(P.values()), lr=1e-2)
+    for v in P.values():
+        v.grad = torch.ones_like(v)
+    opt.step()
+    again = _register_planes(cache, P)
+    assert again["s1"][0][0].data_ptr() == planes["s1"][0][0].data_ptr()
+    after = _flat(again["s1"])
+    assert not torch.equal(before[0], after[0])
+    fresh = _flat(_register_planes(engine.WeightCache(), P)["s1"])
+    for a, b in zip(after, fresh):
+        assert torch.equal(a, b)
+    with torch.no_grad():
+        P["s1"].data.add_(0.25)         # bypasses Tensor._version
+    nets.invalidate_weight_cache()
+    third = _flat(_register_planes(cache, P)["s1"])
+    fresh = _flat(_register_planes(engine.WeightCache(), P)["s1"])
+    for a, b in zip(third, fresh):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_adam_pack_kernels_match_the_pack_kernels_gpu():
+    """the fused kernels' planes == cpcsv_pack_conv_weight / cpcsv_pack_matrix of the same weights"""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    for (Co, Ci, k), kinds in (((72, 136, 3), (0, 1, 2, 3)), ((124, 3, 4), (0, 1)), ((248, 124, 4), (0, 1))):
+        w = (torch.randn(Co, Ci, k, k, generator=g) * 0.05).to(dev)
+        for kind in kinds:
+            tr = kind in (1, 3)
+            rp, cp = (engine.rup(Ci, 64), engine.rup(Co, 64)) if tr else (engine.rup(Co, 64), engine.rup(Ci, 64))
+            ntap = 16 if kind >= 2 else k * k
+            for dtype, two in ((ops.BF16, True), (ops.FP16, False)):
+                t16 = ops.TORCH16[dtype]
+                a_hi = torch.full((ntap * rp, cp), 7.0, device=dev, dtype=t16)
+                a_lo = torch.full((ntap * rp, cp), 7.0, device=dev, dtype=t16) if two else None
+                b_hi, b_lo = torch.empty_like(a_hi), (torch.empty_like(a_hi) if two else None)
+                ops.adam_pack_conv(w, None, None, None, [(kind, dtype, rp, cp, a_hi, a_lo)])
+                ops.pack_conv_weight(w, kind, rp, cp, b_hi, b_lo, dtype)
+                assert torch.equal(a_hi, b_hi), (Co, Ci, k, kind, dtype)
+                if two:
+                    assert torch.equal(a_lo, b_lo)

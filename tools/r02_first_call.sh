@@ -13,6 +13,7 @@ run bench          90  python bench.py --steps 20 --warmup 5
 run bench_overlap  90  python bench.py --steps 20 --warmup 5 --overlap-io --no-cpu-baseline
 run stock_cuda     240 python bench.py --impl stock-cuda --steps 3 --warmup 2
 run smoke          120 python -c "import __graft_entry__ as g; g.smoke()"
+run timeline       120 python tools/timeline_graph.py gpurun_out/r02_timeline_a.csv
 # pair-mode dead-lock: bisect the mix (each run exits 3 on a hang; the watchdog prints the configuration)
 for mix in pairs pairs+single pairs+wgrad pairs+small all; do
   CPCSV_PAIR=1 run "pair_${mix//+/_}" 90 python tools/repro_pair_hang.py --mix "$mix" --replays 300 --heat 10
