@@ -40,8 +40,8 @@ MAX_PLANES = 6
 
 
 class AdamHyper(C.Structure):
-    _fields_ = [("lr", C.c_void_p), ("bc", C.c_void_p), ("beta1", C.c_float), ("beta2", C.c_float),
-                ("eps", C.c_float)]
+    _fields_ = [("lr", C.c_void_p), ("bc", C.c_void_p), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double)]
 
 
 class AdamTensor(C.Structure):
@@ -95,7 +95,7 @@ SIGNATURES = {
     "cpcsv_affine_sigmoid_bwd": [_p, _p, _p, _p, _p, _i64, _p],
     "cpcsv_spectral_sigma": [_p, _i32, _i32, _p, _p, _i32, _f32, _p, _p, _p, _p],
     "cpcsv_spectral_bwd": [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p],
-    "cpcsv_adam_tick": [_p, _f32, _f32, _p, _p],
+    "cpcsv_adam_tick": [_p, C.c_double, C.c_double, _p, _p],
     "cpcsv_adam_multi": [C.POINTER(AdamTensor), _i32, C.POINTER(AdamHyper), _p],
     "cpcsv_adam_pack_conv": [_p, _p, _p, _p, _i32, _i32, _i32, _i32, C.POINTER(AdamHyper), C.POINTER(Plane),
                              _i32, _p],

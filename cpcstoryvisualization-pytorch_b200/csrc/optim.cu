@@ -20,13 +20,13 @@ namespace {
 struct Hyper {
   const float* lr;   // device scalar
   const float* bc;   // device [2]: 1 / (1 - beta1^t), 1 / sqrt(1 - beta2^t)
-  float beta1, beta2, eps;
+  float beta1, beta2, omb1, omb2, eps;   // omb = 1 - beta, rounded from the double difference
 };
 
 __device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, float step_size,
                                              float inv_sqrt_bc2, const Hyper& h) {
-  m = fmaf(1.f - h.beta1, g - m, m);
-  v = h.beta2 * v + (1.f - h.beta2) * g * g;
+  m = fmaf(h.omb1, g - m, m);
+  v = h.beta2 * v + h.omb2 * g * g;
   const float denom = sqrtf(v) * inv_sqrt_bc2 + h.eps;
   return p - step_size * (m / denom);
 }
@@ -45,11 +45,11 @@ __device__ __forceinline__ void split16(float v, int dtype, uint16_t& hi, uint16
   }
 }
 
-__global__ void adam_tick_kernel(float* step, float beta1, float beta2, float* bc) {
+__global__ void adam_tick_kernel(float* step, double beta1, double beta2, float* bc) {
   const float t = *step + 1.f;
   *step = t;
-  bc[0] = 1.f / (1.f - powf(beta1, t));
-  bc[1] = 1.f / sqrtf(1.f - powf(beta2, t));
+  bc[0] = static_cast<float>(1.0 / (1.0 - pow(beta1, static_cast<double>(t))));
+  bc[1] = static_cast<float>(1.0 / sqrt(1.0 - pow(beta2, static_cast<double>(t))));
 }
 
 // ------------------------------------------------------------------------- generic multi-tensor
@@ -120,43 +120,73 @@ __device__ __forceinline__ void merged_range(int a, int i, int& lo, int& hi) {
   else        { lo = i == 0 ? 0 : 2; hi = i == 0 ? 1 : 2; }
 }
 
-constexpr int kTileCo = 8, kTileCi = 16;
+constexpr int kTile = 16;   // (co) x (ci) tile of a block
 
-// A block owns an 8 (co) x 16 (ci) tile of w[Cout][Cin][T] for all T <= 16 taps: the Adam update
-// (when g != nullptr) runs on contiguous runs of 16*T floats per co; the updated tile is staged in
-// 8 KB of shared memory and written out once per requested plane, 16 bytes per thread along the
-// plane's contiguous dimension (ci for [tap][co][ci], co for the transposed [tap][ci][co]).
+// A block owns a 16 (co) x 16 (ci) tile of w[Cout][Cin][T] for all T taps (T = 9 or 16, a template
+// parameter so the index arithmetic is constant divisions).  Every thread first loads its T elements of
+// p / g / m / v (contiguous runs of 16*T floats per co: coalesced, 4*T independent loads in flight),
+// updates them, writes p / m / v back and stages the new weights in shared memory; the tile is then
+// written out once per requested plane, 16 bytes per thread and 32-byte runs along the plane's
+// contiguous dimension (ci for [tap][co][ci], co for the transposed [tap][ci][co]).
+template <int T>
 __global__ void __launch_bounds__(256)
 adam_pack_conv_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                      float* __restrict__ v, int Cout, int Cin, int T, const Hyper h,
+                      float* __restrict__ v, int Cout, int Cin, const Hyper h,
                       const __grid_constant__ PlaneSet S) {
-  __shared__ float s[kTileCo][kTileCi * 16 + 1];
-  const int co0 = blockIdx.y * kTileCo, ci0 = blockIdx.x * kTileCi;
-  const int run = kTileCi * T;
-  float step_size = 0.f, isb2 = 0.f;
+  constexpr int kRun = kTile * T;
+  __shared__ float s[kTile][kRun + 1];
+  const int co0 = blockIdx.y * kTile, ci0 = blockIdx.x * kTile;
   if (g) {
-    step_size = __ldg(h.lr) * __ldg(h.bc);
-    isb2 = __ldg(h.bc + 1);
-  }
-  for (int i = threadIdx.x; i < kTileCo * run; i += 256) {
-    const int r = i / run, j = i - r * run;
-    const int co = co0 + r, ci = ci0 + j / T;
-    float val = 0.f;
-    if (co < Cout && ci < Cin) {
-      const int64_t o = (static_cast<int64_t>(co) * Cin + ci0) * T + j;
-      val = p[o];
-      if (g) {
-        float mm = m[o], vv = v[o];
-        val = adam_update(val, g[o], mm, vv, step_size, isb2, h);
-        p[o] = val;
-        m[o] = mm;
-        v[o] = vv;
+    const float step_size = __ldg(h.lr) * __ldg(h.bc);
+    const float isb2 = __ldg(h.bc + 1);
+    constexpr int kU = 8;   // elements per thread in flight (4 arrays each)
+#pragma unroll
+    for (int u0 = 0; u0 < T; u0 += kU) {
+      float pv[kU], gv[kU], mv[kU], vv[kU];
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        const int u = u0 + k;
+        if (u < T) {
+          const int i = threadIdx.x + 256 * u;
+          const int r = i / kRun, j = i - r * kRun;
+          const int co = co0 + r, ci = ci0 + j / T;
+          const bool ok = co < Cout && ci < Cin;
+          const int64_t o = (static_cast<int64_t>(co) * Cin + ci0) * T + j;
+          pv[k] = ok ? p[o] : 0.f;
+          gv[k] = ok ? g[o] : 0.f;
+          mv[k] = ok ? m[o] : 0.f;
+          vv[k] = ok ? v[o] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        const int u = u0 + k;
+        if (u < T) {
+          const int i = threadIdx.x + 256 * u;
+          const int r = i / kRun, j = i - r * kRun;
+          const int co = co0 + r, ci = ci0 + j / T;
+          if (co < Cout && ci < Cin) {
+            const int64_t o = (static_cast<int64_t>(co) * Cin + ci0) * T + j;
+            pv[k] = adam_update(pv[k], gv[k], mv[k], vv[k], step_size, isb2, h);
+            p[o] = pv[k];
+            m[o] = mv[k];
+            v[o] = vv[k];
+          }
+          s[r][j] = pv[k];
+        }
       }
     }
-    s[r][j] = val;
+  } else {
+#pragma unroll
+    for (int u = 0; u < T; ++u) {
+      const int i = threadIdx.x + 256 * u;
+      const int r = i / kRun, j = i - r * kRun;
+      const int co = co0 + r, ci = ci0 + j / T;
+      s[r][j] = (co < Cout && ci < Cin) ? p[(static_cast<int64_t>(co) * Cin + ci0) * T + j] : 0.f;
+    }
   }
   __syncthreads();
-  constexpr int kVec = kTileCo * kTileCi / 8;   // 16-byte output vectors per tap
+  constexpr int kVec = kTile * kTile / 8;   // 16-byte output vectors per tap
   for (int q = 0; q < S.count; ++q) {
     const cpcsv_plane_t& P = S.pl[q];
     const int kind = P.kind, dtype = P.dtype;
@@ -166,9 +196,11 @@ adam_pack_conv_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     uint16_t* __restrict__ lo = static_cast<uint16_t*>(P.lo);
     for (int i = threadIdx.x; i < ntap * kVec; i += 256) {
       const int tap = i / kVec, vi = i % kVec;
-      int r0, c0, dr, dc;
-      if (!transposed) { c0 = (vi % (kTileCi / 8)) * 8; r0 = vi / (kTileCi / 8); dr = 0; dc = 1; }
-      else             { r0 = (vi % (kTileCo / 8)) * 8; c0 = vi / (kTileCo / 8); dr = 1; dc = 0; }
+      // two consecutive threads write the two 16-byte halves of one 32-byte run
+      const int minor = (vi & 1) * 8, major = vi >> 1;
+      const int r0 = transposed ? minor : major;     // co inside the tile
+      const int c0 = transposed ? major : minor;     // ci inside the tile
+      const int dr = transposed ? 1 : 0, dc = transposed ? 0 : 1;
       const int row = transposed ? ci0 + c0 : co0 + r0;
       const int col = transposed ? co0 + r0 : ci0 + c0;
       if (row >= P.rows_pad || col >= P.cols_pad) continue;
@@ -188,7 +220,7 @@ adam_pack_conv_kernel(float* __restrict__ p, const float* __restrict__ g, float*
         } else {
           val = 0.f;
           for (int ky = y0; ky <= y1; ++ky)
-            for (int kx = x0; kx <= x1; ++kx) val += s[r][c * 9 + ky * 3 + kx];
+            for (int kx = x0; kx <= x1; ++kx) val += s[r][c * T + ky * 3 + kx];
         }
         split16(val, dtype, hv[e], lv[e]);
       }
@@ -285,9 +317,11 @@ inline Hyper make_hyper(const cpcsv_adam_t* a) {
   Hyper h;
   h.lr = a->lr;
   h.bc = a->bc;
-  h.beta1 = a->beta1;
-  h.beta2 = a->beta2;
-  h.eps = a->eps;
+  h.beta1 = static_cast<float>(a->beta1);
+  h.beta2 = static_cast<float>(a->beta2);
+  h.omb1 = static_cast<float>(1.0 - a->beta1);
+  h.omb2 = static_cast<float>(1.0 - a->beta2);
+  h.eps = static_cast<float>(a->eps);
   return h;
 }
 
@@ -297,7 +331,7 @@ inline Hyper make_hyper(const cpcsv_adam_t* a) {
 using namespace cpcsv;
 #define STREAM(s) static_cast<cudaStream_t>(s)
 
-extern "C" int cpcsv_adam_tick(float* step, float beta1, float beta2, float* bc, cpcsv_stream_t stream) {
+extern "C" int cpcsv_adam_tick(float* step, double beta1, double beta2, float* bc, cpcsv_stream_t stream) {
   CPCSV_REQUIRE(step && bc, "adam_tick: args");
   adam_tick_kernel<<<1, 1, 0, STREAM(stream)>>>(step, beta1, beta2, bc);
   return launched("adam_tick");
@@ -331,7 +365,7 @@ extern "C" int cpcsv_adam_multi(const cpcsv_adam_tensor_t* tensors, int32_t coun
 extern "C" int cpcsv_adam_pack_conv(float* p, const float* g, float* m, float* v, int32_t Cout, int32_t Cin,
                                     int32_t kh, int32_t kw, const cpcsv_adam_t* hyper,
                                     const cpcsv_plane_t* planes, int32_t n_planes, cpcsv_stream_t stream) {
-  CPCSV_REQUIRE(p && Cout > 0 && Cin > 0 && kh * kw >= 1 && kh * kw <= 16, "adam_pack_conv: args");
+  CPCSV_REQUIRE(p && Cout > 0 && Cin > 0 && (kh * kw == 9 || kh * kw == 16), "adam_pack_conv: 3x3 / 4x4 kernels only");
   CPCSV_REQUIRE(!g || (m && v && hyper && hyper->lr && hyper->bc), "adam_pack_conv: optimiser state missing");
   CPCSV_REQUIRE(n_planes >= 0 && n_planes <= CPCSV_MAX_PLANES && (n_planes == 0 || planes),
                 "adam_pack_conv: %d planes", n_planes);
@@ -354,8 +388,9 @@ extern "C" int cpcsv_adam_pack_conv(float* p, const float* g, float* m, float* v
   Hyper h = {};
   if (g) h = make_hyper(hyper);
   // tiles cover the PADDED index space so the zero padding of every plane is written too
-  dim3 grid(static_cast<unsigned>(ceil_div(ci_ext, kTileCi)), static_cast<unsigned>(ceil_div(co_ext, kTileCo)));
-  adam_pack_conv_kernel<<<grid, 256, 0, STREAM(stream)>>>(p, g, m, v, Cout, Cin, kh * kw, h, S);
+  dim3 grid(static_cast<unsigned>(ceil_div(ci_ext, kTile)), static_cast<unsigned>(ceil_div(co_ext, kTile)));
+  if (kh * kw == 9) adam_pack_conv_kernel<9><<<grid, 256, 0, STREAM(stream)>>>(p, g, m, v, Cout, Cin, h, S);
+  else adam_pack_conv_kernel<16><<<grid, 256, 0, STREAM(stream)>>>(p, g, m, v, Cout, Cin, h, S);
   return launched("adam_pack_conv");
 }
 

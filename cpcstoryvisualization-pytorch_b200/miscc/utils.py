@@ -48,17 +48,22 @@ def get_multi_acc(predict, real):
 
 
 def compute_discriminator_loss(netD, real_imgs, fake_imgs, real_labels, fake_labels, real_catelabels,
-                               conditions, gpus):
+                               conditions, gpus, real_features=None):
     """real / wrong / fake conditional BCE terms (+ character classification on the real
-    features).  Returns (errD, errD_real, errD_wrong, errD_fake, acc, consistency)."""
+    features).  Returns (errD, errD_real, errD_wrong, errD_fake, acc, consistency).
+    ``real_features`` (extension): ``netD(real_imgs)`` already computed by the caller -- the real pass
+    does not depend on the generator, so the trainer issues it before the fakes exist."""
     if conditions is None:
         raise NotImplementedError("unconditional discriminators are unused by CP-CSV")
     if netD.get_uncond_logits is not None or netD.seq_consisten_model:
         raise NotImplementedError("uncond logits / sequence-consistency critic are disabled in cfg/final.yml")
     batch_size = real_imgs.size(0)
     cond = conditions.detach()
-    real_features, fake_features = _parallel(lambda: _call(netD, real_imgs),
-                                             lambda: _call(netD, fake_imgs.detach()))
+    if real_features is None:
+        real_features, fake_features = _parallel(lambda: _call(netD, real_imgs),
+                                                 lambda: _call(netD, fake_imgs.detach()))
+    else:
+        fake_features = _call(netD, fake_imgs.detach())
     head = netD.get_cond_logits
     errD_real, errD_wrong, errD_fake = _parallel(
         lambda: F.binary_cross_entropy(_call(head, real_features, cond), real_labels),

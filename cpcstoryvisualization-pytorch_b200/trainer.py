@@ -157,6 +157,7 @@ D_NETS = ("D_se", "D_im", "D_st")
 CONCURRENT_D = True     # run the three discriminators on parallel CUDA streams
 CONCURRENT_G = True     # run sample_videos / sample_images of one phase on two streams
 EARLY_G = True          # issue the generator-update forward alongside the discriminator update
+EARLY_D_REAL = True     # issue the discriminators' real-image encoder passes before the fakes exist
 step_stream = streams.step_stream
 Detached = streams.Detached
 
@@ -187,9 +188,18 @@ def stage_discriminators(nets, x, labels, early_generator=False, opts=None):
     gpus = None
     out = {}
     start = None
-    if early_generator and torch.cuda.is_available():
+    if (early_generator or EARLY_D_REAL) and torch.cuda.is_available():
         start = torch.cuda.Event()
         start.record()
+    # The real-image encoder passes (reference miscc/utils.py:58: netD(real_imgs)) depend on the
+    # discriminators' weights and the data only: they are issued first, on detached streams, and fill the
+    # tensor cores while the generator's conditioning path (GRUs, small Linears: latency-bound, no GEMM)
+    # runs.  Module state (BatchNorm running statistics, spectral-norm vectors) is still updated real
+    # pass first, fake pass second, as in the reference.
+    real_pass = None
+    if EARLY_D_REAL:
+        reals = {"D_se": x["se_real"], "D_im": x["im_real"], "D_st": x["st_real"]}
+        real_pass = Detached([lambda k=k: nets[k](reals[k]) for k in D_NETS], after=start)
     # weight re-layout for this stage's discriminator passes and for the next stage's generator
     # passes runs on a side stream, overlapped with the no-grad generator forward below
     prefetch = knets.prefetch_weights([netG, netD_se, netD_im, netD_st], no_grad_forward=True)
@@ -214,9 +224,12 @@ def stage_discriminators(nets, x, labels, early_generator=False, opts=None):
         nets[k].zero_grad(set_to_none=True)
     # the three discriminators are independent networks made of many small kernels at this
     # batch size: run them on three concurrent streams (fork / join around the block)
+    real_feats = dict(zip(D_NETS, real_pass.join())) if real_pass is not None else {}
+
     def d_update(key, real, fake, ones, zeros, cate, cond):
         netD = nets[key]
-        err = compute_discriminator_loss(netD, real, fake, ones, zeros, cate, cond, gpus)[0]
+        err = compute_discriminator_loss(netD, real, fake, ones, zeros, cate, cond, gpus,
+                                         real_features=real_feats.get(key))[0]
         err.backward()
         if opts is not None:
             opts[key].step()

@@ -285,7 +285,7 @@ int cpcsv_spectral_bwd(const float* G, const float* W, const float* u, const flo
 typedef struct {
   const float* lr; /* device scalar */
   const float* bc; /* device [2], from cpcsv_adam_tick */
-  float beta1, beta2, eps;
+  double beta1, beta2, eps; /* doubles: 1 - beta2 is formed in double, as torch.optim.Adam does */
 } cpcsv_adam_t;
 
 typedef struct {
@@ -305,7 +305,7 @@ typedef struct {
 
 #define CPCSV_MAX_PLANES 6
 
-int cpcsv_adam_tick(float* step, float beta1, float beta2, float* bc, cpcsv_stream_t stream);
+int cpcsv_adam_tick(float* step, double beta1, double beta2, float* bc, cpcsv_stream_t stream);
 /* plain parameters (BatchNorm affine, biases, GRU / Linear weights of the conditioning path) */
 int cpcsv_adam_multi(const cpcsv_adam_tensor_t* tensors, int32_t count, const cpcsv_adam_t* hyper,
                      cpcsv_stream_t stream);
