@@ -30,7 +30,7 @@ class Gemm(C.Structure):
         ("n_tiles", C.c_int32), ("splits", C.c_int32), ("accumulate", C.c_int32), ("cta_pair", C.c_int32),
         ("out_stride_n", C.c_int64), ("out_stride_h", C.c_int64), ("out_stride_w", C.c_int64),
         ("ldc", C.c_int64),
-        ("alpha", C.c_void_p), ("out", C.c_void_p),
+        ("alpha", C.c_void_p), ("out", C.c_void_p), ("stats", C.c_void_p), ("stats_ld", C.c_int64),
         ("a", View5 * 2), ("b", View5 * 2),
         ("taps", Tap * MAX_TAPS),
     ]
@@ -64,10 +64,8 @@ SIGNATURES = {
     "cpcsv_bn_bwd_reduce": [_p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _i32, _p, _i64, _p, _p],
     "cpcsv_bn_bwd_apply": [_p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _i64,
                            _p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p],
-    "cpcsv_bn_fwd_fused": [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _i32, _f32, _f32, _i32, _p, _i64, _p, _i64,
-                           _p, _p, _i64, _i32, _p, _p, _p],
-    "cpcsv_bn_bwd_fused": [_p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p, _p,
-                           _i64, _p, _i64, _p, _p, _p],
+    "cpcsv_bn_norm_act_pack": [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _p, _i32, _f32, _f32, _p, _i32, _p, _i64,
+                               _p, _i64, _p, _p, _i64, _i32, _p],
     "cpcsv_pack_nchw": [_p, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _p, _i32, _i64, _p, _p,
                         _i32, _i32, _p],
     "cpcsv_im2col_small": [_p, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p,

@@ -15,10 +15,10 @@ from . import conv, ops
 from .ops import ACT_NONE, ACT_RELU, ACT_LRELU, BF16  # noqa: F401
 
 
-# rows * C up to which BatchNorm runs as ONE cooperative launch (bn_fwd_fused / bn_bwd_fused).  0 = off:
-# once the step's branches really overlap (profiles/r01_schedule_notes.md) the 3-4 launch path is as
-# fast (23.1 vs 23.3 ms / step) and has no grid-wide spin waits next to the persistent GEMM blocks.
-FUSED_BN_MAX_ELEMS = 0
+# BatchNorm batch statistics come out of the producing GEMM's epilogue (cpcsv_gemm_t.stats) whenever that
+# GEMM runs without split-K; otherwise from one statistics pass.  Either way the per-channel constants are
+# derived inside the apply kernel (cpcsv_bn_norm_act_pack): at most 2 launches between consecutive GEMMs.
+EPILOGUE_STATS = True
 
 
 def rup(x, m):
@@ -28,12 +28,14 @@ def rup(x, m):
 class T4:
     """NHWC tensor record: fp32 values and/or 16-bit operand planes, plus gradient slots."""
 
-    __slots__ = ("N", "H", "W", "C", "f32", "hi", "lo", "grad", "grad16", "needs_grad")
+    __slots__ = ("N", "H", "W", "C", "f32", "hi", "lo", "grad", "grad16", "needs_grad", "stats", "stats_done")
 
     def __init__(self, N, H, W, C):
         self.N, self.H, self.W, self.C = N, H, W, C
         self.f32 = self.hi = self.lo = self.grad = self.grad16 = None
         self.needs_grad = False
+        self.stats = None           # zeroed fp64 [2, C]: per-channel sum / sum of squares of f32
+        self.stats_done = False     # filled by the producing GEMM's epilogue
 
     @property
     def rows(self):
@@ -282,12 +284,22 @@ def prefetch_conv_nograd(cache, w, geom):
     pack_conv(cache, w, geom, CONV_GEOM[geom][1], Co_pad, Ci_pad, 1, ops.FP16)
 
 
+def attach_stats(tape, job, out, wanted):
+    """BatchNorm batch statistics of a GEMM's output from its epilogue (no split-K, training mode)"""
+    if wanted and tape.training:
+        out.stats = tape.stat_slot(out.C, out.f32.device)
+        if EPILOGUE_STATS and job.mode == 0 and job.splits == 1 and not job.accumulate and job.block_n % 32 == 0:
+            job.stats = out.stats
+            out.stats_done = True
+
+
 class ConvNode:
     """3x3 s1 / nearest-x2+3x3 / 4x4 s2 convolution, optionally spectrally normalised
     (weight = weight_orig / sigma applied as the epilogue scalar alpha)."""
 
-    def __init__(self, tape, kind, x, weight, name, sn=None, alpha=None):
+    def __init__(self, tape, kind, x, weight, name, sn=None, alpha=None, bn_stats=False):
         self.tape, self.kind, self.x, self.w, self.name, self.sn = tape, kind, x, weight, name, sn
+        self.bn_stats = bn_stats    # a batch-statistics BatchNorm consumes the output
         Co, Ci = weight.shape[0], weight.shape[1]
         self.Co, self.Ci = Co, Ci
         self.Co_pad, self.Ci_pad = rup(Co, 64), x.C
@@ -318,6 +330,7 @@ class ConvNode:
             job = conv.upconv_fwd(xp, wp, out.f32, dtype=t.dtype)
         else:
             job = conv.conv_s2_fwd(xp, wp, out.f32, self.alpha, dtype=t.dtype)
+        attach_stats(t, job, out, self.bn_stats)
         ops.conv_gemm(job)
 
     def backward(self, need_wgrad=True):
@@ -400,8 +413,9 @@ class GemmNode:
     """out[rows, Npad] = x[rows, K] @ W^T for a Linear whose packed weight is supplied by
     ``pack(planes) -> [hi, lo]`` (row re-ordering / padding is the packer's business)."""
 
-    def __init__(self, tape, x, n_out_pad, pack_fwd, pack_bwd, name):
+    def __init__(self, tape, x, n_out_pad, pack_fwd, pack_bwd, name, bn_stats=False):
         self.tape, self.x, self.name = tape, x, name
+        self.bn_stats = bn_stats
         self.pack_fwd, self.pack_bwd = pack_fwd, pack_bwd
         self.out = T4(x.N, x.H, x.W, n_out_pad)
         self.npad = n_out_pad
@@ -412,8 +426,9 @@ class GemmNode:
         dev = x.hi.device
         out.f32 = _e((out.N, out.H, out.W, out.C), dev)
         a = [p.view(x.rows, x.C) if p is not None else None for p in x.planes(t.planes)]
-        ops.conv_gemm(conv.gemm_nt(a, self.pack_fwd(t.planes, t.dtype), out.f32.view(x.rows, self.npad),
-                                   dtype=t.dtype))
+        job = conv.gemm_nt(a, self.pack_fwd(t.planes, t.dtype), out.f32.view(x.rows, self.npad), dtype=t.dtype)
+        attach_stats(t, job, out, self.bn_stats)
+        ops.conv_gemm(job)
 
     def backward(self, need_wgrad=True):
         x, out = self.x, self.out
@@ -493,27 +508,21 @@ class BnActNode:
                 shift = shift + scale * b
         elif self.bn is not None:
             gamma, beta, rmean, rvar, nbt = self.bn
-            if t.training and nbt is not None:
+            if nbt is not None:
                 t.counters.append(nbt)
-            ws = ops.bn_workspace(z.rows, z.C, dev)
             vec = _e((4, z.C), dev)
             self.stat = vec
-            rm, rv = (rmean, rvar) if t.training else (None, None)
-            StateOrder.before(rm)
-            # small layers: one cooperative launch (launch count dominates); large layers: the
-            # multi-launch path, whose reductions use the whole chip
-            if z.rows * z.C <= FUSED_BN_MAX_ELEMS and \
-                    ops.bn_fwd_fused(zm, gamma.detach(), beta.detach(), rm, rv, self.chan_map, self.c_valid,
-                                     self.act, modm, ym, him, lom, t.dtype, ws, vec):
-                StateOrder.after(rm)
-                if not t.need_grad and self.mod is None:
-                    z.f32 = None
-                return
-            ops.bn_stats(zm, ws)
-            ops.bn_finalize(ws, z.rows, gamma.detach(), beta.detach(), rm, rv, self.chan_map, self.c_valid,
-                            vec[0], vec[1], vec[2], vec[3])
-            StateOrder.after(rm)
-            scale, shift = vec[2], vec[3]
+            if z.stats is None:
+                z.stats = t.stat_slot(z.C, dev)
+            if not z.stats_done:
+                ops.bn_stats(zm, z.stats.view(-1))
+            StateOrder.before(rmean)
+            ops.bn_norm_act_pack(zm, z.stats.view(-1), gamma.detach(), beta.detach(), rmean, rvar, self.chan_map,
+                                 self.c_valid, vec, self.act, modm, ym, him, lom, t.dtype)
+            StateOrder.after(rmean)
+            if not t.need_grad and self.mod is None:
+                z.f32 = None        # nothing reads the raw conv output again: release it early
+            return
         ops.bn_act_pack(zm, scale, shift, self.act, modm, ym, him, lom, t.dtype)
         if not t.need_grad and self.mod is None:
             z.f32 = None        # nothing reads the raw conv output again: release it early
@@ -536,16 +545,11 @@ class BnActNode:
         sums = None
         if has_bn:
             vec = self.stat
-            sums = ops.bn_workspace(z.rows, z.C, dev)
+            sums = self.tape.stat_slot(z.C, dev).view(-1)
             if need_param_grad:
                 # every entry is written by the apply stage (all real channels are mapped)
                 self.dgamma = torch.empty_like(self.bn[0])
                 self.dbeta = torch.empty_like(self.bn[1])
-            if z.rows * z.C <= FUSED_BN_MAX_ELEMS and \
-                    ops.bn_bwd_fused(zm, dym, vec[2], vec[3], vec[0], vec[1], self.chan_map, self.c_valid,
-                                     self.act, modm, sums, z.mat(z.grad16), dmod16m, self.dgamma, self.dbeta):
-                out.grad = None
-                return
             ops.bn_bwd_reduce(zm, dym, vec[2], vec[3], vec[0], vec[1], self.act, modm, sums)
         vec = self.stat if has_bn else (None, None, None, None)
         ops.bn_bwd_apply(zm, dym, vec[2], vec[3], vec[0], vec[1], self.chan_map, self.c_valid, self.act,
@@ -560,13 +564,28 @@ class Tape:
     fp16 operands -- SURVEY.md Appendix E: fp16, not bf16, keeps the discriminator gradients that
     are computed on those fakes within tolerance."""
 
-    def __init__(self, cache, training=True, need_grad=True, planes=None, dtype=None):
+    STAT_CHUNK = 1 << 15       # fp64 slots per zero-filled arena chunk (override per network call)
+
+    def __init__(self, cache, training=True, need_grad=True, planes=None, dtype=None, stat_chunk=None):
         self.cache, self.training, self.need_grad = cache, training, need_grad
+        self._arena, self._arena_used = None, 0
+        self._chunk = stat_chunk if stat_chunk is not None else self.STAT_CHUNK
         self.planes = planes if planes is not None else (2 if need_grad else 1)
         self.dtype = dtype if dtype is not None else (ops.BF16 if need_grad else ops.FP16)
         self.nodes = []
         self.counters = []      # num_batches_tracked buffers to bump once the forward is done
         self.aux = AuxBranch()  # weight-gradient side branch of the backward pass
+
+    def stat_slot(self, C, dev):
+        """a zeroed fp64 [2, C] accumulator (BatchNorm sums of the forward / backward pass): slices of
+        arena chunks that are zero-filled with ONE launch each, instead of one fill per layer"""
+        n = 2 * C
+        if self._arena is None or self._arena_used + n > self._arena.numel():
+            self._arena = torch.zeros(max(self._chunk, n), device=dev, dtype=torch.float64)
+            self._arena_used = 0
+        s = self._arena[self._arena_used:self._arena_used + n].view(2, C)
+        self._arena_used += n
+        return s
 
     def finish_forward(self):
         """one multi-tensor launch for all `num_batches_tracked += 1` of this call"""

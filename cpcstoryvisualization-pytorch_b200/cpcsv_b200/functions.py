@@ -81,14 +81,8 @@ class BatchNorm1dFn(torch.autograd.Function):
         ctx.eval_mode = False
         rm, rv = (rmean, rvar) if training else (None, None)
         StateOrder.before(rm)
-        from . import engine
-        if not (M * Cp <= engine.FUSED_BN_MAX_ELEMS and
-                ops.bn_fwd_fused(xp, gamma.detach(), beta.detach(), rm, rv, None, C, ops.ACT_NONE, None, yp,
-                                 None, None, ops.BF16, stats, vec)):
-            ops.bn_stats(xp, stats)
-            ops.bn_finalize(stats, M, gamma.detach(), beta.detach(), rm, rv, None, C, vec[0], vec[1], vec[2],
-                            vec[3])
-            ops.bn_act_pack(xp, vec[2], vec[3], ops.ACT_NONE, y=yp)
+        ops.bn_stats(xp, stats)
+        ops.bn_norm_act_pack(xp, stats, gamma.detach(), beta.detach(), rm, rv, None, C, vec, ops.ACT_NONE, y=yp)
         if training and nbt is not None:
             nbt.add_(1)
         StateOrder.after(rm)

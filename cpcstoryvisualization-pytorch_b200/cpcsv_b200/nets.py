@@ -254,7 +254,7 @@ class TrunkRunner:
         perm = fc_maps(G, C, lin.weight.device)
         node = GemmNode(tape, x0, 16 * rup(C, 64),
                         lambda planes, dtype: pack_fc_fwd(tape.cache, G, lin, C, Kp, planes, dtype),
-                        lambda: pack_fc_bwd(tape.cache, G, lin, C, Kp), name)
+                        lambda: pack_fc_bwd(tape.cache, G, lin, C, Kp), name, bn_stats=True)
         return node, perm
 
     def _latent_planes(self, tape, zmc_all):
@@ -279,7 +279,7 @@ class TrunkRunner:
         G = self.G
         _eval_needs_no_grad(G, self.need_grad)
         N, K = zmc_all.shape
-        tape = Tape(_CACHE, training=G.training, need_grad=self.need_grad)
+        tape = Tape(_CACHE, training=G.training, need_grad=self.need_grad, stat_chunk=1 << 18)
         self.tape = tape
         ngf, nseg = G.gf_dim, G.gf_dim_seg
         x0 = self._latent_planes(tape, zmc_all)
@@ -307,13 +307,13 @@ class TrunkRunner:
         nodes.update({"fc_seg.bn": bn_fs, "seg_c": c_segc, "fc.bn": bn_fc})
         for i in range(1, 5):
             up_s = getattr(G, "upsample%d_seg" % i)
-            cs = ConvNode(tape, "up", a_seg, up_s[1].weight, "upsample%d_seg" % i)
+            cs = ConvNode(tape, "up", a_seg, up_s[1].weight, "upsample%d_seg" % i, bn_stats=True)
             z_s = tape.add(cs)
             bs = BnActNode(tape, z_s, _bn_tuple(up_s[2]), ops.ACT_RELU, "upsample%d_seg.bn" % i,
                            want_planes=True)
             a_seg = tape.add(bs)
             up_i = getattr(G, "upsample%d" % i)
-            ci = ConvNode(tape, "up", a_img, up_i[1].weight, "upsample%d" % i)
+            ci = ConvNode(tape, "up", a_img, up_i[1].weight, "upsample%d" % i, bn_stats=True)
             z_i = tape.add(ci)
             mod = None
             if i == 1:
@@ -567,7 +567,8 @@ class EncoderRunner:
         self.layers = []
         for li, idx in enumerate((2, 5, 8)):
             cmod, bmod = enc[idx], enc[idx + 1]
-            cn = ConvNode(tape, "s2", a, cmod.weight_orig, "enc%d" % idx, sn=sns[li], alpha=alphas[li])
+            cn = ConvNode(tape, "s2", a, cmod.weight_orig, "enc%d" % idx, sn=sns[li], alpha=alphas[li],
+                          bn_stats=True)
             z = tape.add(cn)
             last = (li == 2)
             bn = BnActNode(tape, z, _bn_tuple(bmod), ops.ACT_LRELU, "enc%d.bn" % idx, want_f32=last,
@@ -681,7 +682,7 @@ class LogitsRunner:
         from . import streams
         (alpha, inv_sigma), _ = streams.concurrently(power_iterations, pack_input, enabled=SN_AHEAD)
         self.x, self.Cf = x, Cf
-        cn = ConvNode(tape, "s1", x, seq[0].weight_orig, "logits.conv", sn=sn, alpha=alpha)
+        cn = ConvNode(tape, "s1", x, seq[0].weight_orig, "logits.conv", sn=sn, alpha=alpha, bn_stats=True)
         z = tape.add(cn)
         bn = BnActNode(tape, z, _bn_tuple(seq[1]), ops.ACT_LRELU, "logits.bn", want_f32=True,
                        want_planes=False)

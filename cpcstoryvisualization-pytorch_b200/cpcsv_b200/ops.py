@@ -85,7 +85,7 @@ class GemmJob:
 
     def __init__(self, mode, planes, grid, tile, groups, taps_per_group, k_blocks, taps, a, b, out,
                  n_valid, block_n, n_tiles, m_valid=0, splits=1, accumulate=False,
-                 out_strides=(0, 0, 0), ldc=0, alpha=None, dtype=BF16, pair=False):
+                 out_strides=(0, 0, 0), ldc=0, alpha=None, dtype=BF16, pair=False, stats=None):
         self.mode, self.planes, self.dtype = mode, planes, dtype
         self.grid, self.tile = tuple(grid), tuple(tile)      # (N, H, W), (tile_n, tile_h, tile_w)
         self.groups, self.taps_per_group, self.k_blocks = groups, taps_per_group, k_blocks
@@ -96,6 +96,9 @@ class GemmJob:
         self.splits, self.accumulate = splits, bool(accumulate)
         self.out_strides, self.ldc, self.alpha = tuple(out_strides), ldc, alpha
         self.pair = bool(pair)      # mode 0: cta_group::2 pairs (see conv.use_pair)
+        # mode 0, no split-K: fp64 [2, n_valid] accumulator the epilogue adds the per-column sum and
+        # sum of squares of the stored values into (BatchNorm batch statistics of the conv output)
+        self.stats = stats
 
 
 def conv_gemm(job):
@@ -110,6 +113,9 @@ def conv_gemm(job):
     g.ldc = job.ldc
     g.alpha = _ptr(job.alpha, torch.float32).value if job.alpha is not None else None
     g.out = _ptr(job.out, torch.float32).value
+    if job.stats is not None:
+        assert job.mode == 0 and job.splits == 1 and not job.accumulate and job.stats.dim() == 2
+        g.stats, g.stats_ld = _ptr(job.stats, torch.float64).value, job.stats.stride(0)
     for i in range(job.planes):
         g.a[i] = job.a[i].to_c()
         g.b[i] = job.b[i].to_c()
@@ -126,9 +132,9 @@ def conv_gemm(job):
 
 # ------------------------------------------------------------------ BatchNorm / packing
 def bn_workspace(rows, channels, device):
-    """fp64 buffer for bn_stats / bn_bwd_reduce: [0, 2C) results, then per-block partials."""
+    """zeroed fp64 [2C] accumulator for bn_stats / bn_bwd_reduce (sum | sum of squares)"""
     n = _lib.load().cpcsv_bn_workspace_doubles(rows, channels)
-    return torch.empty(n, device=device, dtype=torch.float64)
+    return torch.zeros(n, device=device, dtype=torch.float64)
 
 
 def bn_stats(x, stats):
@@ -182,35 +188,21 @@ def bn_bwd_apply(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod,
         _ptr(dgamma), _ptr(dbeta), _stream()), "cpcsv_bn_bwd_apply")
 
 
-def bn_fwd_fused(x, gamma, beta, running_mean, running_var, chan_map, c_valid, act, mod, y, hi, lo, dtype,
-                 ws, vec, eps=1e-5, momentum=0.1):
-    """stats + finalize + apply in one cooperative launch; False if the grid cannot be co-resident
-    (caller falls back to bn_stats / bn_finalize / bn_act_pack)."""
+def bn_norm_act_pack(x, stats, gamma, beta, running_mean, running_var, chan_map, c_valid, vec, act, mod=None,
+                     y=None, hi=None, lo=None, dtype=BF16, eps=1e-5, momentum=0.1):
+    """batch-statistics BatchNorm (sums in `stats`) + activation [+ modulation] + operand split in one
+    launch; vec [4, C] receives mean / invstd / scale / shift, the running statistics are updated"""
     rows, Cc, ld = _rows2d(x)
-    rc = _lib.load().cpcsv_bn_fwd_fused(
-        _ptr(x, torch.float32), rows, Cc, ld, _ptr(gamma, torch.float32), _ptr(beta, torch.float32),
-        _ptr(running_mean), _ptr(running_var), _ptr(chan_map, torch.int32), c_valid, eps, momentum, act,
-        _ptr(mod), mod.stride(0) if mod is not None else 0, _ptr(y), y.stride(0) if y is not None else 0,
-        _ptr(hi), _ptr(lo), hi.stride(0) if hi is not None else 0, dtype, _ptr(ws, torch.float64),
-        _ptr(vec, torch.float32), _stream())
-    if rc == -4:
-        return False
-    _lib.check(rc, "cpcsv_bn_fwd_fused")
-    return True
-
-
-def bn_bwd_fused(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod, ws, dx16, dmod16, dgamma,
-                 dbeta):
-    rows, Cc, ld = _rows2d(x)
-    rc = _lib.load().cpcsv_bn_bwd_fused(
-        _ptr(x, torch.float32), _ptr(dy, torch.float32), rows, Cc, ld, dy.stride(0), _ptr(scale), _ptr(shift),
-        _ptr(mean), _ptr(invstd), _ptr(chan_map, torch.int32), c_valid, act, _ptr(mod),
-        mod.stride(0) if mod is not None else 0, _ptr(ws, torch.float64), _ptr(dx16), dx16.stride(0),
-        _ptr(dmod16), dmod16.stride(0) if dmod16 is not None else 0, _ptr(dgamma), _ptr(dbeta), _stream())
-    if rc == -4:
-        return False
-    _lib.check(rc, "cpcsv_bn_bwd_fused")
-    return True
+    assert stats.numel() >= 2 * Cc and vec.numel() == 4 * Cc and vec.is_contiguous()
+    ldp = hi.stride(0) if hi is not None else 0
+    if lo is not None:
+        assert lo.stride(0) == ldp
+    _lib.check(_lib.load().cpcsv_bn_norm_act_pack(
+        _ptr(x, torch.float32), rows, Cc, ld, _ptr(stats, torch.float64), _ptr(gamma, torch.float32),
+        _ptr(beta, torch.float32), _ptr(running_mean, torch.float32), _ptr(running_var, torch.float32),
+        _ptr(chan_map, torch.int32), c_valid, eps, momentum, _ptr(vec, torch.float32), act, _ptr(mod),
+        mod.stride(0) if mod is not None else 0, _ptr(y), y.stride(0) if y is not None else 0, _ptr(hi), _ptr(lo),
+        ldp, dtype, _stream()), "cpcsv_bn_norm_act_pack")
 
 
 # ------------------------------------------------------------------ layout kernels

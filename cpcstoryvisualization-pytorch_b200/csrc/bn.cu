@@ -5,9 +5,11 @@
 // quad for its whole lifetime, so the per-channel constants (scale/shift/mean/invstd, gradient
 // means) sit in registers and the row loop is pure streaming: 16-byte loads, a few FMAs, 8/16-byte
 // stores.  Thread block = `qpb` quads x (256 / qpb) row lanes; grid.x walks the channel quads,
-// grid.y the rows.  Reductions are two-stage (per-block partials, then a small tree kernel):
-// hundreds of blocks doing fp64 atomics on 2C addresses serialise in L2.
-#include <cooperative_groups.h>
+// grid.y the rows.  Reductions: fp64 in registers, a tree over the row lanes of the block in shared
+// memory, then ONE fp64 red.add per channel and block into the caller-zeroed [2C] accumulator (at
+// most a few hundred adds per address, fire-and-forget).  The same accumulator can be filled by the
+// tcgen05 GEMM's epilogue instead (conv_gemm.cu: per-tile column sums), in which case the statistics
+// pass over the conv output disappears.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -62,10 +64,9 @@ inline Tiling make_tiling(int64_t rows, int C, int blocks_per_sm) {
   return t;
 }
 
-inline int reduction_parts(int64_t rows, int C) { return static_cast<int>(make_tiling(rows, C, 4).grid.y); }
 
-// Sum the 8 per-thread fp64 values v[0..8) over the rpb row lanes of each channel quad and hand
-// the totals of lanes rl == 0 to `dst` (dst[c + j] = v[j] totals, dst[C + c + j] = v[4 + j]
+// Sum the 8 per-thread fp64 values v[0..8) over the rpb row lanes of each channel quad and ADD
+// the totals (lanes rl == 0) to `dst` (dst[c + j] += v[j] totals, dst[C + c + j] += v[4 + j]
 // totals).  Two passes through an 8 KB buffer: with 16 KB these kernels would not fit next to a
 // resident tensor-core GEMM block (which leaves ~15 KB of shared memory per SM), and the step's
 // parallel branches could not overlap.
@@ -83,14 +84,14 @@ __device__ __forceinline__ void reduce_rows_to(double (*sh)[4], const double* v,
       for (int j = 0; j < 4; ++j) {
         double t = 0;
         for (int k = 0; k < rpb; ++k) t += sh[k * qpb + ql][j];
-        dst[half * C + c + j] = t;
+        atomicAdd(dst + half * C + c + j, t);
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------- statistics
-// partial[blockIdx.y][0..C) = sum x, [C..2C) = sum x^2  (fp64), written behind the 2C result slots
+// ws[0..C) += sum x, ws[C..2C) += sum x^2  (fp64)
 __global__ void __launch_bounds__(256)
 stats_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx, double* __restrict__ ws,
              int qpb, int rpb) {
@@ -122,26 +123,7 @@ stats_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx, doub
   }
   __shared__ double sh[256][4];
   const double v8[8] = {s[0], s[1], s[2], s[3], ss[0], ss[1], ss[2], ss[3]};
-  reduce_rows_to(sh, v8, qpb, rpb, ql, rl, c < C, ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y), C, c);
-}
-
-// ws[i] = sum_p ws[n * (1 + p) + i]: 32 columns x 8 part lanes per block
-__global__ void __launch_bounds__(256)
-sum_partials_kernel(double* __restrict__ ws, int n, int parts) {
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int lane = threadIdx.x >> 5;
-  double t = 0;
-  if (col < n)
-    for (int p = lane; p < parts; p += 8) t += ws[static_cast<int64_t>(n) * (1 + p) + col];
-  __shared__ double sh[8][32];
-  sh[lane][threadIdx.x & 31] = t;
-  __syncthreads();
-  if (lane == 0 && col < n) {
-    double a = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a += sh[k][threadIdx.x];
-    ws[col] = a;
-  }
+  reduce_rows_to(sh, v8, qpb, rpb, ql, rl, c < C, ws, C, c);
 }
 
 __global__ void finalize_kernel(const double* __restrict__ stats, int64_t rows, int C,
@@ -174,18 +156,62 @@ __global__ void finalize_kernel(const double* __restrict__ stats, int64_t rows, 
 }
 
 // ------------------------------------------------------------------------- forward apply
+// Batch statistics -> per-channel constants, done by the apply kernel itself (no finalize launch):
+// every block derives scale / shift of its own channels from the fp64 sums; the blocks of row 0
+// also publish [mean | invstd | scale | shift] for the backward pass and update the running statistics.
+struct BnNorm {
+  const double* stats;   // [2C] sum, sum of squares (nullptr: use scale / shift as given)
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  const int32_t* chan_map;
+  float* vec;            // [4C]
+  int64_t rows_total;
+  int C_valid;
+  float eps, momentum;
+};
+
 template <bool kMod, bool kY, bool kHi, bool kLo>
 __global__ void __launch_bounds__(256)
 act_pack_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx,
                 const float* __restrict__ scale, const float* __restrict__ shift, int act,
                 const float* __restrict__ mod, int64_t ldmod, float* __restrict__ y, int64_t ldy,
                 uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t ldp, int dtype, int qpb,
-                int rpb) {
+                int rpb, const BnNorm nb) {
   const int ql = threadIdx.x % qpb, rl = threadIdx.x / qpb;
   const int c = (blockIdx.x * qpb + ql) * 4;
   if (c >= C) return;
   float sc[4] = {1.f, 1.f, 1.f, 1.f}, sf[4] = {0.f, 0.f, 0.f, 0.f};
-  if (scale) {
+  if (nb.stats) {
+    const bool writer = blockIdx.y == 0 && rl == 0;
+    const double n = static_cast<double>(nb.rows_total);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = c + j;
+      const int p = nb.chan_map ? nb.chan_map[cc] : cc;
+      float m_ = 0.f, is_ = 0.f, sc_ = 0.f, sf_ = 0.f;
+      if (cc < nb.C_valid && p >= 0) {
+        const double m = nb.stats[cc] / n;
+        double var = nb.stats[C + cc] / n - m * m;
+        if (var < 0) var = 0;
+        is_ = static_cast<float>(1.0 / sqrt(var + static_cast<double>(nb.eps)));
+        m_ = static_cast<float>(m);
+        sc_ = nb.gamma[p] * is_;
+        sf_ = nb.beta[p] - m_ * sc_;
+        if (writer && nb.running_mean) {
+          const double unbiased = nb.rows_total > 1 ? var * n / (n - 1.0) : var;
+          nb.running_mean[p] = (1.f - nb.momentum) * nb.running_mean[p] + nb.momentum * m_;
+          nb.running_var[p] = (1.f - nb.momentum) * nb.running_var[p] + nb.momentum * static_cast<float>(unbiased);
+        }
+      }
+      sc[j] = sc_;
+      sf[j] = sf_;
+      if (writer) {
+        nb.vec[cc] = m_; nb.vec[C + cc] = is_; nb.vec[2 * C + cc] = sc_; nb.vec[3 * C + cc] = sf_;
+      }
+    }
+  } else if (scale) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) { sc[j] = scale[c + j]; sf[j] = shift[c + j]; }
   }
@@ -290,7 +316,7 @@ bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, int
   }
   __shared__ double sh[256][4];
   const double v8[8] = {s[0], s[1], s[2], s[3], sx[0], sx[1], sx[2], sx[3]};
-  reduce_rows_to(sh, v8, qpb, rpb, ql, rl, c < C, ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y), C, c);
+  reduce_rows_to(sh, v8, qpb, rpb, ql, rl, c < C, ws, C, c);
 }
 
 __global__ void __launch_bounds__(256)
@@ -355,235 +381,6 @@ bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, int6
   }
 }
 
-// ------------------------------------------------------------------------- fused (cooperative)
-// One launch per BatchNorm layer instead of four / three: partial sums -> grid.sync -> tree sum by
-// the first row of blocks -> grid.sync -> per-channel constants -> streaming apply.  At the
-// cfg/final.yml batch most layers are a few MB, so the launch count (not bytes) is what costs.
-__device__ __forceinline__ void grid_sync() { cooperative_groups::this_grid().sync(); }
-
-// every block of channel-block blockIdx.x sums the per-row-block partials of its quads: only the
-// blocks with blockIdx.y == 0 do it and publish the totals in ws[0 .. 2C)
-__device__ __forceinline__ void sum_partials_block(double* __restrict__ ws, int C, int c, int ql, int rl,
-                                                   int qpb, int rpb, int parts, double (*sh)[4]) {
-  double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (c < C) {
-    for (int p = rl; p < parts; p += rpb) {
-      const double* part = ws + static_cast<int64_t>(2 * C) * (1 + p);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        t[j] += part[c + j];
-        t[4 + j] += part[C + c + j];
-      }
-    }
-  }
-  reduce_rows_to(sh, t, qpb, rpb, ql, rl, c < C, ws, C, c);
-}
-
-template <bool kMod, bool kY, bool kHi, bool kLo>
-__global__ void __launch_bounds__(256)
-bn_fwd_fused_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx,
-                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                    float* running_mean, float* running_var, const int32_t* __restrict__ chan_map,
-                    int C_valid, float eps, float momentum, int act, const float* __restrict__ mod,
-                    int64_t ldmod, float* __restrict__ y, int64_t ldy, uint16_t* __restrict__ hi,
-                    uint16_t* __restrict__ lo, int64_t ldp, int dtype, double* __restrict__ ws,
-                    float* __restrict__ vec, int qpb, int rpb) {
-  const int ql = threadIdx.x % qpb, rl = threadIdx.x / qpb;
-  const int c = (blockIdx.x * qpb + ql) * 4;
-  const int64_t step = static_cast<int64_t>(gridDim.y) * rpb;
-  __shared__ double sh[256][4];
-  // --- phase A: per-block partial sums
-  {
-    double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-    if (c < C) {
-      int64_t r = static_cast<int64_t>(blockIdx.y) * rpb + rl;
-      for (; r + step < rows; r += 2 * step) {
-        const float4 v0 = *reinterpret_cast<const float4*>(x + r * ldx + c);
-        const float4 v1 = *reinterpret_cast<const float4*>(x + (r + step) * ldx + c);
-        s[0] += static_cast<double>(v0.x) + v1.x; ss[0] += static_cast<double>(v0.x) * v0.x + static_cast<double>(v1.x) * v1.x;
-        s[1] += static_cast<double>(v0.y) + v1.y; ss[1] += static_cast<double>(v0.y) * v0.y + static_cast<double>(v1.y) * v1.y;
-        s[2] += static_cast<double>(v0.z) + v1.z; ss[2] += static_cast<double>(v0.z) * v0.z + static_cast<double>(v1.z) * v1.z;
-        s[3] += static_cast<double>(v0.w) + v1.w; ss[3] += static_cast<double>(v0.w) * v0.w + static_cast<double>(v1.w) * v1.w;
-      }
-      for (; r < rows; r += step) {
-        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
-        s[0] += v.x; ss[0] += static_cast<double>(v.x) * v.x;
-        s[1] += v.y; ss[1] += static_cast<double>(v.y) * v.y;
-        s[2] += v.z; ss[2] += static_cast<double>(v.z) * v.z;
-        s[3] += v.w; ss[3] += static_cast<double>(v.w) * v.w;
-      }
-    }
-    const double v8[8] = {s[0], s[1], s[2], s[3], ss[0], ss[1], ss[2], ss[3]};
-    reduce_rows_to(sh, v8, qpb, rpb, ql, rl, c < C, ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y), C, c);
-  }
-  __threadfence();
-  grid_sync();
-  // --- phase B: tree sum + finalize by the first row of blocks
-  if (blockIdx.y == 0) {
-    __syncthreads();
-    sum_partials_block(ws, C, c, ql, rl, qpb, rpb, static_cast<int>(gridDim.y), sh);
-    if (rl == 0 && c < C) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cc = c + j;
-        float m_ = 0.f, is_ = 0.f, sc_ = 0.f, sf_ = 0.f;
-        const int p = chan_map ? chan_map[cc] : cc;
-        if (cc < C_valid && p >= 0) {
-          const double n = static_cast<double>(rows);
-          const double m = ws[cc] / n;
-          double var = ws[C + cc] / n - m * m;
-          if (var < 0) var = 0;
-          is_ = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-          m_ = static_cast<float>(m);
-          sc_ = gamma[p] * is_;
-          sf_ = beta[p] - m_ * sc_;
-          if (running_mean) {
-            const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
-            running_mean[p] = (1.f - momentum) * running_mean[p] + momentum * m_;
-            running_var[p] = (1.f - momentum) * running_var[p] + momentum * static_cast<float>(unbiased);
-          }
-        }
-        vec[cc] = m_; vec[C + cc] = is_; vec[2 * C + cc] = sc_; vec[3 * C + cc] = sf_;
-      }
-    }
-  }
-  __threadfence();
-  grid_sync();
-  // --- phase C: apply + activation (+ modulation) + operand split
-  if (c >= C) return;
-  float sc[4], sf[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { sc[j] = __ldcg(vec + 2 * C + c + j); sf[j] = __ldcg(vec + 3 * C + c + j); }
-  for (int64_t r = static_cast<int64_t>(blockIdx.y) * rpb + rl; r < rows; r += step) {
-    const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
-    float v[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = apply_act(fmaf(v[j], sc[j], sf[j]), act);
-    if (kMod) {
-      const float4 mv = *reinterpret_cast<const float4*>(mod + r * ldmod + c);
-      v[0] *= 1.f + mv.x; v[1] *= 1.f + mv.y; v[2] *= 1.f + mv.z; v[3] *= 1.f + mv.w;
-    }
-    if (kY) *reinterpret_cast<float4*>(y + r * ldy + c) = make_float4(v[0], v[1], v[2], v[3]);
-    if (kHi) {
-      uint2 hv;
-      hv.x = pack2(v[0], v[1], dtype);
-      hv.y = pack2(v[2], v[3], dtype);
-      *reinterpret_cast<uint2*>(hi + r * ldp + c) = hv;
-      if (kLo) {
-        uint2 lv;
-        lv.x = pack2(v[0] - round16(v[0], dtype), v[1] - round16(v[1], dtype), dtype);
-        lv.y = pack2(v[2] - round16(v[2], dtype), v[3] - round16(v[3], dtype), dtype);
-        *reinterpret_cast<uint2*>(lo + r * ldp + c) = lv;
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-bn_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t rows, int C,
-                    int64_t ldx, int64_t lddy, const float* __restrict__ scale,
-                    const float* __restrict__ shift, const float* __restrict__ mean,
-                    const float* __restrict__ invstd, const int32_t* __restrict__ chan_map, int C_valid,
-                    int act, const float* __restrict__ mod, int64_t ldmod, double* __restrict__ ws,
-                    uint16_t* __restrict__ dx16, int64_t ld16, uint16_t* __restrict__ dmod16,
-                    int64_t lddmod16, float* __restrict__ dgamma, float* __restrict__ dbeta, int qpb,
-                    int rpb) {
-  const int ql = threadIdx.x % qpb, rl = threadIdx.x / qpb;
-  const int c = (blockIdx.x * qpb + ql) * 4;
-  const int64_t step = static_cast<int64_t>(gridDim.y) * rpb;
-  __shared__ double sh[256][4];
-  ChanConst k;
-  if (c < C) k = load_const(scale, shift, mean, invstd, c);
-  {
-    double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
-    if (c < C) {
-      for (int64_t r = static_cast<int64_t>(blockIdx.y) * rpb + rl; r < rows; r += step) {
-        float g0[4], h0[4], a0[4], d0[4];
-        bwd_row(x, dy, mod, r, c, ldx, lddy, ldmod, k, act, g0, h0, a0, d0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          s[j] += g0[j];
-          sx[j] += static_cast<double>(g0[j]) * h0[j];
-        }
-      }
-    }
-    const double v8[8] = {s[0], s[1], s[2], s[3], sx[0], sx[1], sx[2], sx[3]};
-    reduce_rows_to(sh, v8, qpb, rpb, ql, rl, c < C, ws + static_cast<int64_t>(2 * C) * (1 + blockIdx.y), C, c);
-  }
-  __threadfence();
-  grid_sync();
-  if (blockIdx.y == 0) {
-    __syncthreads();
-    sum_partials_block(ws, C, c, ql, rl, qpb, rpb, static_cast<int>(gridDim.y), sh);
-  }
-  __threadfence();
-  grid_sync();
-  if (c >= C) return;
-  float mg[4], mgx[4];
-  const float inv_rows = 1.f / static_cast<float>(rows);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    mg[j] = static_cast<float>(__ldcg(ws + c + j)) * inv_rows;
-    mgx[j] = static_cast<float>(__ldcg(ws + C + c + j)) * inv_rows;
-  }
-  if (dgamma && blockIdx.y == 0 && rl == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (c + j < C_valid) {
-        const int p = chan_map ? chan_map[c + j] : c + j;
-        if (p >= 0) {
-          dgamma[p] = static_cast<float>(__ldcg(ws + C + c + j));
-          dbeta[p] = static_cast<float>(__ldcg(ws + c + j));
-        }
-      }
-    }
-  }
-  for (int64_t r = static_cast<int64_t>(blockIdx.y) * rpb + rl; r < rows; r += step) {
-    float g[4], xhat[4], a[4], dv[4];
-    bwd_row(x, dy, mod, r, c, ldx, lddy, ldmod, k, act, g, xhat, a, dv);
-    uint2 v;
-    v.x = pack2(k.sc[0] * (g[0] - mg[0] - xhat[0] * mgx[0]), k.sc[1] * (g[1] - mg[1] - xhat[1] * mgx[1]), 1);
-    v.y = pack2(k.sc[2] * (g[2] - mg[2] - xhat[2] * mgx[2]), k.sc[3] * (g[3] - mg[3] - xhat[3] * mgx[3]), 1);
-    *reinterpret_cast<uint2*>(dx16 + r * ld16 + c) = v;
-    if (dmod16) {
-      uint2 m;
-      m.x = pack2(dv[0] * a[0], dv[1] * a[1], 1);
-      m.y = pack2(dv[2] * a[2], dv[3] * a[3], 1);
-      *reinterpret_cast<uint2*>(dmod16 + r * lddmod16 + c) = m;
-    }
-  }
-}
-
-constexpr int kCoopBlocksPerSm = 1;
-
-// co-resident grid for a cooperative launch
-template <typename K>
-inline Tiling coop_tiling(K kernel, int64_t rows, int C) {
-  // ONE block per SM: a cooperative grid only starts when all of its blocks fit at once, next to
-  // whatever else is resident.  Sized to fill the machine (4 blocks / SM) these launches could
-  // never overlap the persistent tensor-core GEMM of another branch (which leaves 27 KB of shared
-  // memory per SM) nor each other, and the step's parallel branches serialised on them.
-  (void)kernel;
-  const int per_sm = kCoopBlocksPerSm;
-  // narrow channel blocks (<= 32 quads = 128 channels, 8 row lanes) so that even a [1440, 1024]
-  // layer spreads over 8 x gy blocks; the tree sum between the two grid barriers is done by the
-  // first row of blocks while the rest of the grid waits, so the partial count stays <= 128
-  const int cq = C / 4;
-  Tiling t;
-  t.qpb = 1;
-  while (t.qpb < cq && t.qpb < 32) t.qpb <<= 1;
-  t.rpb = 256 / t.qpb;
-  const int64_t gx = ceil_div(cq, t.qpb);
-  const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
-  int64_t gy = cap / gx;
-  const int64_t max_gy = ceil_div(rows, t.rpb);
-  if (gy > max_gy) gy = max_gy;
-  if (gy > 128) gy = 128;
-  if (gy < 1) gy = 1;
-  t.grid = dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
-  return t;
-}
-
 }  // namespace
 }  // namespace cpcsv
 
@@ -591,7 +388,8 @@ using namespace cpcsv;
 #define STREAM(s) static_cast<cudaStream_t>(s)
 
 extern "C" int64_t cpcsv_bn_workspace_doubles(int64_t rows, int32_t C) {
-  return static_cast<int64_t>(2 * C) * (1 + reduction_parts(rows, C));
+  (void)rows;
+  return static_cast<int64_t>(2 * C);
 }
 
 extern "C" int cpcsv_bn_stats(const float* x, int64_t rows, int32_t C, int64_t ldx, double* stats,
@@ -599,11 +397,7 @@ extern "C" int cpcsv_bn_stats(const float* x, int64_t rows, int32_t C, int64_t l
   CPCSV_REQUIRE(x && stats && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_stats: args");
   const Tiling t = make_tiling(rows, C, 4);
   stats_kernel<<<t.grid, 256, 0, STREAM(stream)>>>(x, rows, C, ldx, stats, t.qpb, t.rpb);
-  int rc = launched("bn_stats");
-  if (rc) return rc;
-  sum_partials_kernel<<<static_cast<unsigned>(ceil_div(2 * C, 32)), 256, 0, STREAM(stream)>>>(
-      stats, 2 * C, static_cast<int>(t.grid.y));
-  return launched("bn_stats/sum");
+  return launched("bn_stats");
 }
 
 extern "C" int cpcsv_bn_finalize(const double* stats, int64_t rows, int32_t C, const float* gamma,
@@ -619,22 +413,17 @@ extern "C" int cpcsv_bn_finalize(const double* stats, int64_t rows, int32_t C, c
   return launched("bn_finalize");
 }
 
-extern "C" int cpcsv_bn_act_pack(const float* x, int64_t rows, int32_t C, int64_t ldx,
-                                 const float* scale, const float* shift, int32_t act,
-                                 const float* mod, int64_t ldmod, float* y, int64_t ldy, void* hi,
-                                 void* lo, int64_t ldp, int32_t dtype, cpcsv_stream_t stream) {
-  CPCSV_REQUIRE(x && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_act_pack: args");
-  CPCSV_REQUIRE((!mod || ldmod % 4 == 0) && (!y || ldy % 4 == 0) && (!hi || ldp % 4 == 0),
-                "bn_act_pack: pitches must be multiples of 4");
-  CPCSV_REQUIRE(hi || y, "bn_act_pack: no output");
-  CPCSV_REQUIRE(!lo || hi, "bn_act_pack: lo without hi");
+static int launch_act_pack(const float* x, int64_t rows, int32_t C, int64_t ldx, const float* scale,
+                           const float* shift, int32_t act, const float* mod, int64_t ldmod, float* y,
+                           int64_t ldy, void* hi, void* lo, int64_t ldp, int32_t dtype, const BnNorm& nb,
+                           cudaStream_t stream, const char* what) {
   const Tiling t = make_tiling(rows, C, 8);
   uint16_t* h = static_cast<uint16_t*>(hi);
   uint16_t* l = static_cast<uint16_t*>(lo);
-#define LAUNCH(M, Y, H, L)                                                                          \
-  act_pack_kernel<M, Y, H, L><<<t.grid, 256, 0, STREAM(stream)>>>(x, rows, C, ldx, scale, shift, act, \
-                                                                   mod, ldmod, y, ldy, h, l, ldp,    \
-                                                                   dtype, t.qpb, t.rpb)
+#define LAUNCH(M, Y, H, L)                                                                     \
+  act_pack_kernel<M, Y, H, L><<<t.grid, 256, 0, stream>>>(x, rows, C, ldx, scale, shift, act, mod, \
+                                                           ldmod, y, ldy, h, l, ldp, dtype, t.qpb, \
+                                                           t.rpb, nb)
   const int key = (mod ? 8 : 0) | (y ? 4 : 0) | (hi ? 2 : 0) | (lo ? 1 : 0);
   switch (key) {
     case 2: LAUNCH(false, false, true, false); break;
@@ -647,10 +436,44 @@ extern "C" int cpcsv_bn_act_pack(const float* x, int64_t rows, int32_t C, int64_
     case 12: LAUNCH(true, true, false, false); break;
     case 14: LAUNCH(true, true, true, false); break;
     case 15: LAUNCH(true, true, true, true); break;
-    default: return fail(-1, "bn_act_pack: unsupported output combination %d", key);
+    default: return fail(-1, "%s: unsupported output combination %d", what, key);
   }
 #undef LAUNCH
-  return launched("bn_act_pack");
+  return launched(what);
+}
+
+extern "C" int cpcsv_bn_act_pack(const float* x, int64_t rows, int32_t C, int64_t ldx,
+                                 const float* scale, const float* shift, int32_t act,
+                                 const float* mod, int64_t ldmod, float* y, int64_t ldy, void* hi,
+                                 void* lo, int64_t ldp, int32_t dtype, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(x && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_act_pack: args");
+  CPCSV_REQUIRE((!mod || ldmod % 4 == 0) && (!y || ldy % 4 == 0) && (!hi || ldp % 4 == 0),
+                "bn_act_pack: pitches must be multiples of 4");
+  CPCSV_REQUIRE(hi || y, "bn_act_pack: no output");
+  CPCSV_REQUIRE(!lo || hi, "bn_act_pack: lo without hi");
+  BnNorm nb = {};
+  return launch_act_pack(x, rows, C, ldx, scale, shift, act, mod, ldmod, y, ldy, hi, lo, ldp, dtype, nb,
+                         STREAM(stream), "bn_act_pack");
+}
+
+extern "C" int cpcsv_bn_norm_act_pack(const float* x, int64_t rows, int32_t C, int64_t ldx,
+                                      const double* stats, const float* gamma, const float* beta,
+                                      float* running_mean, float* running_var, const int32_t* chan_map,
+                                      int32_t C_valid, float eps, float momentum, float* vec, int32_t act,
+                                      const float* mod, int64_t ldmod, float* y, int64_t ldy, void* hi,
+                                      void* lo, int64_t ldp, int32_t dtype, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(x && stats && gamma && beta && vec && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 &&
+                    C_valid <= C,
+                "bn_norm_act_pack: args");
+  CPCSV_REQUIRE((!mod || ldmod % 4 == 0) && (!y || ldy % 4 == 0) && (!hi || ldp % 4 == 0) && (hi || y) &&
+                    (!lo || hi) && (!running_mean == !running_var),
+                "bn_norm_act_pack: outputs");
+  BnNorm nb;
+  nb.stats = stats; nb.gamma = gamma; nb.beta = beta;
+  nb.running_mean = running_mean; nb.running_var = running_var; nb.chan_map = chan_map; nb.vec = vec;
+  nb.rows_total = rows; nb.C_valid = C_valid; nb.eps = eps; nb.momentum = momentum;
+  return launch_act_pack(x, rows, C, ldx, nullptr, nullptr, act, mod, ldmod, y, ldy, hi, lo, ldp, dtype, nb,
+                         STREAM(stream), "bn_norm_act_pack");
 }
 
 extern "C" int cpcsv_bn_bwd_reduce(const float* x, const float* dy, int64_t rows, int32_t C,
@@ -664,11 +487,7 @@ extern "C" int cpcsv_bn_bwd_reduce(const float* x, const float* dy, int64_t rows
   const Tiling t = make_tiling(rows, C, 4);
   bwd_reduce_kernel<<<t.grid, 256, 0, STREAM(stream)>>>(x, dy, rows, C, ldx, lddy, scale, shift, mean,
                                                         invstd, act, mod, ldmod, sums, t.qpb, t.rpb);
-  int rc = launched("bn_bwd_reduce");
-  if (rc) return rc;
-  sum_partials_kernel<<<static_cast<unsigned>(ceil_div(2 * C, 32)), 256, 0, STREAM(stream)>>>(
-      sums, 2 * C, static_cast<int>(t.grid.y));
-  return launched("bn_bwd_reduce/sum");
+  return launched("bn_bwd_reduce");
 }
 
 extern "C" int cpcsv_bn_bwd_apply(const float* x, const float* dy, int64_t rows, int32_t C,
@@ -689,83 +508,4 @@ extern "C" int cpcsv_bn_bwd_apply(const float* x, const float* dy, int64_t rows,
       has_bn, dx, lddx, static_cast<uint16_t*>(dx16), ld16, dmod, lddmod, static_cast<uint16_t*>(dmod16),
       lddmod16, dgamma, dbeta, t.qpb, t.rpb);
   return launched("bn_bwd_apply");
-}
-
-// Fused forward: statistics + finalize (+ running stats) + apply/activation/modulation/split in
-// ONE cooperative launch.  vec = [mean | invstd | scale | shift] (4*C floats), ws as for bn_stats.
-// Returns -4 (nothing enqueued) when the problem cannot be made co-resident; callers then use the
-// unfused entry points.
-extern "C" int cpcsv_bn_fwd_fused(const float* x, int64_t rows, int32_t C, int64_t ldx,
-                                  const float* gamma, const float* beta, float* running_mean,
-                                  float* running_var, const int32_t* chan_map, int32_t C_valid,
-                                  float eps, float momentum, int32_t act, const float* mod,
-                                  int64_t ldmod, float* y, int64_t ldy, void* hi, void* lo,
-                                  int64_t ldp, int32_t dtype, double* ws, float* vec,
-                                  cpcsv_stream_t stream) {
-  CPCSV_REQUIRE(x && gamma && beta && ws && vec && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 &&
-                    C_valid <= C,
-                "bn_fwd_fused: args");
-  CPCSV_REQUIRE((!mod || ldmod % 4 == 0) && (!y || ldy % 4 == 0) && (!hi || ldp % 4 == 0) && (hi || y) &&
-                    (!lo || hi),
-                "bn_fwd_fused: outputs");
-  uint16_t* h = static_cast<uint16_t*>(hi);
-  uint16_t* l = static_cast<uint16_t*>(lo);
-  int qpb = 0, rpb = 0;
-  void* args[] = {&x, &rows, &C, &ldx, &gamma, &beta, &running_mean, &running_var, &chan_map, &C_valid,
-                  &eps, &momentum, &act, &mod, &ldmod, &y, &ldy, &h, &l, &ldp, &dtype, &ws, &vec, &qpb,
-                  &rpb};
-  const void* fn = nullptr;
-  Tiling t;
-#define PICK(M, Y, H, L)                                              \
-  {                                                                   \
-    fn = reinterpret_cast<const void*>(bn_fwd_fused_kernel<M, Y, H, L>); \
-    t = coop_tiling(bn_fwd_fused_kernel<M, Y, H, L>, rows, C);         \
-  }
-  const int key = (mod ? 8 : 0) | (y ? 4 : 0) | (hi ? 2 : 0) | (lo ? 1 : 0);
-  switch (key) {
-    case 2: PICK(false, false, true, false) break;
-    case 3: PICK(false, false, true, true) break;
-    case 4: PICK(false, true, false, false) break;
-    case 6: PICK(false, true, true, false) break;
-    case 7: PICK(false, true, true, true) break;
-    case 10: PICK(true, false, true, false) break;
-    case 11: PICK(true, false, true, true) break;
-    case 12: PICK(true, true, false, false) break;
-    case 14: PICK(true, true, true, false) break;
-    case 15: PICK(true, true, true, true) break;
-    default: return fail(-1, "bn_fwd_fused: unsupported output combination %d", key);
-  }
-#undef PICK
-  if (static_cast<int64_t>(t.grid.x) * t.grid.y > static_cast<int64_t>(num_sms()) * 4)
-    return fail(-4, "bn_fwd_fused: %u x %u blocks cannot be co-resident", t.grid.x, t.grid.y);
-  qpb = t.qpb;
-  rpb = t.rpb;
-  cudaError_t e = cudaLaunchCooperativeKernel(fn, t.grid, dim3(256), args, 0, STREAM(stream));
-  if (e != cudaSuccess) return fail(static_cast<int>(e), "bn_fwd_fused: %s", cudaGetErrorString(e));
-  return launched("bn_fwd_fused");
-}
-
-// Fused backward: reduction + tree sum + apply in one cooperative launch (bf16 outputs only).
-extern "C" int cpcsv_bn_bwd_fused(const float* x, const float* dy, int64_t rows, int32_t C,
-                                  int64_t ldx, int64_t lddy, const float* scale, const float* shift,
-                                  const float* mean, const float* invstd, const int32_t* chan_map,
-                                  int32_t C_valid, int32_t act, const float* mod, int64_t ldmod,
-                                  double* ws, void* dx16, int64_t ld16, void* dmod16,
-                                  int64_t lddmod16, float* dgamma, float* dbeta,
-                                  cpcsv_stream_t stream) {
-  CPCSV_REQUIRE(x && dy && scale && shift && mean && invstd && ws && dx16 && rows > 0 && C > 0 &&
-                    C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && ld16 % 4 == 0,
-                "bn_bwd_fused: args");
-  const Tiling t = coop_tiling(bn_bwd_fused_kernel, rows, C);
-  if (static_cast<int64_t>(t.grid.x) * t.grid.y > static_cast<int64_t>(num_sms()) * 4)
-    return fail(-4, "bn_bwd_fused: %u x %u blocks cannot be co-resident", t.grid.x, t.grid.y);
-  uint16_t* d16 = static_cast<uint16_t*>(dx16);
-  uint16_t* m16 = static_cast<uint16_t*>(dmod16);
-  int qpb = t.qpb, rpb = t.rpb;
-  void* args[] = {&x, &dy, &rows, &C, &ldx, &lddy, &scale, &shift, &mean, &invstd, &chan_map, &C_valid,
-                  &act, &mod, &ldmod, &ws, &d16, &ld16, &m16, &lddmod16, &dgamma, &dbeta, &qpb, &rpb};
-  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(bn_bwd_fused_kernel), t.grid,
-                                              dim3(256), args, 0, STREAM(stream));
-  if (e != cudaSuccess) return fail(static_cast<int>(e), "bn_bwd_fused: %s", cudaGetErrorString(e));
-  return launched("bn_bwd_fused");
 }

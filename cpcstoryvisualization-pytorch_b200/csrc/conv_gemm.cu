@@ -39,7 +39,11 @@ constexpr int kBarrierBytes = 256;
 // row-per-lane v4 writes and for the 8-lanes-per-row v4 reads.
 constexpr int kEpiPitch = 36;
 constexpr int kEpiWarpFloats = 32 * kEpiPitch;
-constexpr int kEpiBytes = 4 * kEpiWarpFloats * 4;
+constexpr int kEpiStageBytes = 4 * kEpiWarpFloats * 4;
+// Column statistics (optional, GemmParams::stats): per-CTA fp32 partial sums / sums of squares of the
+// current tile's columns, two buffers alternating by tile so that one named barrier per tile suffices.
+constexpr int kColAccFloats = 2 * 2 * 256;
+constexpr int kEpiBytes = kEpiStageBytes + kColAccFloats * 4;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;  // columns between the two accumulator stages
 
@@ -60,6 +64,8 @@ struct GemmParams {
   int64_t osn, osh, osw, ldc;
   const float* alpha;
   float* out;
+  double* stats;      // optional [2][stats_ld]: per-column sum / sum of squares of the stored values
+  int64_t stats_ld;
   cpcsv_tap_t taps[CPCSV_MAX_TAPS];
 };
 
@@ -112,6 +118,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* epi_stage = reinterpret_cast<float*>(smem + P.stages * P.stage_bytes + kBarrierBytes);
+  float* colacc = epi_stage + 4 * kEpiWarpFloats;   // [2 buffers][sum | sumsq][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,6 +145,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     fence_barrier_init();
   }
+  if (P.stats)
+    for (int i = threadIdx.x; i < kColAccFloats; i += kThreads) colacc[i] = 0.f;
   if (warp == 2) {
     if (kPair) {
       tmem_alloc_pair(tmem_slot, kTmemCols);
@@ -291,8 +300,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t acc = 0, acc_phase = 0;
     const float alpha = P.alpha ? __ldg(P.alpha) : 1.0f;
     const bool atomic = (P.accumulate != 0) || (P.splits > 1);
+    const bool want_stats = P.stats != nullptr;
+    uint32_t stat_buf = 0;
     for (uint32_t tile = tile0; tile < P.total_tiles; tile += tstep) {
       const TileCoord tc = decode_tile(P, tile, kPair, rank);
+      float* cacc = colacc + stat_buf * 512;
       float* row_ptr;
       bool row_valid;
       if (P.mode == 0) {
@@ -340,6 +352,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           __syncwarp();
           const int32_t col = col0 + c0 + 4 * cq;
+          float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq2[4] = {0.f, 0.f, 0.f, 0.f};
           if (col < P.n_valid) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -354,6 +367,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 } else {
                   *reinterpret_cast<float4*>(dst) = v;
                 }
+                cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
+                cq2[0] = fmaf(v.x, v.x, cq2[0]); cq2[1] = fmaf(v.y, v.y, cq2[1]);
+                cq2[2] = fmaf(v.z, v.z, cq2[2]); cq2[3] = fmaf(v.w, v.w, cq2[3]);
+              }
+            }
+          }
+          if (want_stats) {
+            // sum over the 4 row groups (lane bits 3, 4): lanes 0..7 end up with the 32-row sums of
+            // their 4 columns, added to the CTA's per-tile column accumulators
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+              cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+              cq2[j] += __shfl_xor_sync(0xffffffffu, cq2[j], 8);
+              cq2[j] += __shfl_xor_sync(0xffffffffu, cq2[j], 16);
+            }
+            if (sub == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                atomicAdd(cacc + c0 + 4 * cq + j, cs[j]);
+                atomicAdd(cacc + 256 + c0 + 4 * cq + j, cq2[j]);
               }
             }
           }
@@ -394,6 +428,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if (want_stats) {
+        // all four epilogue warps have added this tile's columns: flush them to the fp64 totals.
+        // The buffer is re-used by the tile after next, i.e. after the next tile's barrier.
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = row; c < P.block_n; c += 128) {
+          const float s1 = cacc[c], s2 = cacc[256 + c];
+          cacc[c] = 0.f;
+          cacc[256 + c] = 0.f;
+          if (col0 + c < P.n_valid) {
+            atomicAdd(P.stats + col0 + c, static_cast<double>(s1));
+            atomicAdd(P.stats + P.stats_ld + col0 + c, static_cast<double>(s2));
+          }
+        }
+        stat_buf ^= 1;
+      }
     }
   }
 
@@ -515,6 +564,11 @@ extern "C" int cpcsv_conv_gemm(const cpcsv_gemm_t* job, cpcsv_stream_t stream_) 
   P.accumulate = J.accumulate;
   P.alpha = J.alpha;
   P.out = J.out;
+  CPCSV_REQUIRE(J.stats == nullptr || (J.mode == 0 && J.splits == 1 && J.accumulate == 0 && J.block_n % 32 == 0 &&
+                                       J.stats_ld >= J.n_valid),
+                "conv_gemm: column statistics need mode 0 without split-K / accumulation and block_n %% 32 == 0");
+  P.stats = J.stats;
+  P.stats_ld = J.stats_ld;
   int ntaps;
   if (J.mode == 0) {
     CPCSV_REQUIRE(J.taps_per_group > 0 && J.k_blocks > 0, "conv_gemm: taps/k_blocks");

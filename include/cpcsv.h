@@ -85,6 +85,11 @@ typedef struct {
   int64_t ldc;                    /* mode 1: row pitch of each output matrix (elements) */
   const float* alpha;             /* optional device scalar multiplied into the result */
   float* out;
+  double* stats;                  /* optional (mode 0, splits == 1, accumulate == 0): per-column sum and
+                                     sum of squares of the stored values over the valid rows, ADDED into
+                                     stats[col] and stats[stats_ld + col] -- the BatchNorm batch statistics
+                                     of the conv output (model.py:31-32) without a pass over it */
+  int64_t stats_ld;
   cpcsv_view5_t a[2];             /* hi, lo */
   cpcsv_view5_t b[2];             /* hi, lo; mode 0: dims (k, rows, 1, 1, 1) */
   cpcsv_tap_t taps[CPCSV_MAX_TAPS];
@@ -97,10 +102,11 @@ int cpcsv_conv_gemm(const cpcsv_gemm_t* job, cpcsv_stream_t stream);
  * 252-263, 503-513; semantics SURVEY.md Appendix A) on fp32 [rows, C] conv outputs, fused
  * with the split into bf16 hi/lo operand planes for the next tcgen05 GEMM.
  */
-/* per-channel sum and sum of squares (fp64): stats[0..C) = sum, stats[C..2C) = sumsq.
- * `stats` (and `sums` of cpcsv_bn_bwd_reduce) must hold cpcsv_bn_workspace_doubles(rows, C)
- * doubles: the first 2C are the result, the rest per-block partials (two-stage reduction, no
- * atomics). */
+/* per-channel sum and sum of squares (fp64), ADDED into stats[0..C) (sum) and stats[C..2C) (sumsq):
+ * the caller zeroes `stats` (2C doubles = cpcsv_bn_workspace_doubles) before the first contribution.
+ * Contributions may also come from the epilogue of cpcsv_conv_gemm (cpcsv_gemm_t.stats), in which
+ * case this pass over the conv output is not needed at all.  Same convention for `sums` of
+ * cpcsv_bn_bwd_reduce. */
 int64_t cpcsv_bn_workspace_doubles(int64_t rows, int32_t C);
 int cpcsv_bn_stats(const float* x, int64_t rows, int32_t C, int64_t ldx, double* stats,
                    cpcsv_stream_t stream);
@@ -120,7 +126,7 @@ int cpcsv_bn_act_pack(const float* x, int64_t rows, int32_t C, int64_t ldx, cons
                       cpcsv_stream_t stream);
 /* backward of the above.  dy is the gradient w.r.t. the (modulated) activation.
  *   a   = act(x*scale+shift);  dmod = dy * a;  da = dy * (1 + mod);  g = da * act'(.)
- * pass 1 (reduce): sums[0..C) += sum g, sums[C..2C) += sum g * xhat  (fp64)
+ * pass 1 (reduce): sums[0..C) += sum g, sums[C..2C) += sum g * xhat  (fp64; caller-zeroed)
  * pass 2 (apply):  dx = scale_g * invstd * (g - mean(g) - xhat * mean(g*xhat))      */
 int cpcsv_bn_bwd_reduce(const float* x, const float* dy, int64_t rows, int32_t C, int64_t ldx,
                         int64_t lddy, const float* scale, const float* shift, const float* mean,
@@ -134,23 +140,15 @@ int cpcsv_bn_bwd_apply(const float* x, const float* dy, int64_t rows, int32_t C,
                        int64_t ld16, float* dmod, int64_t lddmod, void* dmod16, int64_t lddmod16,
                        float* dgamma, float* dbeta, cpcsv_stream_t stream);
 
-/* Single-launch (cooperative, grid-synchronised) forms of the two sequences above -- at the
- * cfg/final.yml batch most BatchNorm layers are a few MB and launch count dominates:
- *   fwd:  bn_stats + bn_finalize + bn_act_pack   (vec = [mean | invstd | scale | shift], 4*C floats)
- *   bwd:  bn_bwd_reduce + bn_bwd_apply           (16-bit outputs)
- * They return -4 without enqueueing anything when the grid cannot be made co-resident; the caller
- * then uses the multi-launch entry points. */
-int cpcsv_bn_fwd_fused(const float* x, int64_t rows, int32_t C, int64_t ldx, const float* gamma,
-                       const float* beta, float* running_mean, float* running_var,
-                       const int32_t* chan_map, int32_t C_valid, float eps, float momentum, int32_t act,
-                       const float* mod, int64_t ldmod, float* y, int64_t ldy, void* hi, void* lo,
-                       int64_t ldp, int32_t dtype, double* ws, float* vec, cpcsv_stream_t stream);
-int cpcsv_bn_bwd_fused(const float* x, const float* dy, int64_t rows, int32_t C, int64_t ldx,
-                       int64_t lddy, const float* scale, const float* shift, const float* mean,
-                       const float* invstd, const int32_t* chan_map, int32_t C_valid, int32_t act,
-                       const float* mod, int64_t ldmod, double* ws, void* dx16, int64_t ld16,
-                       void* dmod16, int64_t lddmod16, float* dgamma, float* dbeta,
-                       cpcsv_stream_t stream);
+/* bn_finalize + bn_act_pack in ONE launch: every block derives scale / shift of its channels from
+ * the fp64 sums in `stats` (batch statistics over `rows` rows); vec = [mean | invstd | scale | shift]
+ * (4*C floats, for the backward pass) and the running statistics are written once. */
+int cpcsv_bn_norm_act_pack(const float* x, int64_t rows, int32_t C, int64_t ldx, const double* stats,
+                           const float* gamma, const float* beta, float* running_mean,
+                           float* running_var, const int32_t* chan_map, int32_t C_valid, float eps,
+                           float momentum, float* vec, int32_t act, const float* mod, int64_t ldmod,
+                           float* y, int64_t ldy, void* hi, void* lo, int64_t ldp, int32_t dtype,
+                           cpcsv_stream_t stream);
 
 /* ------------------------------------------------------------------- layout / pack kernels */
 /* fp32 strided (n, c, h, w) -> NHWC 16-bit hi/lo planes with channel pitch ldp; channels

@@ -102,6 +102,10 @@ def conv_gemm(job):
             off = job.taps[g * job.taps_per_group][2]
             idx = (off + pix_off).reshape(-1, 1) + torch.arange(job.n_valid).view(1, -1)
             vals = (acc[..., :job.n_valid] * alpha).reshape(-1, job.n_valid).float()
+            if getattr(job, "stats", None) is not None:
+                assert job.splits == 1 and not accumulate
+                job.stats[0, :job.n_valid] += vals.double().sum(0)
+                job.stats[1, :job.n_valid] += (vals.double() ** 2).sum(0)
             if accumulate:
                 out_flat[idx.reshape(-1)] += vals.reshape(-1)
             else:
@@ -153,21 +157,22 @@ def _split16(v, dtype):
 
 
 def bn_workspace(rows, channels, device):
-    return torch.empty(2 * channels, device=device, dtype=torch.float64)
+    return torch.zeros(2 * channels, device=device, dtype=torch.float64)
 
 
 def bn_stats(x, stats):
+    """ADDS into the caller-zeroed accumulator (include/cpcsv.h)"""
     Cc = x.shape[1]
     xd = x.double()
-    stats[:Cc] = xd.sum(0)
-    stats[Cc:] = (xd * xd).sum(0)
+    stats[:Cc] += xd.sum(0)
+    stats[Cc:2 * Cc] += (xd * xd).sum(0)
 
 
 def bn_finalize(stats, rows, gamma, beta, running_mean, running_var, chan_map, c_valid,
                 mean, invstd, scale, shift, eps=1e-5, momentum=0.1):
     Cc = mean.numel()
     m = stats[:Cc] / rows
-    var = (stats[Cc:] / rows - m * m).clamp_min(0)
+    var = (stats[Cc:2 * Cc] / rows - m * m).clamp_min(0)
     inv = 1.0 / torch.sqrt(var + eps)
     idx = chan_map.long() if chan_map is not None else torch.arange(Cc)
     valid = (torch.arange(Cc) < c_valid) & (idx >= 0)
@@ -218,8 +223,8 @@ def _bwd_common(x, dy, scale, shift, mean, invstd, act, mod):
 def bn_bwd_reduce(x, dy, scale, shift, mean, invstd, act, mod, sums):
     Cc = x.shape[1]
     _a, g, xhat = _bwd_common(x, dy, scale, shift, mean, invstd, act, mod)
-    sums[:Cc] = g.double().sum(0)
-    sums[Cc:] = (g.double() * xhat.double()).sum(0)
+    sums[:Cc] += g.double().sum(0)
+    sums[Cc:2 * Cc] += (g.double() * xhat.double()).sum(0)
 
 
 def bn_bwd_apply(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod, sums, has_bn,
@@ -228,7 +233,7 @@ def bn_bwd_apply(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod,
     a, g, xhat = _bwd_common(x, dy, scale, shift, mean if has_bn else None, invstd, act, mod)
     if has_bn:
         mg = (sums[:Cc] / rows).float()
-        mgx = (sums[Cc:] / rows).float()
+        mgx = (sums[Cc:2 * Cc] / rows).float()
         d = scale.view(1, -1) * (g - mg.view(1, -1) - xhat * mgx.view(1, -1))
     else:
         d = g
@@ -247,25 +252,12 @@ def bn_bwd_apply(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod,
         dbeta[idx[ok]] = sums[:c_valid].float()[ok]
 
 
-def bn_fwd_fused(x, gamma, beta, running_mean, running_var, chan_map, c_valid, act, mod, y, hi, lo, dtype,
-                 ws, vec, eps=1e-5, momentum=0.1):
-    Cc = x.shape[1]
-    stats = torch.zeros(2 * Cc, dtype=torch.float64)
-    bn_stats(x, stats)
+def bn_norm_act_pack(x, stats, gamma, beta, running_mean, running_var, chan_map, c_valid, vec, act, mod=None,
+                     y=None, hi=None, lo=None, dtype=1, eps=1e-5, momentum=0.1):
+    v4 = vec.view(4, -1)
     bn_finalize(stats, x.shape[0], gamma, beta, running_mean, running_var, chan_map, c_valid,
-                vec[0], vec[1], vec[2], vec[3], eps, momentum)
-    bn_act_pack(x, vec[2], vec[3], act, mod, y, hi, lo, dtype)
-    return True
-
-
-def bn_bwd_fused(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod, ws, dx16, dmod16, dgamma,
-                 dbeta):
-    Cc = x.shape[1]
-    sums = torch.zeros(2 * Cc, dtype=torch.float64)
-    bn_bwd_reduce(x, dy, scale, shift, mean, invstd, act, mod, sums)
-    bn_bwd_apply(x, dy, scale, shift, mean, invstd, chan_map, c_valid, act, mod, sums, True,
-                 dx16=dx16, dmod16=dmod16, dgamma=dgamma, dbeta=dbeta)
-    return True
+                v4[0], v4[1], v4[2], v4[3], eps, momentum)
+    bn_act_pack(x, v4[2], v4[3], act, mod, y, hi, lo, dtype)
 
 
 # ------------------------------------------------------------------------------ layout kernels

@@ -43,12 +43,13 @@ def test_no_cpu_fallback():
 
 
 def test_gemm_struct_layout_matches_header():
-    # sizeof(cpcsv_gemm_t): 18 int32, 4 int64, 2 pointers, 4 views (88 B), 16 taps (40 B)
+    # sizeof(cpcsv_gemm_t): 19 int32, 4 int64, 3 pointers + stats_ld, 4 views (88 B), 16 taps (40 B)
     import ctypes as C
     assert C.sizeof(_lib.View5) == 8 + 5 * 8 + 5 * 8
     assert C.sizeof(_lib.Tap) == 40
     # 19 int32 fields (incl. cta_pair) padded to 20 x 4 bytes before the int64 members
-    assert C.sizeof(_lib.Gemm) == 20 * 4 + 4 * 8 + 2 * 8 + 4 * 88 + 16 * 40
+    assert C.sizeof(_lib.Gemm) == 20 * 4 + 4 * 8 + 2 * 8 + 2 * 8 + 4 * 88 + 16 * 40
+    assert C.sizeof(_lib.AdamHyper) == 2 * 8 + 3 * 8 and C.sizeof(_lib.AdamTensor) == 40 and C.sizeof(_lib.Plane) == 32
 
 
 def test_miscc_package_falls_through_to_the_reference_for_modules_it_does_not_replace(tmp_path):

@@ -1,5 +1,7 @@
-"""Cooperative single-launch BatchNorm forward / backward (cpcsv_bn_fwd_fused / _bwd_fused) against
-the multi-launch contract emulated on the CPU.  GPU only."""
+"""BatchNorm forward / backward as the product issues it -- statistics accumulated with fp64 atomics
+(cpcsv_bn_stats), constants derived inside the apply kernel (cpcsv_bn_norm_act_pack), backward sums
+accumulated likewise -- against the contract emulated on the CPU (reference semantics: model.py:31-33,
+SURVEY.md Appendix A).  GPU only."""
 import pytest
 import torch
 
@@ -21,7 +23,7 @@ def close(a, b, tol):
 
 @pytest.mark.parametrize("rows,C", [(1440, 1024), (90, 4096), (23040, 256), (7, 64), (368640, 128)])
 @pytest.mark.parametrize("act,use_mod", [(1, False), (2, False), (1, True)])
-def test_bn_fused_forward_backward(rows, C, act, use_mod):
+def test_bn_norm_forward_backward(rows, C, act, use_mod):
     if rows * C > 3e7 and use_mod:
         pytest.skip("one large case is enough")
     x = rnd(rows, C, seed=1) * 1.7 + 0.3
@@ -37,21 +39,22 @@ def test_bn_fused_forward_backward(rows, C, act, use_mod):
         lo = torch.empty(rows, C, device=dev, dtype=torch.bfloat16)
         ws = m.bn_workspace(rows, C, dev)
         xd, modd = x.to(dev), (mod.to(dev) if use_mod else None)
-        ok = m.bn_fwd_fused(xd, gamma.to(dev), beta.to(dev), rm, rv, None, C - 4, act, modd, y, hi, lo, 1, ws, vec)
-        assert ok
+        m.bn_stats(xd, ws)
+        m.bn_norm_act_pack(xd, ws, gamma.to(dev), beta.to(dev), rm, rv, None, C - 4, vec, act, modd, y, hi, lo, 1)
         dx16 = torch.empty(rows, C, device=dev, dtype=torch.bfloat16)
         dmod16 = torch.empty(rows, C, device=dev, dtype=torch.bfloat16) if use_mod else None
         dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
         ws2 = m.bn_workspace(rows, C, dev)
-        ok = m.bn_bwd_fused(xd, dy.to(dev), vec[2], vec[3], vec[0], vec[1], None, C - 4, act, modd, ws2, dx16,
-                            dmod16, dg, db)
-        assert ok
+        m.bn_bwd_reduce(xd, dy.to(dev), vec[2], vec[3], vec[0], vec[1], act, modd, ws2)
+        m.bn_bwd_apply(xd, dy.to(dev), vec[2], vec[3], vec[0], vec[1], None, C - 4, act, modd, ws2, True,
+                       dx16=dx16, dmod16=dmod16, dgamma=dg, dbeta=db)
         if dev == "cuda":
             torch.cuda.synchronize()
-        res[dev] = dict(vec=vec.cpu(), rm=rm.cpu(), rv=rv.cpu(), y=y.cpu(), hl=(hi.float() + lo.float()).cpu(),
-                        dx=dx16.float().cpu(), dmod=dmod16.float().cpu() if use_mod else None, dg=dg.cpu(),
-                        db=db.cpu())
+        res[dev] = dict(stats=ws.cpu(), vec=vec.cpu(), rm=rm.cpu(), rv=rv.cpu(), y=y.cpu(),
+                        hl=(hi.float() + lo.float()).cpu(), dx=dx16.float().cpu(),
+                        dmod=dmod16.float().cpu() if use_mod else None, dg=dg.cpu(), db=db.cpu())
     g, c = res["cuda"], res["cpu"]
+    assert close(g["stats"], c["stats"], 1e-9)
     assert torch.allclose(g["vec"], c["vec"], rtol=2e-5, atol=2e-6)
     assert torch.allclose(g["rm"], c["rm"], rtol=1e-5, atol=1e-6) and torch.allclose(g["rv"], c["rv"], rtol=1e-5, atol=1e-6)
     assert close(g["y"], c["y"], 1e-5) and close(g["hl"], c["y"], 3e-5)

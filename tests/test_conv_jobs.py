@@ -219,3 +219,37 @@ def test_split_k_and_many_tiles(dev):
         ops.conv_gemm(conv.conv_s1_fwd(xp, wp, out))
         ref = F.conv2d(x, eff_weight(w, 2), padding=1)
         assert rel(out.permute(0, 3, 1, 2), ref) < 3e-5
+
+
+@pytest.mark.parametrize("kind", ["up", "s2", "gemm"])
+def test_epilogue_column_statistics(dev, kind):
+    """cpcsv_gemm_t.stats: the GEMM epilogue adds the per-column sum / sum of squares of what it stores
+    (the BatchNorm batch statistics of the conv output, reference model.py:31-32) into an fp64 accumulator"""
+    if kind == "up":
+        N, H, Ci, Co = 3, 8, 64, 128
+        x, xe = split(rnd(N, H, H, Ci, seed=41, dev=dev), 2)
+        w = rnd(Co, Ci, 3, 3, seed=42, dev=dev, scale=0.1)
+        out = torch.empty(N, 2 * H, 2 * H, Co, device=dev)
+        job = conv.upconv_fwd(x, pack_w(w, 2, Co, Ci, 2, dev), out)
+    elif kind == "s2":
+        N, H, Ci, Co = 5, 16, 64, 64
+        x, xe = split(rnd(N, H, H, Ci, seed=43, dev=dev), 2)
+        w = rnd(Co, Ci, 4, 4, seed=44, dev=dev, scale=0.1)
+        out = torch.empty(N, H // 2, H // 2, Co, device=dev)
+        job = conv.conv_s2_fwd(x, pack_w(w, 0, Co, Ci, 2, dev), out, alpha=torch.tensor([0.37], device=dev))
+    else:
+        M, K, Nn = 90, 128, 512
+        a, _ = split(rnd(M, K, seed=45, dev=dev), 2)
+        bw, _ = split(rnd(Nn, K, seed=46, dev=dev, scale=0.1), 2)
+        out = torch.empty(M, Nn, device=dev)
+        job = conv.gemm_nt(a, bw, out)
+    job.splits = 1
+    C = out.shape[-1]
+    stats = torch.zeros(2, C, dtype=torch.float64, device=dev)
+    stats[0, 0] = 5.0                      # contributions are ADDED
+    job.stats = stats
+    ops.conv_gemm(job)
+    flat = out.reshape(-1, C).double()
+    ref = torch.stack((flat.sum(0), (flat * flat).sum(0)))
+    ref[0, 0] += 5.0
+    assert float((stats - ref).abs().max() / ref.abs().max()) < 1e-6, kind
