@@ -47,7 +47,7 @@ struct Tiling {
 };
 
 // quads per block: a power of two <= 256 that does not overshoot the channel count much
-inline Tiling make_tiling(int64_t rows, int C, int blocks_per_sm) {
+inline Tiling make_tiling(int64_t rows, int C, int blocks_per_sm, int min_rows_per_thread = 1) {
   const int cq = C / 4;
   int qpb = 1;
   while (qpb < cq && qpb < 256) qpb <<= 1;
@@ -56,7 +56,7 @@ inline Tiling make_tiling(int64_t rows, int C, int blocks_per_sm) {
   t.rpb = 256 / qpb;
   const int64_t gx = ceil_div(cq, qpb);
   int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * blocks_per_sm, gx);
-  const int64_t max_gy = ceil_div(rows, t.rpb);
+  const int64_t max_gy = ceil_div(rows, static_cast<int64_t>(t.rpb) * min_rows_per_thread);
   if (gy > max_gy) gy = max_gy;
   if (gy < 1) gy = 1;
   if (gy > 65535) gy = 65535;
@@ -167,7 +167,8 @@ struct BnNorm {
   float* running_var;
   const int32_t* chan_map;
   float* vec;            // [4C]
-  int64_t rows_total;
+  double inv_rows;       // 1 / rows
+  float unbias;          // rows / (rows - 1)
   int C_valid;
   float eps, momentum;
 };
@@ -184,25 +185,27 @@ act_pack_kernel(const float* __restrict__ x, int64_t rows, int C, int64_t ldx,
   if (c >= C) return;
   float sc[4] = {1.f, 1.f, 1.f, 1.f}, sf[4] = {0.f, 0.f, 0.f, 0.f};
   if (nb.stats) {
+    // mean and variance from the fp64 sums with three fp64 multiplies (1 / rows comes from the host);
+    // everything after the cancellation-prone difference is fp32 -- every thread of every block runs
+    // this prologue, so it must stay a handful of instructions
     const bool writer = blockIdx.y == 0 && rl == 0;
-    const double n = static_cast<double>(nb.rows_total);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int cc = c + j;
       const int p = nb.chan_map ? nb.chan_map[cc] : cc;
       float m_ = 0.f, is_ = 0.f, sc_ = 0.f, sf_ = 0.f;
       if (cc < nb.C_valid && p >= 0) {
-        const double m = nb.stats[cc] / n;
-        double var = nb.stats[C + cc] / n - m * m;
+        const double m = nb.stats[cc] * nb.inv_rows;
+        double var = fma(-m, m, nb.stats[C + cc] * nb.inv_rows);
         if (var < 0) var = 0;
-        is_ = static_cast<float>(1.0 / sqrt(var + static_cast<double>(nb.eps)));
+        const float varf = static_cast<float>(var);
+        is_ = 1.f / sqrtf(varf + nb.eps);
         m_ = static_cast<float>(m);
         sc_ = nb.gamma[p] * is_;
         sf_ = nb.beta[p] - m_ * sc_;
         if (writer && nb.running_mean) {
-          const double unbiased = nb.rows_total > 1 ? var * n / (n - 1.0) : var;
           nb.running_mean[p] = (1.f - nb.momentum) * nb.running_mean[p] + nb.momentum * m_;
-          nb.running_var[p] = (1.f - nb.momentum) * nb.running_var[p] + nb.momentum * static_cast<float>(unbiased);
+          nb.running_var[p] = (1.f - nb.momentum) * nb.running_var[p] + nb.momentum * (varf * nb.unbias);
         }
       }
       sc[j] = sc_;
@@ -395,7 +398,8 @@ extern "C" int64_t cpcsv_bn_workspace_doubles(int64_t rows, int32_t C) {
 extern "C" int cpcsv_bn_stats(const float* x, int64_t rows, int32_t C, int64_t ldx, double* stats,
                               cpcsv_stream_t stream) {
   CPCSV_REQUIRE(x && stats && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0, "bn_stats: args");
-  const Tiling t = make_tiling(rows, C, 4);
+  // every block ends with one fp64 red.add per channel: at least 16 rows per thread
+  const Tiling t = make_tiling(rows, C, 4, 16);
   stats_kernel<<<t.grid, 256, 0, STREAM(stream)>>>(x, rows, C, ldx, stats, t.qpb, t.rpb);
   return launched("bn_stats");
 }
@@ -417,7 +421,7 @@ static int launch_act_pack(const float* x, int64_t rows, int32_t C, int64_t ldx,
                            const float* shift, int32_t act, const float* mod, int64_t ldmod, float* y,
                            int64_t ldy, void* hi, void* lo, int64_t ldp, int32_t dtype, const BnNorm& nb,
                            cudaStream_t stream, const char* what) {
-  const Tiling t = make_tiling(rows, C, 8);
+  const Tiling t = make_tiling(rows, C, 8, 4);
   uint16_t* h = static_cast<uint16_t*>(hi);
   uint16_t* l = static_cast<uint16_t*>(lo);
 #define LAUNCH(M, Y, H, L)                                                                     \
@@ -471,7 +475,9 @@ extern "C" int cpcsv_bn_norm_act_pack(const float* x, int64_t rows, int32_t C, i
   BnNorm nb;
   nb.stats = stats; nb.gamma = gamma; nb.beta = beta;
   nb.running_mean = running_mean; nb.running_var = running_var; nb.chan_map = chan_map; nb.vec = vec;
-  nb.rows_total = rows; nb.C_valid = C_valid; nb.eps = eps; nb.momentum = momentum;
+  nb.inv_rows = 1.0 / static_cast<double>(rows);
+  nb.unbias = rows > 1 ? static_cast<float>(static_cast<double>(rows) / static_cast<double>(rows - 1)) : 1.f;
+  nb.C_valid = C_valid; nb.eps = eps; nb.momentum = momentum;
   return launch_act_pack(x, rows, C, ldx, nullptr, nullptr, act, mod, ldmod, y, ldy, hi, lo, ldp, dtype, nb,
                          STREAM(stream), "bn_norm_act_pack");
 }
@@ -484,7 +490,7 @@ extern "C" int cpcsv_bn_bwd_reduce(const float* x, const float* dy, int64_t rows
   CPCSV_REQUIRE(x && dy && sums && mean && invstd && rows > 0 && C > 0 && C % 4 == 0 &&
                     ldx % 4 == 0 && lddy % 4 == 0,
                 "bn_bwd_reduce: args");
-  const Tiling t = make_tiling(rows, C, 4);
+  const Tiling t = make_tiling(rows, C, 4, 16);
   bwd_reduce_kernel<<<t.grid, 256, 0, STREAM(stream)>>>(x, dy, rows, C, ldx, lddy, scale, shift, mean,
                                                         invstd, act, mod, ldmod, sums, t.qpb, t.rpb);
   return launched("bn_bwd_reduce");
@@ -502,7 +508,7 @@ extern "C" int cpcsv_bn_bwd_apply(const float* x, const float* dy, int64_t rows,
   CPCSV_REQUIRE(x && dy && rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0,
                 "bn_bwd_apply: args");
   CPCSV_REQUIRE(!has_bn || (sums && scale && mean && invstd), "bn_bwd_apply: BN tensors missing");
-  const Tiling t = make_tiling(rows, C, 8);
+  const Tiling t = make_tiling(rows, C, 8, 4);
   bwd_apply_kernel<<<t.grid, 256, 0, STREAM(stream)>>>(
       x, dy, rows, C, ldx, lddy, scale, shift, mean, invstd, chan_map, C_valid, act, mod, ldmod, sums,
       has_bn, dx, lddx, static_cast<uint16_t*>(dx16), ld16, dmod, lddmod, static_cast<uint16_t*>(dmod16),

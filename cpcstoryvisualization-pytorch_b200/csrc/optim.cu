@@ -128,13 +128,17 @@ constexpr int kTile = 16;   // (co) x (ci) tile of a block
 // updates them, writes p / m / v back and stages the new weights in shared memory; the tile is then
 // written out once per requested plane, 16 bytes per thread and 32-byte runs along the plane's
 // contiguous dimension (ci for [tap][co][ci], co for the transposed [tap][ci][co]).
-template <int T>
+// kMerged (3x3 kernels of the up-blocks): all planes hold the 16 sub-pixel merged taps; they are formed
+// ONCE per (co, ci) pair in a second shared-memory tile and every plane is then a plain copy + split.
+template <int T, bool kMerged>
 __global__ void __launch_bounds__(256)
 adam_pack_conv_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                       float* __restrict__ v, int Cout, int Cin, const Hyper h,
                       const __grid_constant__ PlaneSet S) {
   constexpr int kRun = kTile * T;
+  constexpr int kTaps = kMerged ? 16 : T;          // taps of the emitted planes
   __shared__ float s[kTile][kRun + 1];
+  __shared__ float s2[kMerged ? kTile : 1][kMerged ? kTile * 17 + 1 : 1];   // 17: conflict-free per-pair writes
   const int co0 = blockIdx.y * kTile, ci0 = blockIdx.x * kTile;
   if (g) {
     const float step_size = __ldg(h.lr) * __ldg(h.bc);
@@ -186,15 +190,36 @@ adam_pack_conv_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     }
   }
   __syncthreads();
+  if (kMerged) {
+    // thread = one (co, ci) pair of the tile: 3x3 -> 4 phases x 2x2 merged taps
+    const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
+    float w[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w[t] = s[r][c * 9 + t];
+#pragma unroll
+    for (int tap = 0; tap < 16; ++tap) {
+      const int a = tap >> 3, b = (tap >> 2) & 1, ti = (tap >> 1) & 1, tj = tap & 1;
+      int y0, y1, x0, x1;
+      merged_range(a, ti, y0, y1);
+      merged_range(b, tj, x0, x1);
+      float val = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+          if (ky >= y0 && ky <= y1 && kx >= x0 && kx <= x1) val += w[ky * 3 + kx];
+      s2[r][c * 17 + tap] = val;
+    }
+    __syncthreads();
+  }
   constexpr int kVec = kTile * kTile / 8;   // 16-byte output vectors per tap
   for (int q = 0; q < S.count; ++q) {
     const cpcsv_plane_t& P = S.pl[q];
-    const int kind = P.kind, dtype = P.dtype;
-    const bool transposed = (kind == 1 || kind == 3);
-    const int ntap = kind >= 2 ? 16 : T;
+    const int dtype = P.dtype;
+    const bool transposed = (P.kind == 1 || P.kind == 3);
     uint16_t* __restrict__ hi = static_cast<uint16_t*>(P.hi);
     uint16_t* __restrict__ lo = static_cast<uint16_t*>(P.lo);
-    for (int i = threadIdx.x; i < ntap * kVec; i += 256) {
+    for (int i = threadIdx.x; i < kTaps * kVec; i += 256) {
       const int tap = i / kVec, vi = i % kVec;
       // two consecutive threads write the two 16-byte halves of one 32-byte run
       const int minor = (vi & 1) * 8, major = vi >> 1;
@@ -204,24 +229,11 @@ adam_pack_conv_kernel(float* __restrict__ p, const float* __restrict__ g, float*
       const int row = transposed ? ci0 + c0 : co0 + r0;
       const int col = transposed ? co0 + r0 : ci0 + c0;
       if (row >= P.rows_pad || col >= P.cols_pad) continue;
-      int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
-      if (kind >= 2) {
-        const int a = tap >> 3, b = (tap >> 2) & 1, ti = (tap >> 1) & 1, tj = tap & 1;
-        merged_range(a, ti, y0, y1);
-        merged_range(b, tj, x0, x1);
-      }
       uint16_t hv[8], lv[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int r = r0 + e * dr, c = c0 + e * dc;
-        float val;
-        if (kind < 2) {
-          val = s[r][c * T + tap];
-        } else {
-          val = 0.f;
-          for (int ky = y0; ky <= y1; ++ky)
-            for (int kx = x0; kx <= x1; ++kx) val += s[r][c * T + ky * 3 + kx];
-        }
+        const float val = kMerged ? s2[r][c * 17 + tap] : s[r][c * T + tap];
         split16(val, dtype, hv[e], lv[e]);
       }
       const int64_t o = (static_cast<int64_t>(tap) * P.rows_pad + row) * P.cols_pad + col;
@@ -377,6 +389,7 @@ extern "C" int cpcsv_adam_pack_conv(float* p, const float* g, float* m, float* v
     const cpcsv_plane_t& P = planes[i];
     CPCSV_REQUIRE(P.hi && P.kind >= 0 && P.kind <= 3 && (P.dtype == 0 || P.dtype == 1), "adam_pack_conv: plane %d", i);
     CPCSV_REQUIRE(P.kind < 2 || (kh == 3 && kw == 3), "adam_pack_conv: sub-pixel merge needs 3x3");
+    CPCSV_REQUIRE((P.kind >= 2) == (planes[0].kind >= 2), "adam_pack_conv: plain and merged planes of one weight");
     const bool tr = (P.kind == 1 || P.kind == 3);
     CPCSV_REQUIRE(P.rows_pad >= (tr ? Cin : Cout) && P.cols_pad >= (tr ? Cout : Cin) && P.cols_pad % 8 == 0,
                   "adam_pack_conv: plane %d padding", i);
@@ -389,8 +402,10 @@ extern "C" int cpcsv_adam_pack_conv(float* p, const float* g, float* m, float* v
   if (g) h = make_hyper(hyper);
   // tiles cover the PADDED index space so the zero padding of every plane is written too
   dim3 grid(static_cast<unsigned>(ceil_div(ci_ext, kTile)), static_cast<unsigned>(ceil_div(co_ext, kTile)));
-  if (kh * kw == 9) adam_pack_conv_kernel<9><<<grid, 256, 0, STREAM(stream)>>>(p, g, m, v, Cout, Cin, h, S);
-  else adam_pack_conv_kernel<16><<<grid, 256, 0, STREAM(stream)>>>(p, g, m, v, Cout, Cin, h, S);
+  const bool merged = n_planes > 0 && planes[0].kind >= 2;
+  if (merged) adam_pack_conv_kernel<9, true><<<grid, 256, 0, STREAM(stream)>>>(p, g, m, v, Cout, Cin, h, S);
+  else if (kh * kw == 9) adam_pack_conv_kernel<9, false><<<grid, 256, 0, STREAM(stream)>>>(p, g, m, v, Cout, Cin, h, S);
+  else adam_pack_conv_kernel<16, false><<<grid, 256, 0, STREAM(stream)>>>(p, g, m, v, Cout, Cin, h, S);
   return launched("adam_pack_conv");
 }
 
