@@ -124,14 +124,20 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU baseline
-def cpu_reference_rate(steps, warmup, st_batch=2, im_batch=10, threads=None):
-    """The reference algorithm (oracle port, fp32, torch CPU ops) on the host cores, on a bounded
-    sample of the workload: the cfg/final.yml model at `st_batch` stories + `im_batch` images per
-    step instead of 18 + 90.  Returns (stories/s, seconds/step, cores)."""
+def cpu_reference_rate(steps, warmup, st_batch=18, im_batch=90, threads=None, prime=True):
+    """The reference algorithm (oracle port, fp32, torch CPU ops) on the host cores at the FULL cfg/final.yml
+    batch (18 stories + 90 images per step: the same config as the GPU arm).  ``prime``: one step at 2 stories +
+    10 images first (thread pool / oneDNN primitive creation, ~1-2 s), not timed.  Returns (stories/s,
+    seconds/step, cores)."""
     from oracle import functional as Fn
     from oracle import params, synth
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
+    if prime:
+        q = preset_dict(2, 10)
+        q["CUDA"] = False
+        Fn.train_step(Fn.OracleModel(params.init_all(q, 0), q, device="cpu"), synth.make_batch(q, 1),
+                      synth.NoiseFeed(synth.make_noise(q, 2)))
     p = preset_dict(st_batch, im_batch)
     p["CUDA"] = False
     model = Fn.OracleModel(params.init_all(p, 0), p, device="cpu")
@@ -149,14 +155,18 @@ def cpu_reference_rate(steps, warmup, st_batch=2, im_batch=10, threads=None):
 
 
 def run_reference_arm(args):
+    """``--impl reference``: the reference's own CPU implementation of the step (there is no compiled
+    reference: the oracle port of its PyTorch code, all host threads) on THIS arm's config -- the full
+    cfg/final.yml batch -- with a bounded number of steps (a CPU step takes ~10-30 s)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 2))
     warm = 1 if args.warmup > 0 else 0
     rate, sec, cores = cpu_reference_rate(steps, warm)
-    sample = ("oracle port of the reference step (fp32, torch CPU ops, %d threads); cfg/final.yml model, "
-              "bounded sample of 2 stories + 10 images per step (1/9 of the batch); %d timed steps" % (cores, steps))
+    sample = ("oracle port of the reference step (fp32, torch CPU ops, %d threads); cfg/final.yml model and FULL "
+              "batch (18 stories + 90 images per step, same config as the GPU arm); %d warm-up + %d timed steps, "
+              "%.1f s/step" % (cores, warm, steps, sec))
     line = {"impl": "reference", "metric": "train stories/s", "value": rate, "unit": "stories/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -199,6 +209,8 @@ def run_stock_cuda_arm(args, dev=None, p=None):
         out["tf32_on" if tf32 else "tf32_off"] = {"ms_per_step": ms, "stories_per_s": p["ST_BATCH"] / (ms * 1e-3)}
         del model
         torch.cuda.empty_cache()
+    if getattr(args, "return_only", False):
+        return out
     line = {"impl": "stock-cuda", "metric": "train stories/s", "unit": "stories/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "value": out["tf32_off"]["stories_per_s"],
             "ms_per_step": out["tf32_off"]["ms_per_step"], "dtype": "f32", "data": "synthetic",
@@ -320,6 +332,101 @@ def profile_gemm_launches(engine, steps):
             "avg_launch_us": 1e3 * ms / len(recs)}
 
 
+def run_large_config(args):
+    """BASELINE.json configs[3] / configs[4] with the contract's line format (one JSON line per measurement)."""
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    from cpcsv_b200 import _lib
+    _lib.load()
+    peaks = _recorded("../MEASURED_PEAKS.json") or {}
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    sampler = ClockSampler(0)
+    sampler.start()
+
+    def timed(fn, warm, iters):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = _lib.launch_count()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, (_lib.launch_count() - c0) / iters
+
+    lines = []
+    if args.config == "inference":
+        from miscc.config import cfg
+        p = preset_dict()
+        apply_cfg(cfg, p)
+        import trainer
+        G = trainer.build_networks(5)["G"].to(device).train()      # inference.py never calls .eval() (SURVEY 3.3)
+        for B in (16, 64, 256, 1024):
+            motion = torch.randn(B, 5, 365).pin_memory()
+            content = torch.randn(B, 5, 356).pin_memory()
+            dm, dc = motion.to(device), content.to(device)
+            out_host = torch.empty(B, 3, 5, 64, 64).pin_memory()
+
+            def run():
+                with torch.no_grad():
+                    return G.sample_videos(dm, dc, seg=True)
+            run(); run()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs = run()
+            ms, launches = timed(g.replay, max(args.warmup, 3), max(3, min(args.steps, 10)))
+
+            def e2e():
+                dm.copy_(motion, non_blocking=True)
+                dc.copy_(content, non_blocking=True)
+                g.replay()
+                out_host.copy_(outs[1], non_blocking=True)
+            ms_e2e, _ = timed(e2e, 2, max(3, min(args.steps, 10)))
+            gf = 66.9 * B          # GFLOP per 5-frame story, SURVEY.md section 8(d)
+            lines.append({"metric": "inference stories/s", "value": B / ms * 1e3, "unit": "stories/s", "n_gpus": 1,
+                          "steps": max(3, min(args.steps, 10)), "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                          "data": "synthetic",
+                          "config": {"workload": "BASELINE configs[3]: sample_videos (generator + segmentation "
+                                                 "branch) under no_grad, train-mode BN, %d stories x 5 frames" % B,
+                                     "stories": B, "nominal_tflops": gf / ms, "nominal_frac_of_peak": gf / ms / peak,
+                                     "precision": "single-pass fp16 forward GEMMs (no-grad path)"},
+                          "e2e": {"value": B / ms_e2e * 1e3, "unit": "stories/s",
+                                  "h2d_bytes_per_step": (motion.numel() + content.numel()) * 4,
+                                  "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e},
+                          "gpu_launches_per_step": launches})
+            del g, outs
+    else:
+        st_b, im_b = 512, 2560
+        eng = StepEngine(preset_dict(st_b, im_b), device, use_graph=False, grad_sync=None)
+        ms, launches = timed(eng.step, max(2, min(args.warmup, 3)), max(2, min(args.steps, 3)))
+        gf = 659.7 * st_b
+        lines.append({"metric": "train stories/s", "value": st_b / ms * 1e3, "unit": "stories/s", "n_gpus": 1,
+                      "steps": max(2, min(args.steps, 3)), "warmup": max(2, min(args.warmup, 3)), "ms_per_step": ms,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                      "data": "synthetic",
+                      "config": {"workload": "BASELINE configs[4]: 512 stories x 5 frames + 2560 images per step, "
+                                             "full G + 3 D train step (eager, no CUDA graph)",
+                                 "nominal_tflops": gf / ms, "nominal_frac_of_peak": gf / ms / peak,
+                                 "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30},
+                      "gpu_launches_per_step": launches})
+    clocks = sampler.stop()
+    for ln in lines:
+        ln["clocks"] = clocks
+        print(json.dumps(ln), flush=True)
+
+
+def _recorded(name):
+    """a measurement recorded under profiles/ (with its provenance) that the bench line quotes"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", name)))
+    except Exception:
+        return None
+
+
 def _trace(msg):
     if os.environ.get("CPCSV_BENCH_TRACE"):
         print("[bench %.1fs] %s" % (time.perf_counter(), msg), file=sys.stderr, flush=True)
@@ -333,6 +440,12 @@ def main():
     ap.add_argument("--impl", default="cpcsv_b200")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-stock-cuda", action="store_true",
+                    help="also time the oracle step through stock PyTorch / cuDNN on this GPU (TF32 off and on) "
+                         "instead of quoting profiles/r02_stock_cuda.json")
+    ap.add_argument("--config", default="train", choices=["train", "inference", "stress"],
+                    help="train = BASELINE configs[1] (the contract line); inference = configs[3] (no-grad generator "
+                         "+ segmentation branch, batch sweep); stress = configs[4] (512 stories + 2560 images / step)")
     ap.add_argument("--overlap-io", action="store_true",
                     help="e2e loop: copy the next batch on a copy stream while the current step replays "
                          "(trainer.GraphedStep.load_async; opt-in until measured on a GPU)")
@@ -347,6 +460,9 @@ def main():
         return
     if args.impl == "stock-cuda":
         run_stock_cuda_arm(args)
+        return
+    if args.config != "train":
+        run_large_config(args)
         return
     args.warmup = max(args.warmup, 3)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.whole_graph:
@@ -443,6 +559,7 @@ def main():
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
 
+    traffic = _recorded("r02_gemm_traffic.json") or {}
     line = {
         "metric": "train stories/s", "value": stories / (ms_step * 1e-3), "unit": "stories/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -462,10 +579,8 @@ def main():
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": launches_per_step,
         "roofline": {"bound": "tensor", "achieved": prof["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
-                     "frac": prof["achieved_tflops"] / peak, "traffic": None,
-                     "traffic_note": "no per-launch average over the 219 launch shapes; ncu --set full of four "
-                                     "GEMM classes in profiles/r01_ncu_full_v2_head_and_gemm_classes.txt (up3 "
-                                     "forward: 77 MB read + 56 MB written = its operands and output once)",
+                     "frac": prof["achieved_tflops"] / peak, "traffic": traffic.get("avg_bytes_per_launch"),
+                     "traffic_note": traffic.get("note", "no ncu capture recorded under profiles/"),
                      "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM)", "peak_source": peak_src,
                      "executed_gflop_per_step": prof["executed_gflop_per_step"],
                      "gemm_launches_per_step": prof["launches_per_step"],
@@ -476,13 +591,27 @@ def main():
                      "gemm_ms_per_step_serial_events": prof["gemm_ms_per_step"]},
         "clocks": clocks,
     }
+    # the "second bar" of BASELINE.md section 4.4: the same step through stock PyTorch / cuDNN on this GPU
+    stock = _recorded("r02_stock_cuda.json")
+    if rank == 0 and world == 1 and args.with_stock_cuda:
+        del eng
+        torch.cuda.empty_cache()
+        ns = argparse.Namespace(steps=3, warmup=2, return_only=True)
+        live = run_stock_cuda_arm(ns, device, dict(preset_dict(), CUDA=True))
+        stock = {"tf32_off_ms_per_step": live["tf32_off"]["ms_per_step"], "tf32_on_ms_per_step": live["tf32_on"]["ms_per_step"],
+                 "source": "measured in this run (bench.py --with-stock-cuda)"}
+    if stock:
+        stock = dict(stock)
+        stock["speedup_vs_tf32_off"] = stock["tf32_off_ms_per_step"] / ms_step
+        stock["speedup_vs_tf32_on"] = stock["tf32_on_ms_per_step"] / ms_step
+        line["stock_cuda"] = stock
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = cpu_reference_rate(2, 1)
+        rate, sec, cores = cpu_reference_rate(1, 0)
         line["cpu_baseline"] = {
             "value": rate, "unit": "stories/s", "cores": cores, "kind": "port",
             "sample": "oracle port of the reference step (fp32 torch CPU ops, %d threads) on the cfg/final.yml "
-                      "model with 2 stories + 10 images per step (1/9 of the batch), 2 timed steps, %.1f s/step"
-                      % (cores, sec)}
+                      "model at the FULL batch (18 stories + 90 images): 1 timed step (%.1f s) after a "
+                      "2-story priming step" % (cores, sec)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

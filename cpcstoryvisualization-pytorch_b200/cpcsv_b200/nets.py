@@ -231,8 +231,8 @@ class TrunkRunner:
     Inputs of the Function: zmc_all [N, ninput] and the parameters in ``self.names`` order.
     Outputs: img [N,3,64,64], seg [N,1,64,64] (NCHW fp32, tanh range)."""
 
-    def __init__(self, G, need_grad, want_seg):
-        self.G, self.need_grad, self.want_seg = G, need_grad, want_seg
+    @staticmethod
+    def parameter_names():
         names = ["fc.0.weight", "fc.1.weight", "fc.1.bias"]
         for i in range(1, 5):
             names += ["upsample%d.1.weight" % i, "upsample%d.2.weight" % i, "upsample%d.2.bias" % i]
@@ -242,7 +242,11 @@ class TrunkRunner:
             names += ["upsample%d_seg.1.weight" % i, "upsample%d_seg.2.weight" % i,
                       "upsample%d_seg.2.bias" % i]
         names += ["img_seg.0.weight"]
-        self.names = names
+        return names
+
+    def __init__(self, G, need_grad, want_seg):
+        self.G, self.need_grad, self.want_seg = G, need_grad, want_seg
+        self.names = self.parameter_names()
         self.params = dict(G.named_parameters())
 
     def apply(self, zmc_all):

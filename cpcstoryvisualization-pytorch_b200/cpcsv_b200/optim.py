@@ -36,6 +36,11 @@ class PackedAdam(torch.optim.Optimizer):
             cache = nets.weight_cache()
         self.cache = cache
         self._dev = {}          # per group index: device-side step / bc / lr
+        # overlap of the optimiser step with the tail of the backward pass (expect_backward)
+        self._early_params, self._early_ids = [], set()
+        self._armed, self._pending, self._done = False, set(), set()
+        self._ticked = set()
+        self._side, self._side_used = None, False
 
     # ---- device-side scalars ----------------------------------------------------------------
     def _group_state(self, gi, group, device):
@@ -57,21 +62,69 @@ class PackedAdam(torch.optim.Optimizer):
             st["lr_host"] = lr
         return st
 
+    # ---- optimiser step inside the backward pass ------------------------------------------------
+    def overlap_with_backward(self, params):
+        """Declare `params` (the generator trunk: 99.9 % of its bytes) as "early": once ``expect_backward``
+        has armed the optimiser, their Adam + re-layout kernels are issued on a side stream the moment the
+        LAST of their gradients has been accumulated -- while autograd still runs the rest of the backward
+        pass (the latency-bound conditioning path) -- instead of after it.  ``step()`` then only updates the
+        remaining parameters and joins the side stream.  Results are identical to a plain ``step()``."""
+        self._early_params = [p for p in params]
+        self._early_ids = {id(p) for p in self._early_params}
+        for p in self._early_params:
+            p.register_post_accumulate_grad_hook(self._grad_ready)
+
+    def expect_backward(self):
+        """arm the early step for the NEXT backward pass only (a backward pass that is not followed by
+        ``step()`` -- gradient checks, gradient exchange between ranks -- must not be armed)"""
+        if self._early_params:
+            self._armed = True
+            self._pending = set(self._early_ids)
+
+    def disarm(self):
+        self._armed = False
+
+    def _grad_ready(self, p):
+        if not self._armed:
+            return
+        if not p.is_cuda:                    # host-logic tests on the CPU emulator: no streams
+            self._pending.discard(id(p))
+            if not self._pending:
+                self._armed = False
+                self._update([q for q in self._early_params if q.grad is not None])
+            return
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=p.device, priority=cur.priority)
+        self._side.wait_stream(cur)          # this gradient is complete in stream order of `cur`
+        self._side_used = True
+        self._pending.discard(id(p))
+        if not self._pending:
+            self._armed = False
+            with torch.cuda.stream(self._side):
+                self._update([q for q in self._early_params if q.grad is not None])
+
+    def _tick(self, gi, group, st):
+        if gi not in self._ticked:
+            beta1, beta2 = group["betas"]
+            ops.adam_tick(st["step"], beta1, beta2, st["bc"])
+            self._ticked.add(gi)
+
     @torch.no_grad()
-    def step(self, closure=None):
-        loss = None
-        if closure is not None:
-            with torch.enable_grad():
-                loss = closure()
+    def _update(self, only=None):
+        """Adam + re-layout kernels for the parameters of `only` (None: every parameter with a gradient
+        that has not been updated yet in this step)"""
+        only_ids = {id(p) for p in only} if only is not None else None
         for gi, group in enumerate(self.param_groups):
-            params = [p for p in group["params"] if p.grad is not None]
+            params = [p for p in group["params"] if p.grad is not None and id(p) not in self._done and
+                      (only_ids is None or id(p) in only_ids)]
             if not params:
                 continue
             device = params[0].device
             st = self._group_state(gi, group, device)
             beta1, beta2 = group["betas"]
             hyper = ops.AdamHyper(st["lr"], st["bc"], beta1, beta2, group["eps"])
-            ops.adam_tick(st["step"], beta1, beta2, st["bc"])
+            self._tick(gi, group, st)
             plain, touched = [], []
             for p in params:
                 if p.grad.is_sparse:
@@ -103,7 +156,23 @@ class PackedAdam(torch.optim.Optimizer):
                     touched += [(e, p) for _, e in fc]
                 else:
                     plain.append((p, g, m, v))
+                self._done.add(id(p))
             ops.adam_multi(plain, hyper)
             for ent, p in touched:
                 self.cache.refreshed(ent, p)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self._armed = False
+        if self._side_used:
+            # the early part runs on the side stream: same step count / bias corrections, other parameters
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_used = False
+        self._update(None)
+        self._done.clear()
+        self._ticked.clear()
         return loss

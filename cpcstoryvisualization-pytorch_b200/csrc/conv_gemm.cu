@@ -40,9 +40,10 @@ constexpr int kBarrierBytes = 256;
 constexpr int kEpiPitch = 36;
 constexpr int kEpiWarpFloats = 32 * kEpiPitch;
 constexpr int kEpiStageBytes = 4 * kEpiWarpFloats * 4;
-// Column statistics (optional, GemmParams::stats): per-CTA fp32 partial sums / sums of squares of the
-// current tile's columns, two buffers alternating by tile so that one named barrier per tile suffices.
-constexpr int kColAccFloats = 2 * 2 * 256;
+// Column statistics (optional, GemmParams::stats): fp32 sums / sums of squares of the current tile's
+// columns, one region per epilogue warp (its 32 rows; plain stores, no shared-memory atomics), combined
+// and flushed to the fp64 totals between two named barriers of the four epilogue warps.
+constexpr int kColAccFloats = 4 * 2 * 256;
 constexpr int kEpiBytes = kEpiStageBytes + kColAccFloats * 4;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;  // columns between the two accumulator stages
@@ -118,7 +119,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* epi_stage = reinterpret_cast<float*>(smem + P.stages * P.stage_bytes + kBarrierBytes);
-  float* colacc = epi_stage + 4 * kEpiWarpFloats;   // [2 buffers][sum | sumsq][256]
+  float* colacc = epi_stage + 4 * kEpiWarpFloats;   // [4 warps][sum | sumsq][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -145,8 +146,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     fence_barrier_init();
   }
-  if (P.stats)
-    for (int i = threadIdx.x; i < kColAccFloats; i += kThreads) colacc[i] = 0.f;
   if (warp == 2) {
     if (kPair) {
       tmem_alloc_pair(tmem_slot, kTmemCols);
@@ -301,10 +300,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const float alpha = P.alpha ? __ldg(P.alpha) : 1.0f;
     const bool atomic = (P.accumulate != 0) || (P.splits > 1);
     const bool want_stats = P.stats != nullptr;
-    uint32_t stat_buf = 0;
+    float* cacc = colacc + q * 512;
     for (uint32_t tile = tile0; tile < P.total_tiles; tile += tstep) {
       const TileCoord tc = decode_tile(P, tile, kPair, rank);
-      float* cacc = colacc + stat_buf * 512;
       float* row_ptr;
       bool row_valid;
       if (P.mode == 0) {
@@ -384,11 +382,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               cq2[j] += __shfl_xor_sync(0xffffffffu, cq2[j], 16);
             }
             if (sub == 0) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                atomicAdd(cacc + c0 + 4 * cq + j, cs[j]);
-                atomicAdd(cacc + 256 + c0 + 4 * cq + j, cq2[j]);
-              }
+              *reinterpret_cast<float4*>(cacc + c0 + 4 * cq) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+              *reinterpret_cast<float4*>(cacc + 256 + c0 + 4 * cq) = make_float4(cq2[0], cq2[1], cq2[2], cq2[3]);
             }
           }
           __syncwarp();
@@ -429,19 +424,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
       if (want_stats) {
-        // all four epilogue warps have added this tile's columns: flush them to the fp64 totals.
-        // The buffer is re-used by the tile after next, i.e. after the next tile's barrier.
+        // all four epilogue warps have written their 32-row column sums: combine, add to the fp64 totals
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int c = row; c < P.block_n; c += 128) {
-          const float s1 = cacc[c], s2 = cacc[256 + c];
-          cacc[c] = 0.f;
-          cacc[256 + c] = 0.f;
           if (col0 + c < P.n_valid) {
+            const float s1 = colacc[c] + colacc[512 + c] + colacc[1024 + c] + colacc[1536 + c];
+            const float s2 = colacc[256 + c] + colacc[768 + c] + colacc[1280 + c] + colacc[1792 + c];
             atomicAdd(P.stats + col0 + c, static_cast<double>(s1));
             atomicAdd(P.stats + P.stats_ld + col0 + c, static_cast<double>(s2));
           }
         }
-        stat_buf ^= 1;
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // regions are overwritten by the next tile
       }
     }
   }

@@ -27,6 +27,23 @@ SYNC_ACCURACY = True   # reference behaviour: .cpu().numpy() round trip per call
 PARALLEL_PASSES = True  # real / fake (/ wrong-pair) passes of one discriminator on parallel CUDA streams
 
 
+import contextlib  # noqa: E402
+
+
+@contextlib.contextmanager
+def accuracy_on_device():
+    """inside the block ``get_multi_acc`` returns device tensors instead of Python floats (no host round
+    trip: required while a CUDA graph is being captured and wanted in the replayed / eager step); the
+    reference behaviour (``SYNC_ACCURACY``) is restored on exit"""
+    global SYNC_ACCURACY
+    old = SYNC_ACCURACY
+    SYNC_ACCURACY = False
+    try:
+        yield
+    finally:
+        SYNC_ACCURACY = old
+
+
 def _parallel(*thunks):
     """independent passes through the same discriminator on parallel streams; module state they
     share (BatchNorm running statistics, spectral-norm u / v) is still updated in call order"""

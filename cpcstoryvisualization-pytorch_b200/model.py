@@ -99,6 +99,9 @@ class D_GET_LOGITS(nn.Module):
     def forward(self, h_code, c_code=None):
         if c_code is None:
             raise NotImplementedError("D_GET_LOGITS needs the condition vector on this path")
+        if torch.is_grad_enabled() and c_code.requires_grad:
+            raise RuntimeError("cpcsv_b200: D_GET_LOGITS does not return a gradient for c_code (the reference always "
+                               "passes a detached condition, miscc/utils.py:56,130); detach it")
         c_code = c_code.reshape(-1, self.ef_dim)
         need_grad = torch.is_grad_enabled() and (
             h_code.requires_grad or any(p.requires_grad for p in self.parameters()))

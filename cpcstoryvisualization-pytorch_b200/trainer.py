@@ -115,6 +115,12 @@ def build_optimizers(nets, fused=None, lr_tensor_device=None):
             if lr_tensor_device is not None:
                 lr = torch.tensor(float(lr), device=lr_tensor_device)
             opts[k] = PackedAdam(params, lr=lr, betas=(0.5, 0.999))
+            if k == "G" and not hasattr(net, "presample"):
+                # the trunk's Adam + re-layout kernels are issued as soon as its gradients are complete,
+                # overlapping the backward pass of the conditioning path (armed per step in train_step)
+                named = dict(net.named_parameters())
+                opts[k].overlap_with_backward([named[n] for n in knets.TrunkRunner.parameter_names()
+                                               if n in named and named[n].requires_grad])
         else:
             opts[k] = optim.Adam(params, lr=lr, betas=(0.5, 0.999))
     return opts
@@ -333,7 +339,13 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
     if apply_optim and not step_inside:
         for k in D_NETS:
             opts[k].step()
-    out.update(stage_generator(nets, x, labels, ratio, skip_d_wgrad, forward=out.pop("early_generator", None)))
+    if step_inside and hasattr(opts["G"], "expect_backward"):
+        opts["G"].expect_backward()      # the generator's Adam step starts inside the backward pass
+    try:
+        out.update(stage_generator(nets, x, labels, ratio, skip_d_wgrad, forward=out.pop("early_generator", None)))
+    finally:
+        if hasattr(opts["G"], "disarm"):
+            opts["G"].disarm()
     sync_grads(nets, ("G",), grad_sync)
     if apply_optim:
         opts["G"].step()
@@ -377,9 +389,8 @@ class GraphedStep:
 
     def __init__(self, nets, opts, labels, dev_st, dev_im, grad_sync=None, ratio=1.0, use_graph=True,
                  segmented=None):
-        import miscc.utils as mu
-        mu.SYNC_ACCURACY = False            # no host round trip inside the step
         self.nets, self.opts, self.labels, self.ratio = nets, opts, labels, ratio
+        self._captured_grads = None
         self.dev_st, self.dev_im = dev_st, dev_im
         self.device = labels[0].device
         self.grad_sync = grad_sync
@@ -452,21 +463,27 @@ class GraphedStep:
         self.loss_dev.copy_(torch.stack([out[k].reshape(()) for k in self.loss_keys]))
 
     def _step_body(self):
+        from miscc.utils import accuracy_on_device
         x = prepare_inputs(self.dev_st, self.dev_im)
-        self._record(train_step(self.nets, self.opts, x, self.labels, self.ratio, self.grad_sync))
+        with accuracy_on_device():          # no host round trip inside the step (scoped, not process-wide)
+            self._record(train_step(self.nets, self.opts, x, self.labels, self.ratio, self.grad_sync))
 
     # the step in three segments, with the NCCL gradient exchange between them
     def _seg_d(self):
+        from miscc.utils import accuracy_on_device
         self._x = prepare_inputs(self.dev_st, self.dev_im)
-        self._out = stage_discriminators(self.nets, self._x, self.labels, early_generator=EARLY_G)
+        with accuracy_on_device():
+            self._out = stage_discriminators(self.nets, self._x, self.labels, early_generator=EARLY_G)
         if "early_generator" in self._out:
             self._out["early_generator"].join()      # every branch joins before the segment ends
 
     def _seg_g(self):
+        from miscc.utils import accuracy_on_device
         for k in D_NETS:
             self.opts[k].step()
-        self._out.update(stage_generator(self.nets, self._x, self.labels, self.ratio,
-                                         forward=self._out.pop("early_generator", None)))
+        with accuracy_on_device():
+            self._out.update(stage_generator(self.nets, self._x, self.labels, self.ratio,
+                                             forward=self._out.pop("early_generator", None)))
 
     def _seg_opt(self):
         self.opts["G"].step()
@@ -500,6 +517,14 @@ class GraphedStep:
             pool = g.pool()
             self.graphs.append(g)
         self.graph = True
+        # the replayed backward passes write, and the replayed optimiser steps read, THESE gradient tensors;
+        # an eager step in between (a batch of another size) re-points .grad elsewhere
+        self._captured_grads = [(p, p.grad) for net in self.nets.values() for p in net.parameters()]
+
+    def _restore_captured_grads(self):
+        if self._captured_grads is not None:
+            for p, g in self._captured_grads:
+                p.grad = g
 
     def step(self):
         if self._pending:
@@ -510,6 +535,7 @@ class GraphedStep:
             self.graph.replay()
         else:
             # in place: the captured Adam steps read the gradient memory of the captured backward pass
+            self._restore_captured_grads()
             self.graphs[0].replay()
             sync_grads(self.nets, D_NETS, self.grad_sync, inplace=True)
             self.graphs[1].replay()
@@ -534,6 +560,8 @@ def snapshot_sources(output_dir, cfg_file=None):
 
 
 class GANTrainer(object):
+    world, rank = 1, 0      # one process per GPU; set from the torchrun environment in __init__
+
     def __init__(self, output_dir, args, ratio=1.0):
         if cfg.TRAIN.FLAG:
             output_dir = "{}/".format(output_dir)
@@ -559,12 +587,22 @@ class GANTrainer(object):
         local_rank = int(os.environ.get("LOCAL_RANK", self.gpus[0]))
         torch.cuda.set_device(local_rank)
         self.device = torch.device("cuda", local_rank)
+        # data parallel = one process per GPU (torchrun): join the job's process group here, so that the
+        # reference's main_pororo.py / main_clevr.py need no change (they never call init_process_group)
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        if self.world > 1:
+            if not dist.is_available():
+                raise RuntimeError("WORLD_SIZE > 1 but torch.distributed is not available")
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=self.device)
         self._logger = None
-        try:
-            from tensorboardX import SummaryWriter
-            self._logger = SummaryWriter(self.log_dir)
-        except Exception:
-            pass
+        if self.rank == 0:
+            try:
+                from tensorboardX import SummaryWriter
+                self._logger = SummaryWriter(self.log_dir)
+            except Exception:
+                pass
 
     def load_network_stageI(self):
         nets = build_networks(self.video_len)
@@ -618,15 +656,35 @@ class GANTrainer(object):
 
     GRAPH_WARMUP_STEPS = 3      # eager steps (optimiser state, weight caches, NCCL) before the capture
 
+    def _shard_loader(self, loader):
+        """with several ranks every rank must see its own shard of the data: a loader without a
+        DistributedSampler (the reference's main scripts build plain shuffling loaders) is rebuilt around one"""
+        from torch.utils.data import DataLoader
+        from torch.utils.data.distributed import DistributedSampler
+        if self.world <= 1 or loader is None or isinstance(getattr(loader, "sampler", None), DistributedSampler):
+            return loader
+        sampler = DistributedSampler(loader.dataset, num_replicas=self.world, rank=self.rank, shuffle=True,
+                                     drop_last=True)
+        return DataLoader(loader.dataset, batch_size=loader.batch_size, sampler=sampler, drop_last=True,
+                          num_workers=loader.num_workers, collate_fn=loader.collate_fn,
+                          pin_memory=loader.pin_memory)
+
     def train(self, imageloader, storyloader, testloader, stage=1):
         """reference trainer.py:187-485.  On a GPU the step runs through ``GraphedStep``: batches are
         copied into static device buffers and, after ``GRAPH_WARMUP_STEPS`` eager iterations, every
         iteration is one CUDA-graph replay (``CPCSV_GRAPH=0`` keeps the eager step).  Losses stay on
         the device; they are read back only when a logger is attached, every 20 iterations."""
+        imageloader, storyloader = self._shard_loader(imageloader), self._shard_loader(storyloader)
         self.imageloader, self.imagedataset = imageloader, None
         netG, netD_im, netD_st, netD_se = self.load_network_stageI()
         nets = {"G": netG, "D_im": netD_im, "D_st": netD_st, "D_se": netD_se}
         broadcast_initial_state(nets)
+        if self.world > 1:
+            # identical weights on every rank, but independent noise (the reference's mains seed every
+            # process with 0: identical noise would make the averaged gradients equal the local ones)
+            seed = torch.initial_seed() + self.rank
+            torch.manual_seed(seed)
+            torch.cuda.manual_seed(seed)
         dev = self.device
         use_graph = dev.type == "cuda" and os.environ.get("CPCSV_GRAPH", "1") != "0"
         opts = build_capturable_optimizers(nets, dev) if use_graph else build_optimizers(nets)
@@ -646,6 +704,9 @@ class GANTrainer(object):
             start_t = time.time()
             num_step = len(storyloader)
             last = None
+            for ld in (storyloader, imageloader):
+                if self.world > 1 and hasattr(getattr(ld, "sampler", None), "set_epoch"):
+                    ld.sampler.set_epoch(epoch)
             for i, data in enumerate(storyloader):
                 st_batch, im_batch = tensors(data), tensors(self.sample_real_image_batch(to_device=False))
                 want_log = self._logger is not None and i % 20 == 0
@@ -682,7 +743,7 @@ class GANTrainer(object):
                 last = (data, st_batch, i)
             # end-of-epoch sample sheet from the last story batch (reference trainer.py:437-444): one more
             # train-mode no-grad generator call (it moves the BatchNorm running statistics, as there)
-            if last is not None:
+            if last is not None and self.rank == 0:
                 data, st_batch, i = last
                 st_dev = {k: v.to(dev, non_blocking=True) for k, v in st_batch.items()}
                 T = cfg.TEXT.DIMENSION
@@ -704,7 +765,7 @@ class GANTrainer(object):
                 for k in ("D_st", "D_im"):
                     set_lr(opts[k], discriminator_lr)
                 lr_decay_step *= 2
-            if cfg.EVALUATE_FID_SCORE:
+            if cfg.EVALUATE_FID_SCORE and self.rank == 0:
                 self.calculate_vfid(netG, epoch, testloader)
             print("----[{}/{}] epoch {:.1f} min, total {:.1f} h----".format(
                 epoch, self.max_epoch, (time.time() - start_t) / 60, (time.time() - c_time) / 3600))

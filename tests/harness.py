@@ -44,7 +44,7 @@ def product_inputs(batch):
     return trainer.prepare_inputs(st, im)
 
 
-def run_product_step(p, device, seed_w=0, seed_b=1, seed_n=2):
+def run_product_step(p, device, seed_w=0, seed_b=1, seed_n=2, fused=False):
     import trainer
     states = params.init_all(p, seed_w)
     nets = build_product(p, states, device)
@@ -55,7 +55,7 @@ def run_product_step(p, device, seed_w=0, seed_b=1, seed_n=2):
     N, B = p["IM_BATCH"], p["ST_BATCH"]
     labels = (torch.ones(N, device=device), torch.zeros(N, device=device),
               torch.ones(B, device=device), torch.zeros(B, device=device))
-    opts = trainer.build_optimizers(nets, fused=False)
+    opts = trainer.build_optimizers(nets, fused=fused)
     out = trainer.train_step(nets, opts, x, labels, ratio=1.0)
     assert feed.pos == len(feed.tensors)
     grads = {k: {n: (q.grad.detach().clone() if q.grad is not None else torch.zeros_like(q))
@@ -87,7 +87,8 @@ def rel_l2(a, b):
 
 def compare(out, grads, ref_out, ref_grads, verbose=False):
     """returns dict of worst-case metrics against the reference results"""
-    res = {"loss_rel": 0.0, "img_rel": 0.0, "cos_min": 1.0, "cos_min_name": None, "cos_net": {}}
+    res = {"loss_rel": 0.0, "img_rel": 0.0, "cos_min": 1.0, "cos_min_name": None, "cos_net": {},
+           "zero_grad_ratio": 0.0}
     for k in LOSS_KEYS + tuple(k for k in CASCADE_LOSS_KEYS if k in ref_out):
         r = abs(float(out[k]) - float(ref_out[k])) / abs(float(ref_out[k]))
         res["loss_rel"] = max(res["loss_rel"], r)
@@ -106,6 +107,15 @@ def compare(out, grads, ref_out, ref_grads, verbose=False):
             cat_a.append(mine.flatten().double())
             cat_b.append(g.flatten().double())
             if n in ZERO_GRAD:
+                # true gradient identically zero (bias in front of a batch-statistics BatchNorm): checked by
+                # norm, relative to the gradient of the same layer's weight
+                wref = gd.get(n[:-len("bias")] + "weight")
+                scale = float(wref.norm()) if wref is not None else 1.0
+                ratio = float(mine.double().norm()) / max(scale, 1e-30)
+                if verbose:
+                    print("  zero-grad %s.%s |g| %.3e (|ref| %.3e) vs |dW| %.3e" % (
+                        net, n, float(mine.norm()), float(g.norm()), scale))
+                res["zero_grad_ratio"] = max(res["zero_grad_ratio"], ratio)
                 continue
             c = cosine(mine, g)
             if verbose and c < 0.9995:

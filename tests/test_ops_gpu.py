@@ -310,3 +310,51 @@ def test_nested_forks_borrow_distinct_streams():
     assert seen["in1"] == main                       # last piece of the nested fork: the parent
     assert len({seen["a"], seen["b"], seen["in0"], main}) == 4
     assert not any(streams._LENT.values())           # everything given back
+
+
+def test_planes_stay_current_across_graph_replays_that_update_the_weights():
+    """ADVICE r1 (stale packed weights after CUDA-graph replays): an eager generator call, replays of a
+    captured graph whose optimiser step changes the weights, an eager call again -- the second eager call
+    must see the updated conv / fc weights (PackedAdam rewrites the persistent planes inside the graph)."""
+    import harness
+    from cpcsv_b200.optim import PackedAdam
+    from oracle import functional as Fn
+    from oracle import params, presets, synth
+    p = presets.get("small")
+    dev = torch.device("cuda")
+    nets = harness.build_product(p, params.init_all(p, 0), dev)
+    G = nets["G"]
+    batch = synth.make_batch(p, 1, device=dev)
+    x = harness.product_inputs(batch)
+
+    def run():
+        feed = synth.NoiseFeed(synth.make_noise(p, 2, device=dev, calls=("images",)))
+        harness.inject_noise(G, feed)
+        with torch.no_grad():
+            return G.sample_images(x["im_motion"], x["im_content"], seg=True)[1]
+    img0 = run()
+    opt = PackedAdam(list(G.parameters()), lr=torch.tensor(5e-3, device=dev), betas=(0.5, 0.999))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for q in G.parameters():
+        q.grad = torch.randn(q.shape, device=dev, generator=gen)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        opt.step()                                   # eager: allocates the optimiser state
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        opt.step()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert float(opt.state[next(iter(G.parameters()))]["step"]) == 4     # 1 eager step + 3 replays
+    img1 = run()
+    sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    feed = synth.NoiseFeed(synth.make_noise(p, 2, device=dev, calls=("images",)))
+    with torch.no_grad():
+        ref = Fn.sample_images(sd, x["im_motion"], x["im_content"], feed, seg=True)[1]
+    # no-grad generator calls run single-pass fp16 GEMMs: ~1.5e-3 relative on the images
+    assert harness.rel_l2(img1, ref) < 5e-3, harness.rel_l2(img1, ref)
+    assert harness.rel_l2(img0, ref) > 1e-2          # the updates really changed the output

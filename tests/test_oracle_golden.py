@@ -56,7 +56,7 @@ def test_tiny_full_tensors(name):
             assert torch.allclose(t.float(), model.nets[net][n].float(), atol=5e-4, rtol=1e-4), (net, n)
 
 
-@pytest.mark.parametrize("name", ["small", "clevr", "small_cascade"])
+@pytest.mark.parametrize("name", ["small", "clevr", "small_cascade", "pororo"])
 def test_summary_presets(name):
     gold, model, out = _run(name)
     for k, v in gold["losses"].items():

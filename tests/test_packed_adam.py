@@ -154,3 +154,41 @@ def test_adam_pack_kernels_match_the_pack_kernels_gpu():
                 assert torch.equal(a_hi, b_hi), (Co, Ci, k, kind, dtype)
                 if two:
                     assert torch.equal(a_lo, b_lo)
+
+
+def test_early_step_inside_backward_gives_the_same_update(dev):
+    """overlap_with_backward / expect_backward: part of the parameters is updated from a gradient hook in
+    the middle of backward(), the rest in step(); together exactly one Adam step for every parameter"""
+    P = _params(dev, seed=7)
+    Q = {k: torch.nn.Parameter(v.detach().clone()) for k, v in P.items()}
+    cache = engine.WeightCache()
+    _register_planes(cache, P)
+    opt = PackedAdam(list(P.values()), lr=torch.tensor(2e-3, device=dev), betas=(0.5, 0.999), cache=cache)
+    ref = torch.optim.Adam(list(Q.values()), lr=2e-3, betas=(0.5, 0.999))
+    early = ["up", "s1", "fc", "bn_w"]
+    opt.overlap_with_backward([P[k] for k in early])
+
+    def loss(W):
+        return sum(((w * (i + 1)) ** 2).sum() + w.sum() for i, w in enumerate(W.values()))
+    for step in range(2):
+        for W, o in ((P, opt), (Q, ref)):
+            o.zero_grad(set_to_none=True)
+        before = {k: P[k].detach().clone() for k in P}
+        opt.expect_backward()
+        loss(P).backward()
+        # the early parameters have already moved, the others not yet
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        assert all(not torch.equal(before[k], P[k].detach()) for k in early)
+        assert all(torch.equal(before[k], P[k].detach()) for k in P if k not in early)
+        opt.step()
+        loss(Q).backward()
+        ref.step()
+        for k in P:
+            a, b = P[k].detach().double().cpu(), Q[k].detach().double().cpu()
+            assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(b.abs().max())), (k, step)
+    # not armed: backward alone must not touch the weights
+    before = {k: P[k].detach().clone() for k in P}
+    opt.zero_grad(set_to_none=True)
+    loss(P).backward()
+    assert all(torch.equal(before[k], P[k].detach()) for k in P)

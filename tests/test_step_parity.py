@@ -27,6 +27,7 @@ from oracle import presets
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL_LOSS, TOL_IMG, TOL_COS = 1e-3, 2e-2, 0.999
+TOL_ZERO_GRAD = 1e-4        # |g| of an identically-zero gradient, relative to |dW| of the same layer
 
 
 def _step_pair(p, dev, oracle_dev=None, oracle_dtype=torch.float64):
@@ -47,6 +48,7 @@ def _check(res, small_tensor_cos=None):
     assert res["loss_rel"] <= TOL_LOSS, res
     assert res["img_rel"] <= TOL_IMG, res
     assert res["cos_min"] >= (small_tensor_cos or TOL_COS), res
+    assert res["zero_grad_ratio"] <= TOL_ZERO_GRAD, res
     for net, c in res["cos_net"].items():
         assert c >= TOL_COS, (net, c)
 
@@ -115,7 +117,7 @@ def _check_against_golden(gold, out, grads):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["tiny", "small", "clevr"])
+@pytest.mark.parametrize("name", ["tiny", "small", "clevr", "clevr_cascade"])
 def test_step_gpu(name):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -147,3 +149,71 @@ def test_pororo_step_gpu():
     res = harness.compare(out, grads, ref_out, ref_grads, verbose=True)
     print("pororo", res)
     _check(res)
+
+
+def _check_against_summary_golden(gold, out, grads):
+    """discriminator-side quantities of the REAL reference at a full-width preset (summary fixture:
+    losses, per-tensor gradient norms and leading entries, image statistics); they are computed before
+    any optimiser step, so they do not depend on the Adam coupling"""
+    for k in ("se_errD", "im_errD", "st_errD"):
+        assert abs(float(out[k]) - gold["losses"][k]) <= TOL_LOSS * abs(gold["losses"][k]), (
+            k, float(out[k]), gold["losses"][k])
+    for k in ("p1_st_fake", "p1_im_fake", "p1_se_fake"):
+        mean, std, head = gold["image_stats"][k]
+        mine = out[k].float().cpu()
+        assert abs(float(mine.mean()) - mean) <= 2e-3 and abs(float(mine.std()) - std) <= 2e-2 * std, k
+        # single-pass fp16 no-grad generator: ~1.5e-3 relative on the images
+        assert float((mine.flatten()[:64] - head).norm()) <= TOL_IMG * float(head.norm()) + 1e-3, k
+    for net in ("D_im", "D_st", "D_se"):
+        for n, v in gold["grad_norms"][net].items():
+            got = grads[net][n].cpu()
+            assert abs(float(got.norm()) - v) <= 2e-2 * v + 1e-9, (net, n, float(got.norm()), v)
+            head = gold["grad_heads"][net][n]
+            rms = v / max(1.0, got.numel() ** 0.5)
+            assert float((head - got.flatten()[:16]).norm()) <= 0.05 * float(head.norm()) + 0.05 * rms + 1e-9, (net, n)
+
+
+@pytest.mark.gpu
+def test_pororo_step_gpu_vs_reference_golden():
+    """BASELINE.json configs[1] against outputs of the REAL reference at that config
+    (tests/golden/step_pororo.pt, written by oracle/make_golden.py from /root/reference)."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gold = torch.load(os.path.join(GOLD, "step_pororo.pt"))
+    _, out, grads = harness.run_product_step(gold["preset"], torch.device("cuda"), fused=True)
+    _check_against_summary_golden(gold, out, grads)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["clevr", "pororo"])
+def test_coupled_step_gpu(name):
+    """The step as bench.py times it: Adam applied between the phases (PackedAdam), so the generator
+    update sees the UPDATED discriminators.  The first Adam step is sign(g)-like and amplifies
+    rounding-level differences of the discriminator gradients; the yardstick is therefore the
+    reference's own fp32-vs-fp64 deviation through the same coupling, measured here with the oracle:
+    the product (vs the fp64 oracle) must not deviate more than twice that, and everything that does
+    not pass through the coupling keeps the north-star tolerances."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    p = presets.get(name)
+    dev = torch.device("cuda")
+    _, out, grads = harness.run_product_step(p, dev, fused=True)
+    _, ref_out, ref_grads = harness.run_oracle_step(p, dev, torch.float64)
+    _, o32_out, o32_grads = harness.run_oracle_step(p, dev, torch.float32)
+    mine = harness.compare(out, grads, ref_out, ref_grads, verbose=True)
+    band = harness.compare(o32_out, o32_grads, ref_out, ref_grads)
+    print(name, "product vs fp64:", mine)
+    print(name, "fp32 oracle vs fp64:", band)
+    # discriminator side: computed before any optimiser step
+    for k in ("se_errD", "im_errD", "st_errD"):
+        assert abs(float(out[k]) - float(ref_out[k])) <= TOL_LOSS * abs(float(ref_out[k])), k
+    for k in ("p1_st_fake", "p1_im_fake", "p1_se_fake"):
+        assert harness.rel_l2(out[k].float().cpu(), ref_out[k].float().cpu()) <= TOL_IMG, k
+    for net in ("D_im", "D_st", "D_se"):
+        assert mine["cos_net"][net] >= TOL_COS, (net, mine["cos_net"][net])
+    # generator side, through the coupling
+    assert mine["loss_rel"] <= max(TOL_LOSS, 2 * band["loss_rel"]), (mine["loss_rel"], band["loss_rel"])
+    assert mine["img_rel"] <= TOL_IMG
+    assert 1 - mine["cos_net"]["G"] <= max(1 - TOL_COS, 2 * (1 - band["cos_net"]["G"])), (
+        mine["cos_net"]["G"], band["cos_net"]["G"])
+    assert mine["zero_grad_ratio"] <= TOL_ZERO_GRAD
