@@ -54,11 +54,12 @@ class CacheEntry:
     PERSISTENT buffers kept current by the optimiser -- their ``spec`` and the ``fill`` closure that
     re-packs them in place"""
 
-    __slots__ = ("tag", "val", "stream", "event", "ref", "spec", "fill")
+    __slots__ = ("tag", "val", "stream", "event", "ref", "spec", "fill", "in_capture")
 
-    def __init__(self, tag, val, stream, event, ref, spec=None, fill=None):
+    def __init__(self, tag, val, stream, event, ref, spec=None, fill=None, in_capture=False):
         self.tag, self.val, self.stream, self.event, self.ref, self.spec, self.fill = \
             tag, val, stream, event, ref, spec, fill
+        self.in_capture = in_capture     # the event was recorded while a CUDA graph was being captured
 
 
 class WeightCache:
@@ -132,6 +133,13 @@ class WeightCache:
         # parameter's id, address and version can all be recycled by a later one)
         alive = ent is not None and ent.ref() is param
         if alive and ent.tag == tag:
+            if on_gpu and ent.stream is not None and ent.in_capture != capturing:
+                # (maintained planes only: plain entries carry the capture state in their tag.)  An event
+                # recorded outside a capture cannot be waited on inside one, and vice versa.  Packed eagerly,
+                # read inside a capture: torch.cuda.graph() synchronises the device before capturing, so the
+                # pack is complete.  Packed inside a capture, read eagerly: the reader is enqueued after the
+                # replay that produced the planes.
+                ent.stream = ent.event = None
             if on_gpu and ent.stream is not None and ent.stream != cur:
                 cur.wait_event(ent.event)
                 if ent.spec is None:
@@ -154,7 +162,7 @@ class WeightCache:
             ev.record(cur)
         # the entry (and the operand planes it keeps alive) goes away with the parameter
         self.d[key] = CacheEntry(tag, val, cur, ev, weakref.ref(param, lambda _r, k=key, d=self.d: d.pop(k, None)),
-                                 spec, fill)
+                                 spec, fill, capturing)
         return val
 
 
