@@ -16,6 +16,9 @@ _CACHE = engine.WeightCache()
 # activation chain (they depend on the weights only).  No measurable gain on B200 (23.3 ms either
 # way): off by default, one less layer of nested stream forks.
 SN_AHEAD = False
+# img / img_seg heads: pixel-major GEMM + gather (True) or the direct CUDA-core kernel (False)
+import os as _os  # noqa: E402
+HEAD_VIA_GEMM = _os.environ.get("CPCSV_HEAD_GEMM", "1") != "0"
 
 
 def weight_cache():
@@ -349,15 +352,39 @@ class TrunkRunner:
             return hi
         return _CACHE.get((id(w), "head_bwd", 1, ops.BF16), w, build)
 
+    def _head_pack_fwd(self, w, planes, dtype):
+        """3x3 head conv weight as the B operand of the pixel-major forward GEMM: [Npad, Ci_pad] with row
+        tap*Co + co = w[co, :, tap] (Npad = 9*Co rounded up to 16)"""
+        Co, Ci = w.shape[0], w.shape[1]
+        Cip, Np = rup(Ci, 64), rup(9 * Co, 16)
+
+        def build():
+            w2 = w.detach().permute(2, 3, 0, 1).reshape(9 * Co, Ci).contiguous()    # [tap*Co + co, ci]
+            t16 = ops.TORCH16[dtype]
+            hi = _e((Np, Cip), w.device, t16)
+            lo = _e((Np, Cip), w.device, t16) if planes == 2 else None
+            ops.pack_matrix(w2, Np, Cip, Ci, Ci, 1, _row_pad_map(9 * Co, Np, w.device), hi, lo, dtype)
+            return [hi, lo]
+        return _CACHE.get((id(w), "head_fwd", planes, dtype), w, build)
+
     def _head_fwd(self, a, w, Co, name):
-        """img / img_seg: direct conv3x3 + tanh kernel on the operand planes (HBM-bound; a GEMM with
-        3 or 1 output channels would re-read the activation once per tap)"""
+        """img / img_seg: conv3x3 -> tanh with 3 / 1 output channels (reference model.py:272-274, 298-300).
+        HEAD_VIA_GEMM: one pixel-major tensor-core GEMM Z[p, tap*Co + co] (the activation is read once,
+        N = 9*Co padded to 16 / 32) and a gather-tanh kernel over the L2-resident Z; otherwise the direct
+        CUDA-core kernel on the operand planes."""
         dev = a.hi.device
         tp = self.tape
+        y = _e((a.N, Co, a.H, a.W), dev)
+        if HEAD_VIA_GEMM:
+            wp = self._head_pack_fwd(w, tp.planes, tp.dtype)
+            z = _e((a.rows, wp[0].shape[0]), dev)
+            planes = [a.hi.view(a.rows, a.C), a.lo.view(a.rows, a.C) if tp.planes == 2 else None]
+            ops.conv_gemm(conv.gemm_nt(planes, wp, z, dtype=tp.dtype))
+            ops.head_gather_tanh(z, a.N, a.H, a.W, Co, y)
+            return y
         wd = w.detach()
         if wd.shape[1] != a.C:                       # channel-padded activation: zero weight columns
             wd = torch.nn.functional.pad(wd, (0, 0, 0, 0, 0, a.C - wd.shape[1]))
-        y = _e((a.N, Co, a.H, a.W), dev)
         ops.head_conv_tanh_fwd(a.hi, a.lo if tp.planes == 2 else None, wd.contiguous(), y, tp.dtype)
         return y
 

@@ -242,6 +242,14 @@ def head_conv_tanh_fwd(hi, lo, w, y, dtype=BF16):
         _ptr(y, torch.float32), _stream()), "cpcsv_head_conv_tanh_fwd")
 
 
+def head_gather_tanh(z, N, H, W, Co, y):
+    """y[n, co, h, w] = tanh(sum_{ky,kx} z[(n, h+ky-1, w+kx-1), (ky*3+kx)*Co + co]); z [N*H*W, ld] fp32"""
+    assert z.dim() == 2 and z.stride(1) == 1 and z.shape[0] == N * H * W and y.is_contiguous()
+    assert tuple(y.shape) == (N, Co, H, W)
+    _lib.check(_lib.load().cpcsv_head_gather_tanh(_ptr(z, torch.float32), z.stride(0), N, H, W, Co,
+                                                  _ptr(y, torch.float32), _stream()), "cpcsv_head_gather_tanh")
+
+
 def tanh_to_nchw(z, N, Cc, H, W, y):
     assert y.is_contiguous()
     _lib.check(_lib.load().cpcsv_tanh_to_nchw(_ptr(z, torch.float32), z.stride(0), N, Cc, H, W,

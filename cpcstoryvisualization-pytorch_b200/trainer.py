@@ -60,7 +60,7 @@ class GradSync:
         for g in grads:
             offs.append(total)
             total += (g.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-        flat = torch.zeros(total, device=grads[0].device, dtype=grads[0].dtype)
+        flat = torch.empty(total, device=grads[0].device, dtype=grads[0].dtype)     # alignment gaps stay unread
         views = [flat[o:o + g.numel()].view(g.shape) for o, g in zip(offs, grads)]
         torch._foreach_copy_(views, grads)
         if self.world > 1:
@@ -172,7 +172,7 @@ def _concurrently(*thunks, enabled=None):
     return streams.concurrently(*thunks, enabled=CONCURRENT_D if enabled is None else enabled)
 
 
-def stage_discriminators(nets, x, labels, early_generator=False, opts=None):
+def stage_discriminators(nets, x, labels, early_generator=False, opts=None, grad_sync=None):
     """reference trainer.py:290-343 minus the optimiser steps: no-grad fakes, the three
     discriminator losses and their backward passes.  The three discriminators are independent
     networks, so running all backward passes before any of their Adam steps (instead of the
@@ -185,10 +185,12 @@ def stage_discriminators(nets, x, labels, early_generator=False, opts=None):
     after the no-grad calls, so noise is drawn and BatchNorm running statistics are updated in
     the reference's order.  The handle comes back under ``out['early_generator']``.
 
-    ``opts``: when given (single-process training, no gradient exchange), every discriminator's
-    Adam step and the re-layout of its updated weights for the generator stage are issued on that
-    discriminator's own stream right after its backward pass, so they overlap with the other
-    discriminators still running instead of forming a tensor-core-idle gap after the join."""
+    ``opts``: when given, every discriminator's Adam step (which also rewrites the operand planes of its
+    weights for the generator stage) is issued on that discriminator's own stream right after its backward
+    pass, so it overlaps with the other discriminators still running instead of forming a
+    tensor-core-idle gap after the join.  ``grad_sync`` (with ``opts``): the gradient exchange of each
+    discriminator is issued there as well, between its backward pass and its Adam step: the all-reduce of
+    the first two discriminators runs under the remaining compute of the others."""
     netG, netD_im, netD_st, netD_se = nets["G"], nets["D_im"], nets["D_st"], nets["D_se"]
     im_ones, im_zeros, st_ones, st_zeros = labels
     gpus = None
@@ -238,8 +240,9 @@ def stage_discriminators(nets, x, labels, early_generator=False, opts=None):
                                          real_features=real_feats.get(key))[0]
         err.backward()
         if opts is not None:
+            if grad_sync is not None:
+                grad_sync(list(netD.parameters()))
             opts[key].step()
-            knets.prefetch_weights([netD])      # joined with `prefetch` below (same side stream)
         return err
 
     se_errD, im_errD, st_errD = _concurrently(
@@ -334,11 +337,10 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
     Returns a dict of loss tensors (no host sync)."""
     exchange = grad_sync is not None and getattr(grad_sync, "enabled", True)
     step_inside = apply_optim and not exchange
-    out = stage_discriminators(nets, x, labels, early_generator=EARLY_G, opts=opts if step_inside else None)
-    sync_grads(nets, D_NETS, grad_sync)
-    if apply_optim and not step_inside:
-        for k in D_NETS:
-            opts[k].step()
+    out = stage_discriminators(nets, x, labels, early_generator=EARLY_G, opts=opts if apply_optim else None,
+                               grad_sync=grad_sync if exchange else None)
+    if not apply_optim:
+        sync_grads(nets, D_NETS, grad_sync)
     if step_inside and hasattr(opts["G"], "expect_backward"):
         opts["G"].expect_backward()      # the generator's Adam step starts inside the backward pass
     try:

@@ -178,6 +178,11 @@ int cpcsv_tanh_to_nchw(const float* z, int64_t ldz, int32_t N, int32_t C, int32_
 int cpcsv_head_conv_tanh_fwd(const void* a_hi, const void* a_lo, int32_t dtype, int32_t N, int32_t H,
                              int32_t W, int32_t C, const float* w, int32_t Co, float* y,
                              cpcsv_stream_t stream);
+/* img / img_seg heads as a pixel-major GEMM + gather (model.py:272-274,298-300,401-407): z [N*H*W, ldz]
+ * fp32 holds Z[p, tap*Co + co] = sum_c a[p, c] * w[co, c, tap] (cpcsv_conv_gemm, N = 9*Co padded);
+ * y[n, co, h, w] = tanh(sum over the 3x3 taps of Z at the shifted pixel), zero outside the image. */
+int cpcsv_head_gather_tanh(const float* z, int64_t ldz, int32_t N, int32_t H, int32_t W, int32_t Co,
+                           float* y, cpcsv_stream_t stream);
 /* backward of the heads: dz = dy * (1 - y^2), emitted directly as the 3x3 im2col of dz in
  * 16-bit: col[pix, tap*C + c] = dz[pix - delta_tap, c] (pitch ldp), which is both the dgrad
  * A operand and the wgrad B operand.  dy strided (n, c, h, w). */

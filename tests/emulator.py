@@ -299,6 +299,16 @@ def head_conv_tanh_fwd(hi, lo, w, y, dtype=1):
     y.copy_(torch.tanh(z))
 
 
+def head_gather_tanh(z, N, H, W, Co, y):
+    zz = z[:, :9 * Co].reshape(N, H, W, 9, Co).double()
+    pad = torch.nn.functional.pad(zz, (0, 0, 0, 0, 1, 1, 1, 1))          # pad W and H by 1
+    acc = torch.zeros(N, H, W, Co, dtype=torch.float64)
+    for ky in range(3):
+        for kx in range(3):
+            acc += pad[:, ky:ky + H, kx:kx + W, ky * 3 + kx]
+    y.copy_(torch.tanh(acc).permute(0, 3, 1, 2))
+
+
 def tanh_to_nchw(z, N, Cc, H, W, y):
     y.copy_(torch.tanh(z[:, :Cc]).reshape(N, H, W, Cc).permute(0, 3, 1, 2))
 

@@ -358,3 +358,14 @@ def test_planes_stay_current_across_graph_replays_that_update_the_weights():
     # no-grad generator calls run single-pass fp16 GEMMs: ~1.5e-3 relative on the images
     assert harness.rel_l2(img1, ref) < 5e-3, harness.rel_l2(img1, ref)
     assert harness.rel_l2(img0, ref) > 1e-2          # the updates really changed the output
+
+
+@pytest.mark.parametrize("Co", [1, 3])
+def test_head_gather_tanh(Co):
+    """second half of the img / img_seg heads (reference model.py:272-274): 3x3 gather of the per-pixel
+    tap products + tanh"""
+    N, H, W = 3, 16, 64
+    ld = 16 if Co == 1 else 32
+    z = rnd(N * H * W, ld, seed=31)
+    (g, _), (c, _) = both("head_gather_tanh", [z, N, H, W, Co], dict(y=torch.empty(N, Co, H, W)))
+    assert close(g["y"], c["y"], 1e-6)
