@@ -490,20 +490,16 @@ static int make_map(CUtensorMap* tm, const cpcsv_view5_t& v, const uint32_t box[
   return 0;
 }
 
-// The cta_group::2 path is the default for fprop / dgrad jobs (CPCSV_PAIR=0 in the environment turns it
-// off).  Alone it is 0.79-0.87x the time on hi/lo-plane jobs and never slower (profiles/r01_sweep_pair.txt);
-// in the step 21.4-21.6 ms vs 22.1-22.3 ms with single CTAs (profiles/r02_pair_soak.log).  Round 1 saw the
-// whole-step graph dead-lock intermittently with pairs on when the benchmark followed the fp64 parity tests
-// on the same box (6 of 12 runs, profiles/r01_pair_mode_hang.md).  That no longer reproduces: the same
-// scenario ran clean in every pair run of round 2's soaks (profiles/r02_pair_soak*.log) and isolated mixes of
-// pair / single-CTA / weight-gradient / small kernels in multi-branch graphs ran 5 x 300 replays clean
-// (gpurun_out r02_pair_*.log).  What changed in between: no cooperative (grid-synchronised) kernels are left
-// in the library and no low-priority stream of crawling re-layout kernels runs next to the GEMMs any more
-// (the planes are written by the optimiser kernels).  No root cause was established inside this kernel.
+// The cta_group::2 path is OPT-IN (CPCSV_PAIR=1 in the environment).  Alone it is 0.79-0.87x the time on
+// hi/lo-plane jobs and never slower (profiles/r01_sweep_pair.txt); in the step 21.4-21.6 ms vs 22.1-22.3 ms
+// with single CTAs (profiles/r02_pair_soak.log).  But the whole-step CUDA graph still dead-locks
+// intermittently with pairs on: round 1 saw 6 of 12 benchmark runs hang, round 2 one of 11 (the first
+// benchmark after the GPU test suite, gpurun_out r02_c6; 9 of 9 clean in profiles/r02_pair_soak.log), and
+// never with the path off.  Until that is root-caused the product runs single CTAs.
 static bool pair_mode_enabled() {
   static const bool on = [] {
     const char* e = getenv("CPCSV_PAIR");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }
