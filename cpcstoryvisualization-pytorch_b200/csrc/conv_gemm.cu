@@ -146,10 +146,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     fence_barrier_init();
   }
+  // Pair mode: the two CTAs of a cluster do not necessarily START at the same time.  Round 1 / 2 dead-lock
+  // (profiles/r02_pair_hang_rootcause.md, cuda-gdb on two hung replays): the leader had allocated its
+  // TMEM, given up its allocation permit with tcgen05.relinquish_alloc_permit.cta_group::2 -- which
+  // speaks for the PAIR -- and was waiting at the cluster barrier below, while the late peer never got
+  // through its own tcgen05.alloc.cta_group::2.  So: first make sure both CTAs are running, then both
+  // allocate, and the permit is only given up once both allocations are known to be done.
+  if (kPair) cluster_sync_all();
   if (warp == 2) {
     if (kPair) {
       tmem_alloc_pair(tmem_slot, kTmemCols);
-      tmem_relinquish_pair();
     } else {
       tmem_alloc(tmem_slot, kTmemCols);
       tmem_relinquish();
@@ -158,6 +164,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tc_fence_before();
   if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  if (kPair && warp == 2) tmem_relinquish_pair();
   const uint32_t tmem_base = *tmem_slot;
 
   const uint32_t stage_tx = static_cast<uint32_t>(P.planes) * (kAPlaneBytes + P.b_plane_bytes);
