@@ -497,16 +497,17 @@ static int make_map(CUtensorMap* tm, const cpcsv_view5_t& v, const uint32_t box[
   return 0;
 }
 
-// The cta_group::2 path is OPT-IN (CPCSV_PAIR=1 in the environment).  Alone it is 0.79-0.87x the time on
-// hi/lo-plane jobs and never slower (profiles/r01_sweep_pair.txt); in the step 21.4-21.6 ms vs 22.1-22.3 ms
-// with single CTAs (profiles/r02_pair_soak.log).  But the whole-step CUDA graph still dead-locks
-// intermittently with pairs on: round 1 saw 6 of 12 benchmark runs hang, round 2 one of 11 (the first
-// benchmark after the GPU test suite, gpurun_out r02_c6; 9 of 9 clean in profiles/r02_pair_soak.log), and
-// never with the path off.  Until that is root-caused the product runs single CTAs.
+// The cta_group::2 path is the default for fprop / dgrad jobs (CPCSV_PAIR=0 in the environment turns it
+// off).  Alone it is 0.79-0.87x the time on hi/lo-plane jobs and never slower (profiles/r01_sweep_pair.txt);
+// in the step 21.4-21.6 ms vs 22.1-22.3 ms with single CTAs (profiles/r02_pair_soak.log).  The intermittent
+// dead-lock of round 1 (6 of 12 runs) and of this round's first soaks (2 of 7 processes) was the TMEM
+// allocation handshake between the two CTAs of a cluster (kernel prologue above;
+// profiles/r02_pair_hang_rootcause.md); with the fix 32 of 32 processes x 150 whole-step graph replays ran
+// clean under the conditions that hung before (profiles/r02_pair_trace_after_fix.log).
 static bool pair_mode_enabled() {
   static const bool on = [] {
     const char* e = getenv("CPCSV_PAIR");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }();
   return on;
 }
