@@ -450,7 +450,7 @@ def main():
                     help="e2e loop: copy the next batch on a copy stream while the current step replays "
                          "(trainer.GraphedStep.load_async; opt-in until measured on a GPU)")
     ap.add_argument("--whole-graph", action="store_true",
-                    help="N > 1: capture the NCCL all-reduces inside ONE step graph (experimental)")
+                    help="(default since round 2) N > 1: the NCCL all-reduces are captured inside the ONE step graph")
     ap.add_argument("--segmented", action="store_true",
                     help="three CUDA graphs with the gradient all-reduces issued eagerly between them "
                          "instead of one graph that contains them")
@@ -465,10 +465,9 @@ def main():
         run_large_config(args)
         return
     args.warmup = max(args.warmup, 3)
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.whole_graph:
-        # capturing the NCCL all-reduces inside the one-graph step hung on the 2-GPU box (r01):
-        # multi-GPU runs use the three-graph step with the collectives between the graphs
-        args.segmented = True
+    # N > 1: ONE graph per step with the NCCL all-reduces captured inside (each discriminator's exchange runs
+    # under the other discriminators' compute).  Round 1's "hang" of this variant was the process group
+    # tear-down at exit, not the replays (see the end of main); --segmented keeps the three-graph variant.
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -615,7 +614,14 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing the communicator down: destroying a process group whose collectives were
+        # captured into CUDA graphs that are still alive blocked at exit on the 2-GPU box
+        # (gpurun_out r02_multi2_whole.log).  Every rank is done (barrier), the line is out.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

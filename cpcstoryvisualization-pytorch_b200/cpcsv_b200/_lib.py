@@ -71,8 +71,6 @@ SIGNATURES = {
     "cpcsv_im2col_small": [_p, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p,
                            _i32, _i32, _p],
     "cpcsv_col2im_small": [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
-    "cpcsv_tanh_to_nchw": [_p, _i64, _i32, _i32, _i32, _i32, _p, _p],
-    "cpcsv_head_conv_tanh_fwd": [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p],
     "cpcsv_head_gather_tanh": [_p, _i64, _i32, _i32, _i32, _i32, _p, _p],
     "cpcsv_tanh_bwd_im2col": [_p, _i64, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "cpcsv_pack_matrix": [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i32, _p],

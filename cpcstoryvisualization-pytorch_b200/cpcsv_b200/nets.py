@@ -16,9 +16,6 @@ _CACHE = engine.WeightCache()
 # activation chain (they depend on the weights only).  No measurable gain on B200 (23.3 ms either
 # way): off by default, one less layer of nested stream forks.
 SN_AHEAD = False
-# img / img_seg heads: pixel-major GEMM + gather (True) or the direct CUDA-core kernel (False)
-import os as _os  # noqa: E402
-HEAD_VIA_GEMM = _os.environ.get("CPCSV_HEAD_GEMM", "1") != "0"
 
 
 def weight_cache():
@@ -368,24 +365,18 @@ class TrunkRunner:
         return _CACHE.get((id(w), "head_fwd", planes, dtype), w, build)
 
     def _head_fwd(self, a, w, Co, name):
-        """img / img_seg: conv3x3 -> tanh with 3 / 1 output channels (reference model.py:272-274, 298-300).
-        HEAD_VIA_GEMM: one pixel-major tensor-core GEMM Z[p, tap*Co + co] (the activation is read once,
-        N = 9*Co padded to 16 / 32) and a gather-tanh kernel over the L2-resident Z; otherwise the direct
-        CUDA-core kernel on the operand planes."""
+        """img / img_seg: conv3x3 -> tanh with 3 / 1 output channels (reference model.py:272-274, 298-300):
+        one pixel-major tensor-core GEMM Z[p, tap*Co + co] (the activation is read once, N = 9*Co padded to
+        16 / 32) and a gather-tanh kernel over the L2-resident Z.  In the step 21.33 vs 21.47 ms against the
+        direct CUDA-core kernel of round 1 (gpurun_out r02_c6)."""
         dev = a.hi.device
         tp = self.tape
         y = _e((a.N, Co, a.H, a.W), dev)
-        if HEAD_VIA_GEMM:
-            wp = self._head_pack_fwd(w, tp.planes, tp.dtype)
-            z = _e((a.rows, wp[0].shape[0]), dev)
-            planes = [a.hi.view(a.rows, a.C), a.lo.view(a.rows, a.C) if tp.planes == 2 else None]
-            ops.conv_gemm(conv.gemm_nt(planes, wp, z, dtype=tp.dtype))
-            ops.head_gather_tanh(z, a.N, a.H, a.W, Co, y)
-            return y
-        wd = w.detach()
-        if wd.shape[1] != a.C:                       # channel-padded activation: zero weight columns
-            wd = torch.nn.functional.pad(wd, (0, 0, 0, 0, 0, a.C - wd.shape[1]))
-        ops.head_conv_tanh_fwd(a.hi, a.lo if tp.planes == 2 else None, wd.contiguous(), y, tp.dtype)
+        wp = self._head_pack_fwd(w, tp.planes, tp.dtype)
+        z = _e((a.rows, wp[0].shape[0]), dev)
+        planes = [a.hi.view(a.rows, a.C), a.lo.view(a.rows, a.C) if tp.planes == 2 else None]
+        ops.conv_gemm(conv.gemm_nt(planes, wp, z, dtype=tp.dtype))
+        ops.head_gather_tanh(z, a.N, a.H, a.W, Co, y)
         return y
 
     def _head_bwd(self, a, w, y, dy, need_w, pg, name):

@@ -231,29 +231,12 @@ def col2im_small(dcol, N, Cc, H, W, k, s, p, dx):
         _stream()), "cpcsv_col2im_small")
 
 
-def head_conv_tanh_fwd(hi, lo, w, y, dtype=BF16):
-    """y[N, Co, H, W] = tanh(conv3x3(hi + lo, w)); hi / lo NHWC 16-bit planes, w [Co, C, 3, 3] fp32"""
-    N, H, W, Cc = hi.shape
-    Co = w.shape[0]
-    assert hi.is_contiguous() and (lo is None or lo.is_contiguous()) and w.is_contiguous() and y.is_contiguous()
-    assert tuple(w.shape) == (Co, Cc, 3, 3) and tuple(y.shape) == (N, Co, H, W)
-    _lib.check(_lib.load().cpcsv_head_conv_tanh_fwd(
-        _ptr(hi, TORCH16[dtype]), _ptr(lo, TORCH16[dtype]), dtype, N, H, W, Cc, _ptr(w, torch.float32), Co,
-        _ptr(y, torch.float32), _stream()), "cpcsv_head_conv_tanh_fwd")
-
-
 def head_gather_tanh(z, N, H, W, Co, y):
     """y[n, co, h, w] = tanh(sum_{ky,kx} z[(n, h+ky-1, w+kx-1), (ky*3+kx)*Co + co]); z [N*H*W, ld] fp32"""
     assert z.dim() == 2 and z.stride(1) == 1 and z.shape[0] == N * H * W and y.is_contiguous()
     assert tuple(y.shape) == (N, Co, H, W)
     _lib.check(_lib.load().cpcsv_head_gather_tanh(_ptr(z, torch.float32), z.stride(0), N, H, W, Co,
                                                   _ptr(y, torch.float32), _stream()), "cpcsv_head_gather_tanh")
-
-
-def tanh_to_nchw(z, N, Cc, H, W, y):
-    assert y.is_contiguous()
-    _lib.check(_lib.load().cpcsv_tanh_to_nchw(_ptr(z, torch.float32), z.stride(0), N, Cc, H, W,
-                                              _ptr(y, torch.float32), _stream()), "cpcsv_tanh_to_nchw")
 
 
 def tanh_bwd_im2col(dy, y, col, dtype=BF16):

@@ -167,17 +167,6 @@ int cpcsv_im2col_small(const float* x, int32_t N, int32_t C, int32_t H, int32_t 
 /* adjoint of im2col_small: dx[n, c, h, w] (contiguous NCHW fp32) = sum over taps of dcol */
 int cpcsv_col2im_small(const float* dcol, int64_t ldc, int32_t N, int32_t C, int32_t H, int32_t W,
                        int32_t k, int32_t s, int32_t p, float* dx, cpcsv_stream_t stream);
-/* img / img_seg heads (model.py:272-274,298-300): y = tanh(z[:, :C]) written NCHW fp32. */
-int cpcsv_tanh_to_nchw(const float* z, int64_t ldz, int32_t N, int32_t C, int32_t H, int32_t W,
-                       float* y, cpcsv_stream_t stream);
-/* img / img_seg heads, forward in one launch (model.py:272-274,298-300,401-407): direct 3x3
- * convolution (pad 1, no bias) of the NHWC 16-bit operand planes a_hi (+ a_lo, may be NULL)
- * [N, H, W, C] with the fp32 weight w [Co, C, 3, 3], then tanh, written NCHW fp32
- * y [N, Co, H, W].  fp32 arithmetic on the activation value hi + lo.  Requires H % 8 == 0,
- * W % 64 == 0, C % 16 == 0, 1 <= Co <= 3.  dtype: 0 fp16, 1 bf16. */
-int cpcsv_head_conv_tanh_fwd(const void* a_hi, const void* a_lo, int32_t dtype, int32_t N, int32_t H,
-                             int32_t W, int32_t C, const float* w, int32_t Co, float* y,
-                             cpcsv_stream_t stream);
 /* img / img_seg heads as a pixel-major GEMM + gather (model.py:272-274,298-300,401-407): z [N*H*W, ldz]
  * fp32 holds Z[p, tap*Co + co] = sum_c a[p, c] * w[co, c, tap] (cpcsv_conv_gemm, N = 9*Co padded);
  * y[n, co, h, w] = tanh(sum over the 3x3 taps of Z at the shifted pixel), zero outside the image. */

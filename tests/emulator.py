@@ -293,12 +293,6 @@ def col2im_small(dcol, N, Cc, H, W, k, s, p, dx):
     dx.copy_(torch.nn.functional.fold(d, (H, W), k, padding=p, stride=s))
 
 
-def head_conv_tanh_fwd(hi, lo, w, y, dtype=1):
-    a = hi.double() + (lo.double() if lo is not None else 0.0)
-    z = torch.nn.functional.conv2d(a.permute(0, 3, 1, 2), w.double(), padding=1)
-    y.copy_(torch.tanh(z))
-
-
 def head_gather_tanh(z, N, H, W, Co, y):
     zz = z[:, :9 * Co].reshape(N, H, W, 9, Co).double()
     pad = torch.nn.functional.pad(zz, (0, 0, 0, 0, 1, 1, 1, 1))          # pad W and H by 1
@@ -307,10 +301,6 @@ def head_gather_tanh(z, N, H, W, Co, y):
         for kx in range(3):
             acc += pad[:, ky:ky + H, kx:kx + W, ky * 3 + kx]
     y.copy_(torch.tanh(acc).permute(0, 3, 1, 2))
-
-
-def tanh_to_nchw(z, N, Cc, H, W, y):
-    y.copy_(torch.tanh(z[:, :Cc]).reshape(N, H, W, Cc).permute(0, 3, 1, 2))
 
 
 def tanh_bwd_im2col(dy, y, col, dtype=1):

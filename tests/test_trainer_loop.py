@@ -154,7 +154,7 @@ def _capture_paths(monkeypatch, trainer, p, nets, st, im, labels):
     monkeypatch.setattr(torch.cuda, "CUDAGraph", _FakeGraph)
     monkeypatch.setattr(torch.cuda, "graph", _FakeCapture)
     noise = synth.make_noise(p, 2)
-    for exchange in (False, True):
+    for exchange, segmented in ((False, False), (True, False), (True, True)):
         nn_ = copy.deepcopy(nets)
         opts = trainer.build_optimizers(nn_, fused=False)
         calls = []
@@ -168,8 +168,9 @@ def _capture_paths(monkeypatch, trainer, p, nets, st, im, labels):
                 calls.append((len(list(params)), inplace))
                 return orig_call(params, inplace=inplace)
         gs = trainer.GraphedStep(nn_, opts, labels, {k: v.clone() for k, v in st.items()},
-                                 {k: v.clone() for k, v in im.items()}, grad_sync=Spy() if exchange else None)
-        assert gs.segmented == exchange
+                                 {k: v.clone() for k, v in im.items()}, grad_sync=Spy() if exchange else None,
+                                 segmented=segmented)
+        assert gs.segmented == segmented
         bodies = []
 
         def run_capture():
@@ -196,10 +197,13 @@ def _capture_paths(monkeypatch, trainer, p, nets, st, im, labels):
         losses = gs.losses()
         assert all(v == v for v in losses.values())          # finite, not NaN
         if exchange:
-            # D_se, D_im, D_st after the discriminator stage, G after the generator stage
+            # D_se, D_im, D_st (each between its backward pass and its Adam step), G after the generator stage
             assert len(calls) == 4, calls
-            # replayed optimiser steps read the captured gradient memory: the exchange must be in place
-            assert all(inplace for _, inplace in calls), calls
+            # segmented: replayed optimiser steps read the captured gradient memory, the exchange between the
+            # graphs must be in place; whole graph: the exchange is part of the captured step
+            assert all(inplace == segmented for _, inplace in calls), calls
+        gs.close()
+        assert gs.graph is None
 
 
 def test_snapshot_model_copy_is_importable_under_another_name(tmp_path):

@@ -104,23 +104,32 @@ if __name__ == "__main__":
     b = planes((32768, 640))
     out = torch.empty(N, 32768, device=dev)
     report("fc fwd", conv.gemm_nt(a, b, out), N * 640 * 32768, 3)
-    # direct head kernels (alone on the GPU)
+    # heads: pixel-major GEMM (N = 9*Co padded) + gather-tanh (alone on the GPU)
     for C, Co, two in ((128, 3, True), (128, 3, False), (64, 1, True), (64, 1, False)):
-        hi = torch.randn(N, 64, 64, C, device=dev).to(torch.bfloat16)
+        hi = torch.randn(N * 64 * 64, C, device=dev).to(torch.bfloat16)
         lo = hi.clone() if two else None
-        w = torch.randn(Co, C, 3, 3, device=dev) * 0.05
+        Np = 32 if Co == 3 else 16
+        wp = [torch.randn(Np, C, device=dev).to(torch.bfloat16), None]
+        if two:
+            wp[1] = wp[0].clone()
+        z = torch.empty(N * 64 * 64, Np, device=dev)
         y = torch.empty(N, Co, 64, 64, device=dev)
-        ops.head_conv_tanh_fwd(hi, lo, w, y)
+
+        def run():
+            ops.conv_gemm(conv.gemm_nt([hi, lo], wp, z))
+            ops.head_gather_tanh(z, N, 64, 64, Co, y)
+        run()
         torch.cuda.synchronize()
         ts = []
         for _ in range(5):
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
             e0.record()
-            ops.head_conv_tanh_fwd(hi, lo, w, y)
+            run()
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ts.sort()
         gb = hi.numel() * 2 * (2 if two else 1) / 1e9
-        print("head conv C=%d Co=%d planes=%d   %.1f us  (%.0f GB/s of operand planes)" % (
+        print("head C=%d Co=%d planes=%d   %.1f us  (%.0f GB/s of operand planes)" % (
             C, Co, 2 if two else 1, ts[2] * 1e3, gb / (ts[2] * 1e-3)))
+

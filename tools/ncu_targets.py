@@ -25,10 +25,12 @@ def bf(*shape):
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "head"):
-        hi, lo = bf(N, 64, 64, 128), bf(N, 64, 64, 128)
-        w = torch.randn(3, 128, 3, 3, device=dev) * 0.05
+        hi, lo = bf(N * 64 * 64, 128), bf(N * 64 * 64, 128)
+        wp = [bf(32, 128), bf(32, 128)]
+        z = torch.empty(N * 64 * 64, 32, device=dev)
         y = torch.empty(N, 3, 64, 64, device=dev)
-        ops.head_conv_tanh_fwd(hi, lo, w, y)                         # launch 0: img head, 2 planes
+        ops.conv_gemm(conv.gemm_nt([hi, lo], wp, z))                 # launch 0: img head GEMM, 2 planes
+        ops.head_gather_tanh(z, N, 64, 64, 3, y)                     # launch 0b: gather + tanh
     if which in ("all", "gemm"):
         # launch 1: upsample3 forward, hi/lo split operands (3 MMAs / k-step)
         x2 = [bf(N, 16, 16, 512), bf(N, 16, 16, 512)]
