@@ -92,6 +92,8 @@ SIGNATURES = {
     "cpcsv_affine_sigmoid_bwd": [_p, _p, _p, _p, _p, _i64, _p],
     "cpcsv_spectral_sigma": [_p, _i32, _i32, _p, _p, _i32, _f32, _p, _p, _p, _p],
     "cpcsv_spectral_bwd": [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p],
+    "cpcsv_spectral_bwd_apply": [_p, _p, _p, _p, _p, _i32, _i32, _p, _p],
+    "cpcsv_unpack_conv_wgrad_dot": [_p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p],
     "cpcsv_adam_tick": [_p, C.c_double, C.c_double, _p, _p],
     "cpcsv_adam_multi": [C.POINTER(AdamTensor), _i32, C.POINTER(AdamHyper), _p],
     "cpcsv_adam_pack_conv": [_p, _p, _p, _p, _i32, _i32, _i32, _i32, C.POINTER(AdamHyper), C.POINTER(Plane),

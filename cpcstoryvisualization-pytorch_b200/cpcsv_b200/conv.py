@@ -41,9 +41,11 @@ def pick_splits(tiles, iters, penalty=0.04):
     if iters < 8:
         return 1
     if tiles * 8 < NUM_SMS:
-        # a handful of output tiles with a very long reduction (first-layer / head weight
-        # gradients: K = all pixels): one split per SM
-        return max(1, min(-(-NUM_SMS // tiles), iters // 4))
+        # a handful of output tiles with a very long reduction (first-layer / head weight gradients,
+        # K = all pixels; the 16-tap weight gradients of the 64x64 layers): as many splits as fill ONE wave
+        # (rounding up gave 160 work items on 148 SMs, i.e. a second wave with 12 of them: 0.54 wave efficiency,
+        # profiles/r01_gemm_bounds_single.txt)
+        return max(1, min(NUM_SMS // tiles, iters // 4))
     best, best_score = 1, -1.0
     for s in range(1, min(8, iters // 4) + 1):
         n = tiles * s

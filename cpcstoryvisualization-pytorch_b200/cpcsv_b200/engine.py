@@ -378,8 +378,15 @@ class ConvNode:
             job = conv.conv_s2_wgrad(dz, x.hi, dwt)
         ops.conv_gemm(job)
         g = _e(tuple(self.w.shape), dev)
-        ops.unpack_conv_wgrad(dwt, self.Co_pad * self.Ci_pad, self.Ci_pad, ukind, None, g)
-        self.dW = self.sn.backward(g, self.w) if self.sn is not None else g
+        if self.sn is not None and ukind in (0, 2):
+            # spectral norm: sum(dW_eff .* W_orig) comes out of the same pass that un-packs the gradient
+            dot = torch.zeros(1, device=dev)
+            ops.unpack_conv_wgrad_dot(dwt, self.Co_pad * self.Ci_pad, self.Ci_pad, ukind, None, g,
+                                      self.w.detach(), dot)
+            self.dW = self.sn.backward(g, self.w, dot)
+        else:
+            ops.unpack_conv_wgrad(dwt, self.Co_pad * self.Ci_pad, self.Ci_pad, ukind, None, g)
+            self.dW = self.sn.backward(g, self.w) if self.sn is not None else g
 
 
 class SpectralNorm:
@@ -408,9 +415,13 @@ class SpectralNorm:
         StateOrder.after(self.u)
         return sig[1:2]
 
-    def backward(self, g, w_orig):
+    def backward(self, g, w_orig, dot=None):
+        """``dot``: sum(g * w_orig) already accumulated by the caller -> one in-place pass"""
         u, v, sig = self.saved
         R = w_orig.shape[0]
+        if dot is not None:
+            ops.spectral_bwd_apply(g.view(R, -1), u, v, sig[0:1], dot, g.view(R, -1))
+            return g
         dw = torch.empty_like(g)
         ops.spectral_bwd(g.view(R, -1), w_orig.detach().view(R, -1), u, v, sig[0:1], dw.view(R, -1),
                          _e((4,), g.device))

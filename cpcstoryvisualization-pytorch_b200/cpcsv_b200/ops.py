@@ -276,6 +276,16 @@ def unpack_conv_wgrad(dwt, mat_stride, ldc, kind, alpha, dw):
         _ptr(dw, torch.float32), _stream()), "cpcsv_unpack_conv_wgrad")
 
 
+def unpack_conv_wgrad_dot(dwt, mat_stride, ldc, kind, alpha, dw, w, dot):
+    """unpack_conv_wgrad (kinds 0 / 2) + dot[0] += sum(dw * w)"""
+    Cout, Cin, kh, kw = dw.shape
+    assert dw.is_contiguous() and w.is_contiguous() and tuple(w.shape) == tuple(dw.shape)
+    _lib.check(_lib.load().cpcsv_unpack_conv_wgrad_dot(
+        _ptr(dwt, torch.float32), mat_stride, ldc, Cout, Cin, kh, kw, kind, _ptr(alpha),
+        _ptr(dw, torch.float32), _ptr(w, torch.float32), _ptr(dot, torch.float32), _stream()),
+        "cpcsv_unpack_conv_wgrad_dot")
+
+
 # ------------------------------------------------------------------ conditioning path (fp32)
 def linear_f32(x, w, bias, y, accumulate=False):
     """y[M,N] = x[M,K] @ w[N,K]^T + bias."""
@@ -446,3 +456,12 @@ def adam_pack_fc(w, g, m, v, C_, P, Cp, Kp, fwd16=None, fwd_hi=None, fwd_lo=None
         _ptr(w, torch.float32), _ptr(g, torch.float32), _ptr(m, torch.float32), _ptr(v, torch.float32), C_, K, P,
         Cp, Kp, C.byref(h) if h is not None else None, _ptr(fwd16, torch.float16), _ptr(fwd_hi, torch.bfloat16),
         _ptr(fwd_lo, torch.bfloat16), _ptr(bwd, torch.bfloat16), _stream()), "cpcsv_adam_pack_fc")
+
+
+def spectral_bwd_apply(g2d, u, v, sigma, dot, dw2d):
+    """dW = (G - (dot / sigma) u v^T) / sigma with dot = sum(G * W) given; dw2d may be g2d"""
+    R, Cc = g2d.shape
+    assert g2d.is_contiguous() and dw2d.is_contiguous()
+    _lib.check(_lib.load().cpcsv_spectral_bwd_apply(
+        _ptr(g2d, torch.float32), _ptr(u), _ptr(v), _ptr(sigma), _ptr(dot, torch.float32), R, Cc,
+        _ptr(dw2d, torch.float32), _stream()), "cpcsv_spectral_bwd_apply")

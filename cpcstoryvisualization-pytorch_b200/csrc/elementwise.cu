@@ -357,10 +357,13 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
 // Coalesced variant for the untransposed layouts dwt[tap][co][ci]: one block = one `co` and 128
 // consecutive `ci`; reads are contiguous in ci, the T = kh*kw values of every (co, ci) are
 // transposed through shared memory so the writes to dw[co][ci][t] are contiguous too.
+// wdot / dot (optional): also accumulates sum(dw .* wdot) into *dot -- the scalar the spectral-norm
+// backward needs (cpcsv_spectral_bwd_apply), without another pass over the gradient.
 __global__ void __launch_bounds__(128)
 unpack_conv_wgrad_rows_kernel(const float* __restrict__ dwt, int64_t mat_stride, int64_t ldc, int Cout,
                               int Cin, int T, int kind, const float* __restrict__ alpha,
-                              float* __restrict__ dw) {
+                              float* __restrict__ dw, const float* __restrict__ wdot,
+                              float* __restrict__ dot) {
   __shared__ float s[128 * 16];
   const int co = blockIdx.y;
   const int ci0 = blockIdx.x * 128;
@@ -398,8 +401,22 @@ unpack_conv_wgrad_rows_kernel(const float* __restrict__ dwt, int64_t mat_stride,
   }
   __syncthreads();
   const int nvalid = min(128, Cin - ci0);
-  float* dst = dw + (static_cast<int64_t>(co) * Cin + ci0) * T;
-  for (int j = threadIdx.x; j < nvalid * T; j += 128) dst[j] = s[j];
+  const int64_t base = (static_cast<int64_t>(co) * Cin + ci0) * T;
+  float* dst = dw + base;
+  float part = 0.f;
+  for (int j = threadIdx.x; j < nvalid * T; j += 128) {
+    const float g = s[j];
+    dst[j] = g;
+    if (wdot) part = fmaf(g, wdot[base + j], part);
+  }
+  if (wdot) {
+    __shared__ float red[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(dot, red[0] + red[1] + red[2] + red[3]);
+  }
 }
 
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwt, int64_t mat_stride,
@@ -563,10 +580,23 @@ extern "C" int cpcsv_unpack_conv_wgrad(const float* dwt, int64_t mat_stride, int
   if ((kind == 0 || kind == 2) && kh * kw <= 16) {
     dim3 grid(static_cast<unsigned>(ceil_div(Cin, 128)), static_cast<unsigned>(Cout));
     unpack_conv_wgrad_rows_kernel<<<grid, 128, 0, STREAM(stream)>>>(dwt, mat_stride, ldc, Cout, Cin,
-                                                                   kh * kw, kind, alpha, dw);
+                                                                   kh * kw, kind, alpha, dw, nullptr, nullptr);
     return launched("unpack_conv_wgrad");
   }
   unpack_conv_wgrad_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(
       dwt, mat_stride, ldc, Cout, Cin, kh, kw, kind, alpha, dw);
   return launched("unpack_conv_wgrad");
+}
+
+extern "C" int cpcsv_unpack_conv_wgrad_dot(const float* dwt, int64_t mat_stride, int64_t ldc,
+                                           int32_t Cout, int32_t Cin, int32_t kh, int32_t kw,
+                                           int32_t kind, const float* alpha, float* dw, const float* w,
+                                           float* dot, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(dwt && dw && w && dot && (kind == 0 || kind == 2) && kh * kw <= 16,
+                "unpack_conv_wgrad_dot: args (untransposed kinds, <= 16 taps)");
+  CPCSV_REQUIRE(kind < 2 || (kh == 3 && kw == 3), "unpack_conv_wgrad_dot: sub-pixel merge needs 3x3");
+  dim3 grid(static_cast<unsigned>(ceil_div(Cin, 128)), static_cast<unsigned>(Cout));
+  unpack_conv_wgrad_rows_kernel<<<grid, 128, 0, STREAM(stream)>>>(dwt, mat_stride, ldc, Cout, Cin, kh * kw,
+                                                                 kind, alpha, dw, w, dot);
+  return launched("unpack_conv_wgrad_dot");
 }

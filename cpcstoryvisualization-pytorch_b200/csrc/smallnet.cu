@@ -398,17 +398,19 @@ __global__ void sn_bwd_dot_kernel(const float* __restrict__ G, const float* __re
   const float s = block_sum(acc, sh);
   if (threadIdx.x == 0) atomicAdd(acc_out, s);
 }
-__global__ void sn_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ u,
-                                    const float* __restrict__ v, const float* __restrict__ sigma,
-                                    const float* __restrict__ gw, int R, int C,
-                                    float* __restrict__ dW) {
-  const int64_t n = static_cast<int64_t>(R) * C;
+// one block per row chunk (blockIdx.y walks the rows, blockIdx.x the columns): no per-element division;
+// G and dW may be the same buffer
+__global__ void __launch_bounds__(256)
+sn_bwd_apply_kernel(const float* G, const float* __restrict__ u, const float* __restrict__ v,
+                    const float* __restrict__ sigma, const float* __restrict__ gw, int R, int C, float* dW) {
   const float inv = 1.f / *sigma;
   const float coef = *gw * inv;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<int64_t>(r) * C);
-    dW[i] = (G[i] - coef * u[r] * v[c]) * inv;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  const float vc = coef * v[c];
+  for (int r = blockIdx.y; r < R; r += gridDim.y) {
+    const int64_t i = static_cast<int64_t>(r) * C + c;
+    dW[i] = (G[i] - u[r] * vc) * inv;
   }
 }
 
@@ -569,6 +571,24 @@ extern "C" int cpcsv_spectral_bwd(const float* G, const float* W, const float* u
   sn_bwd_dot_kernel<<<blocks, 256, 0, stream>>>(G, W, n, scratch);
   int rc = launched("spectral_bwd/dot");
   if (rc) return rc;
-  sn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(G, u, v, sigma, scratch, R, C, dW);
+  {
+    const unsigned gx = static_cast<unsigned>(ceil_div(C, 256));
+    int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 8, gx);
+    if (gy > R) gy = R;
+    sn_bwd_apply_kernel<<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, stream>>>(G, u, v, sigma, scratch, R, C, dW);
+  }
   return launched("spectral_bwd/apply");
+}
+
+// second half alone: *dot = sum(G .* W) has already been accumulated (cpcsv_unpack_conv_wgrad_dot)
+extern "C" int cpcsv_spectral_bwd_apply(const float* G, const float* u, const float* v, const float* sigma,
+                                        const float* dot, int32_t R, int32_t C, float* dW,
+                                        cpcsv_stream_t stream_) {
+  cudaStream_t stream = STREAM(stream_);
+  CPCSV_REQUIRE(G && u && v && sigma && dot && dW && R > 0 && C > 0, "spectral_bwd_apply: args");
+  const unsigned gx = static_cast<unsigned>(ceil_div(C, 256));
+  int64_t gy = ceil_div(static_cast<int64_t>(num_sms()) * 8, gx);
+  if (gy > R) gy = R;
+  sn_bwd_apply_kernel<<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, stream>>>(G, u, v, sigma, dot, R, C, dW);
+  return launched("spectral_bwd_apply");
 }

@@ -207,6 +207,12 @@ int cpcsv_unpack_conv_wgrad(const float* dwt, int64_t mat_stride, int64_t ldc, i
                             int32_t Cin, int32_t kh, int32_t kw, int32_t kind, const float* alpha,
                             float* dw, cpcsv_stream_t stream);
 
+/* cpcsv_unpack_conv_wgrad (kinds 0 / 2) that also adds sum(dW .* w) into *dot (caller-zeroed): the scalar
+ * of the spectral-norm backward, without another pass over the gradient */
+int cpcsv_unpack_conv_wgrad_dot(const float* dwt, int64_t mat_stride, int64_t ldc, int32_t Cout,
+                                int32_t Cin, int32_t kh, int32_t kw, int32_t kind, const float* alpha,
+                                float* dw, const float* w, float* dot, cpcsv_stream_t stream);
+
 /* ------------------------------------------------------------- conditioning path (fp32)
  * CA_NET (model.py:37-65), GRUCells (model.py:223-224,313-346), m_net/c_net/image_net/
  * filter_net Linear+BN1d (model.py:250-257,302-308), DynamicFilterLayer1D (layers.py:62-80).
@@ -265,6 +271,11 @@ int cpcsv_spectral_sigma(const float* W, int32_t R, int32_t C, float* u, float* 
 int cpcsv_spectral_bwd(const float* G, const float* W, const float* u, const float* v,
                        const float* sigma, int32_t R, int32_t C, float* dW, float* scratch,
                        cpcsv_stream_t stream);
+/* cpcsv_spectral_bwd with *dot = sum(G .* W) already known (cpcsv_unpack_conv_wgrad_dot):
+ * dW = (G - (dot / sigma) u v^T) / sigma; G and dW may alias */
+int cpcsv_spectral_bwd_apply(const float* G, const float* u, const float* v, const float* sigma,
+                             const float* dot, int32_t R, int32_t C, float* dW, cpcsv_stream_t stream);
+
 
 /* ------------------------------------------------------------------ optimiser (Adam)
  * optim.Adam(lr, betas=(0.5, 0.999)) of reference trainer.py:212-220, stepped at trainer.py:345-346

@@ -557,3 +557,13 @@ def adam_pack_fc(w, g, m, v, C_, P, Cp, Kp, fwd16=None, fwd_hi=None, fwd_lo=None
                 fwd_lo.copy_(l)
         if bwd is not None:
             bwd.copy_(full.t().to(torch.bfloat16))
+
+
+def unpack_conv_wgrad_dot(dwt, mat_stride, ldc, kind, alpha, dw, w, dot):
+    unpack_conv_wgrad(dwt, mat_stride, ldc, kind, alpha, dw)
+    dot[0] += float((dw.double() * w.double()).sum())
+
+
+def spectral_bwd_apply(g2d, u, v, sigma, dot, dw2d):
+    s = float(sigma)
+    dw2d.copy_((g2d - (float(dot[0]) / s) * torch.outer(u, v)) / s)

@@ -350,3 +350,30 @@ def test_head_gather_tanh(Co):
     z = rnd(N * H * W, ld, seed=31)
     (g, _), (c, _) = both("head_gather_tanh", [z, N, H, W, Co], dict(y=torch.empty(N, Co, H, W)))
     assert close(g["y"], c["y"], 1e-6)
+
+
+def test_unpack_wgrad_dot_and_spectral_apply():
+    """the fused form of the spectral-norm backward: sum(dW .* W) out of the un-packing pass, then one
+    in-place pass -- same result as cpcsv_unpack_conv_wgrad + cpcsv_spectral_bwd"""
+    Co, Ci, k = 24, 200, 4
+    rp, cp = 64, 256
+    dwt = rnd(k * k * rp, cp, seed=61)
+    w = rnd(Co, Ci, k, k, seed=62)
+    u, v = rnd(Co, seed=63), rnd(Ci * k * k, seed=64)
+    sigma = torch.tensor([1.7])
+    res = {}
+    for dev, mod in (("cuda", ops), ("cpu", emu)):
+        g = torch.empty(Co, Ci, k, k, device=dev)
+        dot = torch.zeros(1, device=dev)
+        mod.unpack_conv_wgrad_dot(dwt.to(dev), rp * cp, cp, 0, None, g, w.to(dev), dot)
+        g_ref = torch.empty(Co, Ci, k, k, device=dev)
+        mod.unpack_conv_wgrad(dwt.to(dev), rp * cp, cp, 0, None, g_ref)
+        assert torch.equal(g, g_ref)
+        dw_ref = torch.empty(Co, Ci * k * k, device=dev)
+        mod.spectral_bwd(g_ref.view(Co, -1), w.to(dev).view(Co, -1), u.to(dev), v.to(dev), sigma.to(dev), dw_ref,
+                         torch.zeros(4, device=dev))
+        mod.spectral_bwd_apply(g.view(Co, -1), u.to(dev), v.to(dev), sigma.to(dev), dot, g.view(Co, -1))
+        res[dev] = (g.cpu().view(Co, -1), dw_ref.cpu(), float(dot))
+    assert close(res["cuda"][0], res["cuda"][1], 1e-5)
+    assert close(res["cuda"][0], res["cpu"][0], 1e-5)
+    assert abs(res["cuda"][2] - res["cpu"][2]) <= 1e-4 * abs(res["cpu"][2]) + 1e-4
