@@ -20,6 +20,15 @@ from .ops import ACT_NONE, ACT_RELU, ACT_LRELU, BF16  # noqa: F401
 # derived inside the apply kernel (cpcsv_bn_norm_act_pack): at most 2 launches between consecutive GEMMs.
 EPILOGUE_STATS = True
 
+# Operand precision of NO-GRAD network calls (the fakes for the discriminator update, inference).  Default:
+# single-pass fp16 (SURVEY.md Appendix E recipe R*), which leaves ~1.5e-3 relative error on the images and is
+# what bounds the discriminator-gradient parity (cosine 0.9998 at the cfg/final.yml batch, 0.9990-0.9995 per
+# tensor on reduced-width models).  CPCSV_NOGRAD_SPLIT=1: bf16 hi/lo planes (3 MMAs) there as well -- images
+# to 2e-5, discriminator gradients to 0.99997 -- at 3x the tensor-core work of those calls (+2.4 TFLOP per step
+# at cfg/final.yml).
+import os as _os  # noqa: E402
+NOGRAD_SPLIT = _os.environ.get("CPCSV_NOGRAD_SPLIT", "0") == "1"
+
 
 def rup(x, m):
     return (x + m - 1) // m * m
@@ -589,8 +598,9 @@ class Tape:
         self.cache, self.training, self.need_grad = cache, training, need_grad
         self._arena, self._arena_used = None, 0
         self._chunk = stat_chunk if stat_chunk is not None else self.STAT_CHUNK
-        self.planes = planes if planes is not None else (2 if need_grad else 1)
-        self.dtype = dtype if dtype is not None else (ops.BF16 if need_grad else ops.FP16)
+        split = need_grad or NOGRAD_SPLIT
+        self.planes = planes if planes is not None else (2 if split else 1)
+        self.dtype = dtype if dtype is not None else (ops.BF16 if split else ops.FP16)
         self.nodes = []
         self.counters = []      # num_batches_tracked buffers to bump once the forward is done
         self.aux = AuxBranch()  # weight-gradient side branch of the backward pass
