@@ -98,14 +98,6 @@ class Detached:
             with torch.cuda.stream(st):
                 self.results.append(t())
 
-    def wait_here(self):
-        """make the CURRENT stream wait for the pieces without ending them (a consumer on another branch
-        that needs the results before the issuing stream joins)"""
-        cur = torch.cuda.current_stream() if self.streams else None
-        for st in self.streams:
-            cur.wait_stream(st)
-        return self.results
-
     def join(self):
         if self.streams:
             main = torch.cuda.current_stream()

@@ -164,8 +164,6 @@ CONCURRENT_D = True     # run the three discriminators on parallel CUDA streams
 CONCURRENT_G = True     # run sample_videos / sample_images of one phase on two streams
 EARLY_G = True          # issue the generator-update forward alongside the discriminator update
 EARLY_D_REAL = True     # issue the discriminators' real-image encoder passes before the fakes exist
-# each discriminator scores the generator-update fakes right after its own Adam step (CPCSV_PIPELINE_G=0: off)
-PIPELINE_G_LOSS = os.environ.get("CPCSV_PIPELINE_G", "1") != "0"
 step_stream = streams.step_stream
 Detached = streams.Detached
 
@@ -174,7 +172,7 @@ def _concurrently(*thunks, enabled=None):
     return streams.concurrently(*thunks, enabled=CONCURRENT_D if enabled is None else enabled)
 
 
-def stage_discriminators(nets, x, labels, early_generator=False, opts=None, grad_sync=None, skip_d_wgrad=True):
+def stage_discriminators(nets, x, labels, early_generator=False, opts=None, grad_sync=None):
     """reference trainer.py:290-343 minus the optimiser steps: no-grad fakes, the three
     discriminator losses and their backward passes.  The three discriminators are independent
     networks, so running all backward passes before any of their Adam steps (instead of the
@@ -236,13 +234,6 @@ def stage_discriminators(nets, x, labels, early_generator=False, opts=None, grad
     # batch size: run them on three concurrent streams (fork / join around the block)
     real_feats = dict(zip(D_NETS, real_pass.join())) if real_pass is not None else {}
 
-    # Generator-update losses, pipelined per discriminator (reference trainer.py:391-399): the forward pass
-    # of discriminator X on the generator-update fakes needs X's updated weights and the (early) generator
-    # forward, nothing else -- it is issued on X's stream right after X's Adam step instead of after the join
-    # of all three, so it runs while the other discriminators are still in their update.
-    g_forward = out.get("early_generator") if (PIPELINE_G_LOSS and opts is not None and skip_d_wgrad) else None
-    g_losses = {}
-
     def d_update(key, real, fake, ones, zeros, cate, cond):
         netD = nets[key]
         err = compute_discriminator_loss(netD, real, fake, ones, zeros, cate, cond, gpus,
@@ -252,13 +243,6 @@ def stage_discriminators(nets, x, labels, early_generator=False, opts=None, grad
             if grad_sync is not None:
                 grad_sync(list(netD.parameters()))
             opts[key].step()
-        if g_forward is not None:
-            g_vid, g_img = g_forward.wait_here()
-            g_st_mu, g_im_mu = _cond_vectors(x, g_vid[4], g_img[4])
-            g_fake, g_cond = {"D_se": (g_img[6], g_im_mu), "D_im": (g_img[1], g_im_mu),
-                              "D_st": (g_vid[1], g_st_mu)}[key]
-            _set_requires_grad(netD, False)      # restored by stage_generator
-            g_losses[key] = compute_generator_loss(netD, g_fake, real, ones, cate, g_cond, gpus)[0]
         return err
 
     se_errD, im_errD, st_errD = _concurrently(
@@ -266,8 +250,6 @@ def stage_discriminators(nets, x, labels, early_generator=False, opts=None, grad
         lambda: d_update("D_im", x["im_real"], im_fake, im_ones, im_zeros, x["im_labels"], im_mu),
         lambda: d_update("D_st", x["st_real"], st_fake, st_ones, st_zeros, x["st_labels"], st_mu))
     out.update(se_errD=se_errD.detach(), im_errD=im_errD.detach(), st_errD=st_errD.detach())
-    if g_losses:
-        out["g_losses"] = g_losses
     knets.join_prefetch(prefetch)
     return out
 
@@ -281,7 +263,7 @@ def generator_forward(nets, x, after=None):
                      lambda: netG.sample_images(x["im_motion"], x["im_content"], seg=True)], after=after)
 
 
-def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True, forward=None, g_losses=None):
+def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True, forward=None):
     """reference trainer.py:365-415: generator forward with fresh noise (or the already issued
     ``forward`` handle of ``generator_forward``), the three adversarial losses + KL terms,
     backward."""
@@ -316,13 +298,10 @@ def stage_generator(nets, x, labels, ratio=1.0, skip_d_wgrad=True, forward=None,
                                 + torch.nn.functional.mse_loss(rec_fake, se_fake)) / 2.0
             out.update(video_latent_loss=video_latent_loss.detach(), image_latent_loss=image_latent_loss.detach(),
                        reconstruct_loss=reconstruct_loss.detach())
-        if g_losses:      # already issued per discriminator inside the discriminator stage
-            se_errG, im_errG, st_errG = g_losses["D_se"], g_losses["D_im"], g_losses["D_st"]
-        else:
-            se_errG, im_errG, st_errG = _concurrently(
-                lambda: compute_generator_loss(netD_se, se_fake, x["se_real"], im_ones, x["im_labels"], im_mu, gpus)[0],
-                lambda: compute_generator_loss(netD_im, im_fake, x["im_real"], im_ones, x["im_labels"], im_mu, gpus)[0],
-                lambda: compute_generator_loss(netD_st, st_fake, x["st_real"], st_ones, x["st_labels"], st_mu, gpus)[0])
+        se_errG, im_errG, st_errG = _concurrently(
+            lambda: compute_generator_loss(netD_se, se_fake, x["se_real"], im_ones, x["im_labels"], im_mu, gpus)[0],
+            lambda: compute_generator_loss(netD_im, im_fake, x["im_real"], im_ones, x["im_labels"], im_mu, gpus)[0],
+            lambda: compute_generator_loss(netD_st, st_fake, x["st_real"], st_ones, x["st_labels"], st_mu, gpus)[0])
         im_kl = KL_loss(cim_mu, cim_logvar)
         st_kl = KL_loss(c_mu, c_logvar)
         kl_w = cfg.TRAIN.COEFF.KL
@@ -359,14 +338,13 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
     exchange = grad_sync is not None and getattr(grad_sync, "enabled", True)
     step_inside = apply_optim and not exchange
     out = stage_discriminators(nets, x, labels, early_generator=EARLY_G, opts=opts if apply_optim else None,
-                               grad_sync=grad_sync if exchange else None, skip_d_wgrad=skip_d_wgrad)
+                               grad_sync=grad_sync if exchange else None)
     if not apply_optim:
         sync_grads(nets, D_NETS, grad_sync)
     if step_inside and hasattr(opts["G"], "expect_backward"):
         opts["G"].expect_backward()      # the generator's Adam step starts inside the backward pass
     try:
-        out.update(stage_generator(nets, x, labels, ratio, skip_d_wgrad, forward=out.pop("early_generator", None),
-                                   g_losses=out.pop("g_losses", None)))
+        out.update(stage_generator(nets, x, labels, ratio, skip_d_wgrad, forward=out.pop("early_generator", None)))
     finally:
         if hasattr(opts["G"], "disarm"):
             opts["G"].disarm()
