@@ -446,9 +446,9 @@ def main():
     ap.add_argument("--config", default="train", choices=["train", "inference", "stress"],
                     help="train = BASELINE configs[1] (the contract line); inference = configs[3] (no-grad generator "
                          "+ segmentation branch, batch sweep); stress = configs[4] (512 stories + 2560 images / step)")
-    ap.add_argument("--overlap-io", action="store_true",
-                    help="e2e loop: copy the next batch on a copy stream while the current step replays "
-                         "(trainer.GraphedStep.load_async; opt-in until measured on a GPU)")
+    ap.add_argument("--no-overlap-io", action="store_true",
+                    help="e2e loop: copy every batch on the step's own stream right before the step instead of one "
+                         "batch ahead on a copy stream (trainer.GraphedStep.load_async)")
     ap.add_argument("--whole-graph", action="store_true",
                     help="(default since round 2) N > 1: the NCCL all-reduces are captured inside the ONE step graph")
     ap.add_argument("--segmented", action="store_true",
@@ -485,7 +485,7 @@ def main():
     if args.segmented and world == 1:
         grad_sync = trainer.GradSync(enabled=False)
     eng = StepEngine(p, device, use_graph=not args.no_graph, grad_sync=grad_sync, segmented=args.segmented)
-    eng.overlap_io = args.overlap_io
+    eng.overlap_io = not args.no_overlap_io and not args.no_graph
 
     # warm-up (eager: builds caches, sets kernel attributes), then capture
     side = torch.cuda.Stream()
@@ -514,12 +514,23 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            if with_io:
-                eng.upload()
-            eng.step()
-            if with_io:
+        if with_io and eng.overlap_io:
+            # the product's pipelined input path (GraphedStep.load_async, as GANTrainer.train uses it): the
+            # pinned batch of step i+1 is copied on a copy stream into staging buffers while step i replays;
+            # all K host-to-device copies and K loss read-backs are inside the timed region
+            eng.upload()
+            for i in range(args.steps):
+                eng.step()
+                if i + 1 < args.steps:
+                    eng.upload()
                 eng.download()
+        else:
+            for _ in range(args.steps):
+                if with_io:
+                    eng.upload()
+                eng.step()
+                if with_io:
+                    eng.download()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)

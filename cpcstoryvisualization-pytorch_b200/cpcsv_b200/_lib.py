@@ -66,6 +66,7 @@ SIGNATURES = {
                            _p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p],
     "cpcsv_bn_norm_act_pack": [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _p, _i32, _f32, _f32, _p, _i32, _p, _i64,
                                _p, _i64, _p, _p, _i64, _i32, _p],
+    "cpcsv_images_to_u8": [_p, _i32, _i32, _i32, _i64, _i64, _i64, _p, _p],
     "cpcsv_pack_nchw": [_p, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _p, _i32, _i64, _p, _p,
                         _i32, _i32, _p],
     "cpcsv_im2col_small": [_p, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p,

@@ -206,6 +206,15 @@ def bn_norm_act_pack(x, stats, gamma, beta, running_mean, running_var, chan_map,
 
 
 # ------------------------------------------------------------------ layout kernels
+def images_to_u8(x, out):
+    """x [C, H, W] fp32 in [-1, 1] (any strides) -> out uint8 [H, W, C] (contiguous)"""
+    Cc, H, W = x.shape
+    assert out.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape) == (H, W, Cc)
+    sc, sh, sw = x.stride()
+    _lib.check(_lib.load().cpcsv_images_to_u8(_ptr(x, torch.float32), Cc, H, W, sc, sh, sw, _ptr(out), _stream()),
+               "cpcsv_images_to_u8")
+
+
 def pack_nchw(x, bcast, hi, lo, cpad, dtype=BF16):
     N, Cc, H, W = x.shape
     sn, sc, sh, sw = x.stride()

@@ -129,6 +129,25 @@ __global__ void col2im_small_kernel(const float* __restrict__ dcol, int64_t ldc,
   }
 }
 
+// ------------------------------------------------------------------------- image output
+// [C, H, W] fp32 in [-1, 1] (any strides) -> uint8 [H, W, C]: the conversion the reference does on the host
+// for every generated frame / sheet (miscc/utils.py:230-235 images_to_numpy); on the device the read-back is
+// a quarter of the bytes and already in the layout PIL / the PNG writer wants.
+__global__ void images_to_u8_kernel(const float* __restrict__ x, int C, int H, int W, int64_t sc, int64_t sh,
+                                    int64_t sw, uint8_t* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(H) * W * C;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int64_t p = i / C;
+    const int w = static_cast<int>(p % W), h = static_cast<int>(p / W);
+    float v = x[c * sc + h * sh + w * sw];
+    v = fminf(fmaxf(v, -1.f), 1.f);
+    // (v + 1) / 2 * 255 truncated, exactly the host formula
+    out[i] = static_cast<uint8_t>((v + 1.0f) / 2.0f * 255.0f);
+  }
+}
+
 // ------------------------------------------------------------------------- heads
 __global__ void tanh_to_nchw_kernel(const float* __restrict__ z, int64_t ldz, int N, int C, int H,
                                     int W, float* __restrict__ y) {
@@ -464,6 +483,14 @@ using namespace cpcsv;
 #define STREAM(s) static_cast<cudaStream_t>(s)
 
 // (the BatchNorm entry points live in bn.cu)
+
+extern "C" int cpcsv_images_to_u8(const float* x, int32_t C, int32_t H, int32_t W, int64_t sc, int64_t sh,
+                                  int64_t sw, uint8_t* out, cpcsv_stream_t stream) {
+  CPCSV_REQUIRE(x && out && C > 0 && H > 0 && W > 0, "images_to_u8: args");
+  const int64_t work = static_cast<int64_t>(C) * H * W;
+  images_to_u8_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>(x, C, H, W, sc, sh, sw, out);
+  return launched("images_to_u8");
+}
 
 extern "C" int cpcsv_pack_nchw(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t sn,
                                int64_t sc, int64_t sh, int64_t sw, const float* bcast, int32_t Cb,

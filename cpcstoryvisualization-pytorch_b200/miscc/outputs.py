@@ -83,8 +83,16 @@ def _sheet(images, per_row):
 
 
 def images_to_numpy(tensor):
-    """[C, H, W] in [-1, 1] -> uint8 [H, W, C] (values outside the range are clipped)"""
-    arr = tensor.detach().cpu().numpy().transpose(1, 2, 0)
+    """[C, H, W] in [-1, 1] -> uint8 [H, W, C] (values outside the range are clipped).  A CUDA tensor is
+    converted on the device (cpcsv_images_to_u8) and read back as uint8 HWC: a quarter of the bytes of the
+    reference's fp32 read-back (miscc/utils.py:230-235), no host-side transpose / clip / cast."""
+    tensor = tensor.detach()
+    if tensor.is_cuda and tensor.dtype == torch.float32 and tensor.dim() == 3:
+        from cpcsv_b200 import ops
+        out = torch.empty((tensor.shape[1], tensor.shape[2], tensor.shape[0]), dtype=torch.uint8, device=tensor.device)
+        ops.images_to_u8(tensor, out)
+        return out.cpu().numpy()
+    arr = tensor.cpu().numpy().transpose(1, 2, 0)
     return ((np.clip(arr, -1.0, 1.0) + 1.0) / 2.0 * 255.0).astype("uint8")
 
 

@@ -718,24 +718,41 @@ class GANTrainer(object):
             for ld in (storyloader, imageloader):
                 if self.world > 1 and hasattr(getattr(ld, "sampler", None), "set_epoch"):
                     ld.sampler.set_epoch(epoch)
-            for i, data in enumerate(storyloader):
-                st_batch, im_batch = tensors(data), tensors(self.sample_real_image_batch(to_device=False))
+            # One batch of look-ahead (reference trainer.py:143-158,248): while the
+            # graph of step i replays, the host-to-device copy of batch i+1 runs on a copy stream into staging
+            # buffers (GraphedStep.load_async); step i+1 starts with one device-to-device multi-tensor copy.
+            batches = ((data, tensors(data), tensors(self.sample_real_image_batch(to_device=False)))
+                       for data in storyloader)
+            pending = next(batches, None)
+            staged = False
+            i = -1
+            while pending is not None:
+                i += 1
+                data, st_batch, im_batch = pending
                 want_log = self._logger is not None and i % 20 == 0
                 stats = None
                 if use_graph and graphed is None:
                     graphed = GraphedStep(nets, opts, labels, {k: v.to(dev) for k, v in st_batch.items()},
                                           {k: v.to(dev) for k, v in im_batch.items()}, grad_sync, self.ratio)
+                async_io = use_graph and dev.type == "cuda"
                 if use_graph and graphed.fits(st_batch, im_batch):
-                    graphed.load(st_batch, im_batch)
+                    if not staged:
+                        graphed.load(st_batch, im_batch)
                     if graphed.graph is None:
                         if eager_steps >= self.GRAPH_WARMUP_STEPS:
                             graphed.capture(capture_error_mode="thread_local")   # loader threads
                         else:
                             eager_steps += 1
-                    graphed.step()
+                    graphed.step()                      # consumes a staged batch first
+                    pending = next(batches, None)       # the loader works while the GPU runs step i
+                    staged = False
+                    if async_io and pending is not None and graphed.fits(pending[1], pending[2]):
+                        graphed.load_async(pending[1], pending[2])
+                        staged = True
                     if want_log:
                         stats = graphed.losses()
                 else:
+                    pending, staged = next(batches, None), False
                     # the eager step on the same kernels: CPCSV_GRAPH=0, or a batch of another size
                     # (a loader without drop_last)
                     st_dev = {k: v.to(dev, non_blocking=True) for k, v in st_batch.items()}

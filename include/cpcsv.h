@@ -151,6 +151,11 @@ int cpcsv_bn_norm_act_pack(const float* x, int64_t rows, int32_t C, int64_t ldx,
                            cpcsv_stream_t stream);
 
 /* ------------------------------------------------------------------- layout / pack kernels */
+/* generated frames / image sheets for the PNG writers (miscc/utils.py:230-235 images_to_numpy,
+ * inference.py:181-197): x [C, H, W] fp32 in [-1, 1] with element strides (sc, sh, sw) ->
+ * uint8 [H, W, C] = trunc((clip(x, -1, 1) + 1) / 2 * 255) */
+int cpcsv_images_to_u8(const float* x, int32_t C, int32_t H, int32_t W, int64_t sc, int64_t sh,
+                       int64_t sw, uint8_t* out, cpcsv_stream_t stream);
 /* fp32 strided (n, c, h, w) -> NHWC 16-bit hi/lo planes with channel pitch ldp; channels
  * c >= C are zero-filled up to Cpad.  `bcast` (optional, [n, Cb]) is appended after the C
  * tensor channels and broadcast over (h, w): the concat of D_GET_LOGITS (model.py:88-92). */

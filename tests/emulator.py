@@ -261,6 +261,11 @@ def bn_norm_act_pack(x, stats, gamma, beta, running_mean, running_var, chan_map,
 
 
 # ------------------------------------------------------------------------------ layout kernels
+def images_to_u8(x, out):
+    arr = (x.float().clamp(-1.0, 1.0) + 1.0) / 2.0 * 255.0
+    out.copy_(arr.permute(1, 2, 0).to(torch.uint8))
+
+
 def pack_nchw(x, bcast, hi, lo, cpad, dtype=1):
     N, Cc, H, W = x.shape
     full = torch.zeros(N, H, W, cpad)

@@ -377,3 +377,16 @@ def test_unpack_wgrad_dot_and_spectral_apply():
     assert close(res["cuda"][0], res["cuda"][1], 1e-5)
     assert close(res["cuda"][0], res["cpu"][0], 1e-5)
     assert abs(res["cuda"][2] - res["cpu"][2]) <= 1e-4 * abs(res["cpu"][2]) + 1e-4
+
+
+def test_images_to_u8_matches_the_host_formula():
+    """device-side image conversion == reference miscc/utils.py:230-235 on the host"""
+    import numpy as np
+    x = (rnd(3, 70, 130, seed=71) * 0.8).permute(0, 2, 1).contiguous().permute(0, 2, 1)   # strided
+    x[0, 0, :4] = torch.tensor([-1.5, -1.0, 1.0, 1.5])
+    ref = ((np.clip(x.numpy().transpose(1, 2, 0), -1.0, 1.0) + 1.0) / 2.0 * 255.0).astype("uint8")
+    out = torch.empty(70, 130, 3, dtype=torch.uint8, device="cuda")
+    ops.images_to_u8(x.cuda(), out)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    from miscc.outputs import images_to_numpy
+    assert np.array_equal(images_to_numpy(x.cuda()), ref)
