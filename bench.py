@@ -287,6 +287,25 @@ def job_flops(job):
     return 2.0 * pix * job.groups * job.m_valid * job.n_valid
 
 
+def job_bytes(job):
+    """algorithmic HBM bytes of one conv_gemm launch: every operand plane read once (whatever the number of
+    filter taps that re-read it through L2 / shared memory), the fp32 output written once"""
+    def numel(view):
+        n = 1
+        for d in view.dims:
+            n *= d
+        return n
+    n, h, w = job.grid
+    pix = n * h * w
+    a = sum(numel(v) for v in job.a[:job.planes]) * 2
+    b = sum(numel(v) for v in job.b[:job.planes]) * 2
+    if job.mode == 0:
+        out = pix * job.groups * job.n_valid * 4
+    else:
+        out = job.groups * job.m_valid * job.n_valid * 4
+    return a + b + out
+
+
 def profile_gemm_launches(engine, steps):
     """Average launch duration of the dominant kernel, measured live with CUDA events: the step is
     run eagerly on ONE stream behind a long device-side sleep (so the host stays ahead and each
@@ -309,7 +328,7 @@ def profile_gemm_launches(engine, steps):
         e1.record()
         if restore:
             job.accumulate = False
-        recs.append((e0, e1, job_flops(job)))
+        recs.append((e0, e1, job_flops(job), job_bytes(job)))
 
     tr = engine.trainer
     flags = (tr.CONCURRENT_D, tr.CONCURRENT_G, tr.EARLY_G, tr.streams.ENABLED, keng.WGRAD_ON_AUX_STREAM)
@@ -325,11 +344,11 @@ def profile_gemm_launches(engine, steps):
     finally:
         ops.conv_gemm = orig
         tr.CONCURRENT_D, tr.CONCURRENT_G, tr.EARLY_G, tr.streams.ENABLED, keng.WGRAD_ON_AUX_STREAM = flags
-    ms = sum(a.elapsed_time(b) for a, b, _ in recs)
-    fl = sum(f for _, _, f in recs)
+    ms = sum(r[0].elapsed_time(r[1]) for r in recs)
+    fl = sum(r[2] for r in recs)
     return {"launches_per_step": len(recs) / steps, "gemm_ms_per_step": ms / steps,
             "executed_gflop_per_step": fl / steps / 1e9, "achieved_tflops": fl / (ms * 1e-3) / 1e12,
-            "avg_launch_us": 1e3 * ms / len(recs)}
+            "avg_launch_us": 1e3 * ms / len(recs), "algorithmic_bytes_per_launch": sum(r[3] for r in recs) / len(recs)}
 
 
 def run_large_config(args):
@@ -591,6 +610,7 @@ def main():
         "roofline": {"bound": "tensor", "achieved": prof["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
                      "frac": prof["achieved_tflops"] / peak, "traffic": traffic.get("avg_bytes_per_launch"),
                      "traffic_note": traffic.get("note", "no ncu capture recorded under profiles/"),
+                     "algorithmic_bytes_per_launch": prof["algorithmic_bytes_per_launch"],
                      "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM)", "peak_source": peak_src,
                      "executed_gflop_per_step": prof["executed_gflop_per_step"],
                      "gemm_launches_per_step": prof["launches_per_step"],

@@ -16,7 +16,8 @@ run traffic 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__
 # 3. full sets of the GEMM classes (pair mode) and of the head GEMM + gather
 run full 600 ncu --set full --clock-control none --import-source on -o $O/r02_ncu_targets python tools/ncu_targets.py all
 # 4. stress-512: tensor-pipe activity of every conv_gemm launch of one step
-run stress 900 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum \
+# (application replay: kernel replay would save / restore the 65 GB working set around every launch)
+run stress 600 ncu --replay-mode application --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
     --clock-control none -k regex:conv_gemm --launch-skip 454 -c 227 --csv --log-file $O/r02_stress_gemm.csv \
     python bench.py --config stress --steps 2 --warmup 2
 cat $O/r02_prof_summary.log
