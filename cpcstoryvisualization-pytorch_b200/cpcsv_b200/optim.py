@@ -41,6 +41,7 @@ class PackedAdam(torch.optim.Optimizer):
         self._armed, self._pending, self._done = False, set(), set()
         self._ticked = set()
         self._side, self._side_used = None, False
+        self._pre_update, self.early_fired = None, False
 
     # ---- device-side scalars ----------------------------------------------------------------
     def _group_state(self, gi, group, device):
@@ -74,12 +75,20 @@ class PackedAdam(torch.optim.Optimizer):
         for p in self._early_params:
             p.register_post_accumulate_grad_hook(self._grad_ready)
 
-    def expect_backward(self):
+    def expect_backward(self, pre_update=None):
         """arm the early step for the NEXT backward pass only (a backward pass that is not followed by
-        ``step()`` -- gradient checks, gradient exchange between ranks -- must not be armed)"""
+        ``step()`` -- gradient checks -- must not be armed).  ``pre_update(params)``: called on the side
+        stream right before the early parameters are updated -- the gradient exchange between ranks
+        (trainer.GradSync) for exactly those parameters; ``early_fired`` tells the caller afterwards whether
+        it ran (then only the remaining parameters are left to exchange)."""
+        self.early_fired = False
+        self._pre_update = pre_update
         if self._early_params:
             self._armed = True
             self._pending = set(self._early_ids)
+
+    def early_parameters(self):
+        return list(self._early_params)
 
     def disarm(self):
         self._armed = False
@@ -91,7 +100,7 @@ class PackedAdam(torch.optim.Optimizer):
             self._pending.discard(id(p))
             if not self._pending:
                 self._armed = False
-                self._update([q for q in self._early_params if q.grad is not None])
+                self._early_step()
             return
         cur = torch.cuda.current_stream()
         if self._side is None:
@@ -102,7 +111,14 @@ class PackedAdam(torch.optim.Optimizer):
         if not self._pending:
             self._armed = False
             with torch.cuda.stream(self._side):
-                self._update([q for q in self._early_params if q.grad is not None])
+                self._early_step()
+
+    def _early_step(self):
+        params = [q for q in self._early_params if q.grad is not None]
+        if self._pre_update is not None:
+            self._pre_update(params)
+        self.early_fired = True
+        self._update(params)
 
     def _tick(self, gi, group, st):
         if gi not in self._ticked:

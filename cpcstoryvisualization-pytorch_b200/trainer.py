@@ -336,19 +336,25 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
     ``prepare_inputs`` (device tensors), ``labels`` = (im_ones, im_zeros, st_ones, st_zeros).
     Returns a dict of loss tensors (no host sync)."""
     exchange = grad_sync is not None and getattr(grad_sync, "enabled", True)
-    step_inside = apply_optim and not exchange
     out = stage_discriminators(nets, x, labels, early_generator=EARLY_G, opts=opts if apply_optim else None,
                                grad_sync=grad_sync if exchange else None)
     if not apply_optim:
         sync_grads(nets, D_NETS, grad_sync)
-    if step_inside and hasattr(opts["G"], "expect_backward"):
-        opts["G"].expect_backward()      # the generator's Adam step starts inside the backward pass
+    early = apply_optim and hasattr(opts["G"], "expect_backward")
+    if early:
+        # the generator's Adam step starts inside the backward pass; with several ranks the gradient
+        # exchange of those (trunk) parameters is issued there too, right before their update
+        opts["G"].expect_backward(pre_update=(lambda params: grad_sync(params)) if exchange else None)
     try:
         out.update(stage_generator(nets, x, labels, ratio, skip_d_wgrad, forward=out.pop("early_generator", None)))
     finally:
         if hasattr(opts["G"], "disarm"):
             opts["G"].disarm()
-    sync_grads(nets, ("G",), grad_sync)
+    if exchange and early and opts["G"].early_fired:
+        done = {id(p) for p in opts["G"].early_parameters()}
+        grad_sync([p for p in nets["G"].parameters() if id(p) not in done])
+    else:
+        sync_grads(nets, ("G",), grad_sync)
     if apply_optim:
         opts["G"].step()
     return out

@@ -70,7 +70,7 @@ class _Patch:
         setattr(obj, name, value)
 
 
-def _dp_worker(rank, world, port, out):
+def _dp_worker(rank, world, port, out, fused=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -94,8 +94,12 @@ def _dp_worker(rank, world, port, out):
     for mode, sync in (("local", None), ("synced", trainer.GradSync())):
         nets = harness.build_product(p, params.init_all(p, 0), dev)     # identical weights on every rank
         harness.inject_noise(nets["G"], synth.NoiseFeed(noise))
-        opts = trainer.build_optimizers(nets, fused=False)
+        # fused: cpcsv_b200.optim.PackedAdam on the emulator -- the generator's trunk gradients are then
+        # exchanged and applied from inside the backward pass, the rest after it
+        opts = trainer.build_optimizers(nets, fused=fused)
         trainer.train_step(nets, opts, x, labels, 1.0, grad_sync=sync, apply_optim=(mode == "synced"))
+        if fused and mode == "synced":
+            assert opts["G"].early_fired
         grads[mode] = torch.cat([q.grad.flatten() for k in ("D_im", "G") for q in nets[k].parameters()
                                  if q.grad is not None])
         if mode == "synced":
@@ -109,14 +113,20 @@ def _dp_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_data_parallel_step_world2():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_data_parallel_step_world2(fused):
     """SURVEY.md section 8e on two gloo ranks (kernel-contract emulator): each rank runs train_step on
     its own shard; after the one exchange per optimiser step the discriminator gradients are the
-    mean of the per-rank gradients and every rank ends the step with identical weights."""
+    mean of the per-rank gradients and every rank ends the step with identical weights.  ``fused``: with
+    PackedAdam (per-discriminator exchange inside the discriminator stage, trunk exchange + update inside
+    the generator's backward pass)."""
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_dp_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_dp_worker, args=(world, _free_port(), out, fused), nprocs=world, join=True)
     for rank in range(world):
         err, scale, _ = out[rank]
         assert err <= 1e-6 * max(scale, 1.0), (rank, err, scale)
