@@ -10,7 +10,7 @@ run() { local name=$1 secs=$2; shift 2; echo "== $name" ; timeout "$secs" "$@" >
 
 run gpu_tests      240 python -m pytest tests -m gpu -q --timeout 120 -p no:cacheprovider
 run bench          90  python bench.py --steps 20 --warmup 5
-run bench_overlap  90  python bench.py --steps 20 --warmup 5 --no-overlap-io --no-cpu-baseline
+run bench_overlap  90  python bench.py --steps 20 --warmup 5 --overlap-io --no-cpu-baseline
 run stock_cuda     240 python bench.py --impl stock-cuda --steps 3 --warmup 2
 run smoke          120 python -c "import __graft_entry__ as g; g.smoke()"
 run timeline       120 python tools/timeline_graph.py gpurun_out/r02_timeline_a.csv
