@@ -104,8 +104,10 @@ def _planes(ts, fn):
 
 
 def _plain_out_strides(out):
-    N, H, W, Cc = out.shape
-    return (H * W * Cc, W * Cc, Cc)
+    """element strides of an [N, H, W, C] output (C contiguous); `out` may be a strided view, e.g. every second
+    frame of a [B, T, HW, C] tensor"""
+    assert out.stride(3) == 1
+    return (out.stride(0), out.stride(1), out.stride(2))
 
 
 # ------------------------------------------------------------------ k x k, stride 1
@@ -261,3 +263,60 @@ def gemm_tn(a, b, out):
     taps = [((0, 0, 0, 0), (0, 0, 0, 0), 0)]
     return _wgrad_job(View.nhwc(_rows_as_nhwc(a)), View.nhwc(_rows_as_nhwc(b)), (R, 1, 1), taps, Ma, Nb,
                       out, out.stride(0))
+
+
+# ------------------------------------------------------------------ temporal 3-tap, stride 2, pad 1
+# Conv3d(kernel (3, 1, 1), stride (2, 1, 1), padding (1, 0, 0)) of the order-consistency critic (reference
+# model.py:160-189).  Activations are [B, T, HW, C] (NHWC with H = T, W = H*W of the frame); output frame t_out
+# reads input frames 2*t_out + kt - 1.  The EVEN input frames (kt = 1) and the ODD ones (kt = 0, 2) are two
+# strided views x[:, 0::2] / x[:, 1::2] of the same buffer, so a tap is a plain coordinate offset and TMA's
+# zero fill outside a view is exactly the temporal zero padding, for odd and even T alike.
+def _even_odd(t5):
+    return t5[:, 0::2], t5[:, 1::2]
+
+
+def conv_t3_fwd(x_planes, w_planes, out, alpha=None, dtype=BF16):
+    """out[B, T_out, HW, Co] = temporal conv of x[B, T, HW, Ci]; w_planes: packed kind 0 ``[3 * Co_pad, Ci]``
+    (tap kt at rows [kt * Co_pad, ...)).  Two jobs: even frames (overwrite), odd frames (accumulate)."""
+    B, T, HW, Ci = x_planes[0].shape
+    To, npad = out.shape[1], out.shape[-1]
+    assert To == (T - 1) // 2 + 1
+    ev = [_even_odd(t)[0] for t in x_planes if t is not None]
+    od = [_even_odd(t)[1] for t in x_planes if t is not None]
+    wv = _planes(w_planes, View.matrix)
+    jobs = [_fwd_job([View.nhwc(t) for t in ev], wv, (B, To, HW), 1, 1, [((0, 0, 0, 0), (1 * npad, 0, 0, 0), 0)],
+                     Ci // 64, out, npad, _plain_out_strides(out), alpha, False, dtype=dtype, splits=1)]
+    if T > 1:
+        taps = [((0, 0, 0, -1), (0 * npad, 0, 0, 0), 0), ((0, 0, 0, 0), (2 * npad, 0, 0, 0), 0)]
+        jobs.append(_fwd_job([View.nhwc(t) for t in od], wv, (B, To, HW), 1, 2, taps, Ci // 64, out, npad,
+                             _plain_out_strides(out), alpha, True, dtype=dtype, splits=1))
+    return jobs
+
+
+def conv_t3_dgrad(dy, wt, dx, alpha=None):
+    """dx[B, T, HW, Ci] = transposed temporal conv of dy[B, T_out, HW, Co]; wt: packed kind 1
+    ``[3 * Ci_pad, Co]``.  Even input frames receive tap 1, odd ones taps 0 (from t_out = hh + 1) and 2 (hh)."""
+    B, To, HW, Co = dy.shape
+    T, npad = dx.shape[1], dx.shape[-1]
+    dxe, dxo = _even_odd(dx)
+    jobs = [_fwd_job([View.nhwc(dy)], [View.matrix(wt)], (B, dxe.shape[1], HW), 1, 1,
+                     [((0, 0, 0, 0), (1 * npad, 0, 0, 0), 0)], Co // 64, dxe, npad, _plain_out_strides(dxe), alpha,
+                     splits=1)]
+    if T > 1:
+        taps = [((0, 0, 0, 1), (0 * npad, 0, 0, 0), 0), ((0, 0, 0, 0), (2 * npad, 0, 0, 0), 0)]
+        jobs.append(_fwd_job([View.nhwc(dy)], [View.matrix(wt)], (B, dxo.shape[1], HW), 1, 2, taps, Co // 64, dxo,
+                             npad, _plain_out_strides(dxo), alpha, splits=1))
+    return jobs
+
+
+def conv_t3_wgrad(dy, x_hi, dwt):
+    """dwt[kt][co][ci] = sum dy[b, t_out, p, co] * x[b, 2 t_out + kt - 1, p, ci]  (fp32 ``[3, Co, Ci]``)"""
+    B, To, HW, Co = dy.shape
+    T, Ci = x_hi.shape[1], x_hi.shape[-1]
+    xe, xo = _even_odd(x_hi)
+    jobs = [_wgrad_job(View.nhwc(dy), View.nhwc(xe), (B, To, HW), [((0, 0, 0, 0), (0, 0, 0, 0), 1 * Co * Ci)],
+                       Co, Ci, dwt, Ci)]
+    if T > 1:
+        taps = [((0, 0, 0, 0), (0, 0, 0, -1), 0 * Co * Ci), ((0, 0, 0, 0), (0, 0, 0, 0), 2 * Co * Ci)]
+        jobs.append(_wgrad_job(View.nhwc(dy), View.nhwc(xo), (B, To, HW), taps, Co, Ci, dwt, Ci))
+    return jobs

@@ -67,8 +67,9 @@ def conv_gemm(job):
     assert job.planes in (1, 2) and len(job.taps) <= 16
     out = job.out
     assert out.dtype == torch.float32
-    out_flat = out.reshape(-1) if out.is_contiguous() else None
-    assert out_flat is not None, "emulator needs a contiguous output buffer"
+    # element offsets below are relative to the output POINTER (a strided view's first element)
+    n_store = out.untyped_storage().nbytes() // 4
+    out_flat = torch.empty(0, dtype=torch.float32).set_(out.untyped_storage(), 0, (n_store,), (1,))[out.storage_offset():]
     alpha = float(job.alpha) if job.alpha is not None else 1.0
     A = [_dense_view(v) for v in job.a[:job.planes]]
     B = [_dense_view(v) for v in job.b[:job.planes]]
