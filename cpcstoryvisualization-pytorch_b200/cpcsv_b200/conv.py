@@ -17,9 +17,13 @@ NUM_SMS = 148
 
 
 def pixel_tile(N, H, W, rows):
-    """Box (tile_n, tile_h, tile_w) of `rows` pixels; H, W are powers of two here."""
+    """Box (tile_n, tile_h, tile_w) of `rows` pixels.  W is a power of two; H usually is -- for any other H (an odd
+    number of frames of the temporal convolutions) the box height is the next power of two: the kernel masks rows
+    outside the grid and TMA zero-fills their loads."""
     tw = min(W, rows)
-    th = min(H, rows // tw)
+    th = 1
+    while th < H and th * 2 <= rows // tw:
+        th *= 2
     tn = rows // (tw * th)
     assert tn * th * tw == rows, (N, H, W, rows)
     return tn, th, tw

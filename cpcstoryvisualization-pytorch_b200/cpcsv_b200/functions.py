@@ -6,7 +6,7 @@ forward/backward below is one or a few libcpcsv.so launches; torch only allocate
 import torch
 
 from . import ops
-from .engine import StateOrder
+from .engine import SpectralNorm, StateOrder
 
 
 def _c(t):
@@ -228,6 +228,31 @@ class DynamicFilter1dFn(torch.autograd.Function):
         dimg, dfilt = torch.empty_like(img), torch.empty_like(filt)
         ops.dfn1d_bwd(img, filt, _c(dout), dimg, dfilt)
         return dimg, dfilt
+
+
+class SpectralWeightFn(torch.autograd.Function):
+    """weight = weight_orig / sigma of the legacy torch spectral_norm hook (one power iteration per training-mode
+    call, u / v updated in place) for a Linear that runs as an fp32 kernel (the detector of the VideoEncoder,
+    reference model.py:192-197)"""
+
+    @staticmethod
+    def forward(ctx, w_orig, u, v, training):
+        sn = SpectralNorm(u, v)
+        inv_sigma = sn.forward(w_orig, training, True)
+        ctx.sn = sn
+        ctx.save_for_backward(w_orig)
+        return w_orig.detach() * inv_sigma
+
+    @staticmethod
+    def backward(ctx, g):
+        (w_orig,) = ctx.saved_tensors
+        sn, ctx.sn = ctx.sn, None
+        return sn.backward(_c(g), w_orig), None, None, None
+
+
+def spectral_weight(mod):
+    """mod: holder module carrying weight_orig / weight_u / weight_v"""
+    return SpectralWeightFn.apply(mod.weight_orig, mod.weight_u, mod.weight_v, mod.training)
 
 
 def linear(x, w, b=None):

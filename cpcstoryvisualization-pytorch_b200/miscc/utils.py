@@ -72,8 +72,8 @@ def compute_discriminator_loss(netD, real_imgs, fake_imgs, real_labels, fake_lab
     does not depend on the generator, so the trainer issues it before the fakes exist."""
     if conditions is None:
         raise NotImplementedError("unconditional discriminators are unused by CP-CSV")
-    if netD.get_uncond_logits is not None or netD.seq_consisten_model:
-        raise NotImplementedError("uncond logits / sequence-consistency critic are disabled in cfg/final.yml")
+    if netD.get_uncond_logits is not None:
+        raise NotImplementedError("unconditional logits are unused by CP-CSV (get_uncond_logits is None)")
     batch_size = real_imgs.size(0)
     cond = conditions.detach()
     if real_features is None:
@@ -92,7 +92,16 @@ def compute_discriminator_loss(netD, real_imgs, fake_imgs, real_labels, fake_lab
         cate_logits = _call(netD.cate_classify, real_features).squeeze()
         errD = errD + 1.0 * F.multilabel_soft_margin_loss(cate_logits, real_catelabels)
         acc = get_multi_acc(cate_logits.detach(), real_catelabels)
-    return errD, errD_real.detach(), errD_wrong.detach(), errD_fake.detach(), acc, 0
+    consistency = 0
+    if netD.seq_consisten_model is not None:
+        # order-consistency critic (reference l.110-122): real stories, about half of them with their frames
+        # permuted (label 1), BCE-with-logits on the critic's order logit
+        shuffled, order_labels = create_random_shuffle(real_imgs)
+        order_logits = _call(netD.seq_consisten_model, shuffled)
+        consistency = F.binary_cross_entropy_with_logits(order_logits, order_labels.unsqueeze(-1))
+        errD = errD + cfg.CONSISTENCY_RATIO * consistency
+        consistency = consistency.detach()
+    return errD, errD_real.detach(), errD_wrong.detach(), errD_fake.detach(), acc, consistency
 
 
 def compute_generator_loss(netD, fake_imgs, real_imgs, real_labels, fake_catelabels, conditions, gpus):
@@ -107,7 +116,16 @@ def compute_generator_loss(netD, fake_imgs, real_imgs, real_labels, fake_catelab
         cate_logits = _call(netD.cate_classify, fake_features).squeeze()
         errD_fake = errD_fake + 1.0 * F.multilabel_soft_margin_loss(cate_logits, fake_catelabels)
         acc = get_multi_acc(cate_logits.detach(), fake_catelabels)
-    return errD_fake, acc, 0
+    consistency = 0
+    if netD.seq_consisten_model is not None:
+        # reference l.155-169: the critic's logit of the generated story regressed onto its logit of the real one
+        with torch.no_grad():
+            real_logits = _call(netD.seq_consisten_model, real_imgs)
+        fake_logits = _call(netD.seq_consisten_model, fake_imgs)
+        consistency = F.mse_loss(fake_logits, real_logits)
+        errD_fake = errD_fake + cfg.CONSISTENCY_RATIO * consistency
+        consistency = consistency.detach()
+    return errD_fake, acc, consistency
 
 
 def KL_loss(mu, logvar):

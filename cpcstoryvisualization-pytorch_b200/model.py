@@ -120,6 +120,62 @@ class CateClassifyConv2d(nn.Conv2d):
         return Fx.linear(flat, rows, None).view(n, self.out_channels, 1, 1)
 
 
+# --------------------------------------------------------------------------- order-consistency critic
+class R2Plus1dStem(nn.Sequential):
+    """Parameter holders of the reference's stem (model.py:99-113): spectral-norm Conv3d (1, 7, 7) stride
+    (1, 2, 2) -> BatchNorm3d -> ReLU -> spectral-norm Conv3d (1, 1, 1) with temporal padding 1 -> BatchNorm3d
+    -> ReLU."""
+
+    def __init__(self):
+        super(R2Plus1dStem, self).__init__(
+            spectral_norm(nn.Conv3d(3, 45, kernel_size=(1, 7, 7), stride=(1, 2, 2), padding=(0, 3, 3), bias=False)),
+            nn.BatchNorm3d(45),
+            nn.ReLU(inplace=True),
+            spectral_norm(nn.Conv3d(45, 64, kernel_size=(1, 1, 1), stride=(1, 1, 1), padding=(1, 0, 0), bias=False)),
+            nn.BatchNorm3d(64),
+            nn.ReLU(inplace=True))
+
+
+class VideoEncoder(nn.Module):
+    """Order-consistency critic (reference model.py:150-210): story [B, 3, T, H, W] -> one logit per story.
+    The modules below only hold parameters (same state_dict keys as the reference); the convolutions run on the
+    kernel tape of ``cpcsv_b200.video``, the detector in the fp32 kernels of ``cpcsv_b200.functions``."""
+
+    def __init__(self):
+        super(VideoEncoder, self).__init__()
+
+        def spatial(cin, cout):
+            return spectral_norm(nn.Conv3d(cin, cout, kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1),
+                                           bias=False))
+
+        def temporal(cin, cout):
+            return spectral_norm(nn.Conv3d(cin, cout, kernel_size=(3, 1, 1), stride=(2, 1, 1), padding=(1, 0, 0),
+                                           bias=False))
+
+        block = [R2Plus1dStem()]
+        for make, cin, cout in ((spatial, 64, 128), (temporal, 128, 128), (spatial, 128, 128), (temporal, 128, 256),
+                                (spatial, 256, 256), (temporal, 256, 512), (spatial, 512, 512),
+                                (temporal, 512, 512)):
+            block += [make(cin, cout), nn.BatchNorm3d(cout), nn.LeakyReLU(0.2)]
+        self.pool = nn.AdaptiveAvgPool3d(1)
+        self.story_encoder = nn.Sequential(*block)
+        self.detector = nn.Sequential(
+            spectral_norm(nn.Linear(512, 128)),
+            nn.BatchNorm1d(128),
+            nn.ReLU(),
+            spectral_norm(nn.Linear(128, 1)))
+
+    def forward(self, story):
+        from cpcsv_b200 import video
+        need_grad = torch.is_grad_enabled() and (
+            story.requires_grad or any(p.requires_grad for p in self.parameters()))
+        latents = video.VideoEncoderRunner(self, need_grad).apply(story)
+        det = self.detector
+        x = Fx.linear(latents, Fx.spectral_weight(det[0]), det[0].bias)
+        x = torch.relu(Fx.batch_norm_1d(x, det[1]))
+        return Fx.linear(x, Fx.spectral_weight(det[3]), det[3].bias)
+
+
 # --------------------------------------------------------------------------- generator
 class StoryGAN(nn.Module):
     """CP-CSV generator with the figure-ground segmentation branch (reference model.py:214-483)."""
@@ -317,9 +373,8 @@ class STAGE1_D_STY_V2(_DiscriminatorBase):
 
     def __init__(self):
         super(STAGE1_D_STY_V2, self).__init__(use_categories=False)
-        if cfg.USE_SEQ_CONSISTENCY:
-            raise NotImplementedError("USE_SEQ_CONSISTENCY (VideoEncoder critic) is disabled in "
-                                      "cfg/final.yml:16 and outside the accelerated path")
+        if cfg.USE_SEQ_CONSISTENCY:       # reference model.py:599-601
+            self.seq_consisten_model = VideoEncoder()
 
     def forward(self, story):
         N, C, video_len, W, H = story.shape

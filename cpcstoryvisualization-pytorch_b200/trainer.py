@@ -406,6 +406,11 @@ class GraphedStep:
         self.grad_sync = grad_sync
         exchange = grad_sync is not None and getattr(grad_sync, "enabled", True)
         self.segmented = bool(segmented) if segmented is not None else False
+        if use_graph and getattr(nets["D_st"], "seq_consisten_model", None) is not None:
+            # create_random_shuffle (miscc/utils.py:14-44) permutes the real stories on the HOST from the python /
+            # numpy generators every step: a replayed graph would repeat one permutation forever
+            raise NotImplementedError("cfg.USE_SEQ_CONSISTENCY draws a host-side shuffle every step; "
+                                      "run the eager step (use_graph=False / CPCSV_GRAPH=0)")
         self.use_graph = use_graph
         self.graph = None
         self.graphs = []
@@ -704,6 +709,8 @@ class GANTrainer(object):
             torch.cuda.manual_seed(seed)
         dev = self.device
         use_graph = dev.type == "cuda" and os.environ.get("CPCSV_GRAPH", "1") != "0"
+        if cfg.USE_SEQ_CONSISTENCY:
+            use_graph = False       # per-step host-side story shuffle (see GraphedStep.__init__)
         opts = build_capturable_optimizers(nets, dev) if use_graph else build_optimizers(nets)
         labels = (torch.ones(self.imbatch_size, device=dev), torch.zeros(self.imbatch_size, device=dev),
                   torch.ones(self.stbatch_size, device=dev), torch.zeros(self.stbatch_size, device=dev))

@@ -301,7 +301,7 @@ def multi_acc(logits, labels):
     return (hit.float() / labels.sum()).item()
 
 
-def discriminator_loss(sd, real_imgs, fake_imgs, real_labels, fake_labels, cate_labels, cond):
+def discriminator_loss(sd, real_imgs, fake_imgs, real_labels, fake_labels, cate_labels, cond, consistency_ratio=1.0):
     """compute_discriminator_loss, conditional branch (miscc/utils.py:48-123).  Returns
     (errD, errD_real, errD_wrong, errD_fake, cate_logits-or-None)."""
     n = real_imgs.size(0)
@@ -316,10 +316,16 @@ def discriminator_loss(sd, real_imgs, fake_imgs, real_labels, fake_labels, cate_
     if "cate_classify.weight" in sd:
         cate = cate_classify(sd, real_f).squeeze()
         err = err + 1.0 * F.multilabel_soft_margin_loss(cate, cate_labels)
+    if "seq_consisten_model.detector.3.weight_orig" in sd:
+        # miscc/utils.py:110-122 (cfg.USE_SEQ_CONSISTENCY)
+        from . import video_encoder as VE
+        shuffled, order_labels = VE.create_random_shuffle(real_imgs)
+        order, _ = VE.order_loss_d(VE.sub_state(sd), shuffled, order_labels)
+        err = err + consistency_ratio * order
     return err, e_real.detach(), e_wrong.detach(), e_fake.detach(), cate
 
 
-def generator_loss(sd, fake_imgs, real_labels, cate_labels, cond):
+def generator_loss(sd, fake_imgs, real_labels, cate_labels, cond, real_imgs=None, consistency_ratio=1.0):
     """compute_generator_loss, conditional branch (miscc/utils.py:126-171)."""
     cond = cond.detach()
     fake_f = d_forward(sd, fake_imgs)
@@ -328,6 +334,10 @@ def generator_loss(sd, fake_imgs, real_labels, cate_labels, cond):
     if "cate_classify.weight" in sd:
         cate = cate_classify(sd, fake_f).squeeze()
         err = err + 1.0 * F.multilabel_soft_margin_loss(cate, cate_labels)
+    if "seq_consisten_model.detector.3.weight_orig" in sd:
+        # miscc/utils.py:155-169
+        from . import video_encoder as VE
+        err = err + consistency_ratio * VE.order_loss_g(VE.sub_state(sd), real_imgs, fake_imgs)
     return err, cate
 
 
@@ -412,7 +422,8 @@ def train_step(model, batch, noise, ratio=1.0, apply_optim=True):
         model.zero_grad(net)
     se_errD, *_ = discriminator_loss(D_se, se_real, se_fake, im_ones, im_zeros, im_labels, im_mu)
     im_errD, *_ = discriminator_loss(D_im, im_real, im_fake, im_ones, im_zeros, im_labels, im_mu)
-    st_errD, *_ = discriminator_loss(D_st, st_real, st_fake, st_ones, st_zeros, st_labels, st_mu)
+    st_errD, *_ = discriminator_loss(D_st, st_real, st_fake, st_ones, st_zeros, st_labels, st_mu,
+                                     p.get("CONSISTENCY_RATIO", 1.0))
     se_errD.backward()
     if apply_optim:
         model.opt["D_se"].step()
@@ -446,7 +457,7 @@ def train_step(model, batch, noise, ratio=1.0, apply_optim=True):
     st_mu, im_mu = cond_vectors(c_mu, cim_mu)
     se_errG, _ = generator_loss(D_se, se_fake, im_ones, im_labels, im_mu)
     im_errG, _ = generator_loss(D_im, im_fake, im_ones, im_labels, im_mu)
-    st_errG, _ = generator_loss(D_st, st_fake, st_ones, st_labels, st_mu)
+    st_errG, _ = generator_loss(D_st, st_fake, st_ones, st_labels, st_mu, st_real, p.get("CONSISTENCY_RATIO", 1.0))
     im_kl = kl_loss(cim_mu, cim_logvar)
     st_kl = kl_loss(c_mu, c_logvar)
     kl_w = p["KL"]

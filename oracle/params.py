@@ -114,6 +114,11 @@ def discriminator_inventory(p, kind):
     _sn_conv(d, "get_cond_logits.outlogits.3", 1, ndf * 8, 4, bias=True)
     if kind != "sty":
         d["cate_classify.weight"] = ("w", (p["LABEL_NUM"], ndf * 8, 4, 4))
+    elif p.get("USE_SEQ_CONSISTENCY"):
+        # model.py:599-601: the VideoEncoder critic is a child module of the story discriminator
+        from .video_encoder import inventory as video_inventory
+        for k, spec in video_inventory().items():
+            d["seq_consisten_model." + k] = spec
     return d
 
 

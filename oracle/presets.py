@@ -6,7 +6,7 @@ Every preset is a flat dict of the ``cfg`` fields the model reads at constructio
 
 _COMMON = dict(
     CUDA=False, USE_SEQ_CONSISTENCY=False, SEGMENT_LEARNING=True, CASCADE_MODEL=False,
-    SEGMENT_RATIO=1.0, IMAGE_RATIO=5.0, KL=1.0, RECONSTRUCT_LOSS=1.0,
+    SEGMENT_RATIO=1.0, IMAGE_RATIO=5.0, KL=1.0, RECONSTRUCT_LOSS=1.0, CONSISTENCY_RATIO=1.0,
     DISCRIMINATOR_LR=4e-4, GENERATOR_LR=1e-4,
 )
 
@@ -30,6 +30,9 @@ PRESETS = {
 # the cascade generator (cascade_model.py, cfg.CASCADE_MODEL)
 for _n in ("tiny", "small", "clevr", "pororo"):
     PRESETS[_n + "_cascade"] = dict(PRESETS[_n], CASCADE_MODEL=True)
+# the order-consistency critic inside the story discriminator (cfg.USE_SEQ_CONSISTENCY)
+for _n in ("tiny", "small", "clevr", "pororo"):
+    PRESETS[_n + "_seq"] = dict(PRESETS[_n], USE_SEQ_CONSISTENCY=True)
 
 
 def get(name, **overrides):
@@ -50,6 +53,7 @@ def apply_to_cfg(cfg, p):
     cfg.SEGMENT_RATIO = p["SEGMENT_RATIO"]
     cfg.IMAGE_RATIO = p["IMAGE_RATIO"]
     cfg.RECONSTRUCT_LOSS = p.get("RECONSTRUCT_LOSS", 1.0)
+    cfg.CONSISTENCY_RATIO = p.get("CONSISTENCY_RATIO", 1.0)
     cfg.Z_DIM = p["Z_DIM"]
     cfg.TRAIN.IM_BATCH_SIZE = p["IM_BATCH"]
     cfg.TRAIN.ST_BATCH_SIZE = p["ST_BATCH"]

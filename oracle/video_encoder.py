@@ -6,8 +6,10 @@ Layer list = ``VideoEncoder.story_encoder`` (model.py:155-190) with the ``R2Plus
 front and the ``detector`` of model.py:192-197 behind; every Conv3d / Linear carries the legacy spectral-norm
 hook, no conv has a bias, BatchNorm3d / 1d in train mode.
 """
+import random
 from collections import OrderedDict
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -115,3 +117,35 @@ def order_loss_g(sd, real_stories, fake_stories):
     real_logits = video_encoder(sd, real_stories)
     fake_logits = video_encoder(sd, fake_stories)
     return F.mse_loss(fake_logits, real_logits.detach())
+
+
+def create_random_shuffle(stories, random_rate=0.5):
+    """miscc/utils.py:14-44: per story, with probability ``random_rate`` (numpy global RNG) permute the frames
+    into a non-sorted order (python ``random``; re-drawn with numpy while still sorted) and, when another story
+    is drawn, replace one frame by that story's frame of the same position; label 1 = shuffled.  Consumes the
+    two global generators in the reference's order, so equal seeds give equal batches."""
+    host = stories.detach().cpu()
+    n, T = host.shape[0], host.shape[2]
+    out, labels = [], []
+    for i in range(n):
+        label = 1 if random_rate > np.random.random() else 0
+        labels.append(label)
+        if label == 0:
+            out.append(host[i].clone())
+            continue
+        seq = random.sample(range(T), T)
+        while all(seq[j] <= seq[j + 1] for j in range(T - 1)):
+            np.random.shuffle(seq)
+        story = host[i][:, list(seq)].clone()
+        j = random.randint(0, n - 1)
+        if j != i:
+            mix = random.sample(range(T), 1)
+            story[:, mix] = host[j][:, mix].clone()
+        out.append(story)
+    return torch.stack(out, 0).to(stories.device), torch.tensor(labels, dtype=stories.dtype, device=stories.device)
+
+
+def sub_state(sd, prefix="seq_consisten_model."):
+    """the critic's tensors inside a story-discriminator state dict (same tensor objects: in-place buffer
+    updates and .grad land in the parent's dict)"""
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}

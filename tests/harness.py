@@ -1,5 +1,8 @@
 """Shared helpers of the parity tests: build the product networks for a preset, load the
 oracle-initialised weights, inject the oracle's noise list, run one step, compare."""
+import random
+
+import numpy as np
 import torch
 
 from oracle import functional as Fn
@@ -8,7 +11,9 @@ from oracle import params, presets, synth
 ZERO_GRAD = ("filter_net.0.bias", "image_net.0.bias", "m_net.0.bias", "c_net.0.bias",
              # cascade downBlocks: conv bias directly followed by BatchNorm (cascade_model.py:36-41)
              "downsample1_seg.0.bias", "downsample2_seg.0.bias", "downsample3_seg.0.bias",
-             "downsample4_seg.0.bias")
+             "downsample4_seg.0.bias",
+             # order-consistency critic: Linear bias in front of BatchNorm1d (model.py:192-194)
+             "seq_consisten_model.detector.0.bias")
 LOSS_KEYS = ("se_errD", "im_errD", "st_errD", "se_errG", "im_errG", "st_errG", "im_kl", "st_kl")
 CASCADE_LOSS_KEYS = ("video_latent_loss", "image_latent_loss", "reconstruct_loss")
 IMG_KEYS = ("p1_st_fake", "p1_im_fake", "p1_se_fake", "p3_st_fake", "p3_im_fake", "p3_se_fake")
@@ -44,8 +49,15 @@ def product_inputs(batch):
     return trainer.prepare_inputs(st, im)
 
 
+def _seed_host_rngs(seed):
+    """create_random_shuffle (cfg.USE_SEQ_CONSISTENCY) draws from the two global host generators"""
+    random.seed(seed)
+    np.random.seed(seed)
+
+
 def run_product_step(p, device, seed_w=0, seed_b=1, seed_n=2, fused=False):
     import trainer
+    _seed_host_rngs(seed_b)
     states = params.init_all(p, seed_w)
     nets = build_product(p, states, device)
     feed = synth.NoiseFeed(synth.make_noise(p, seed_n, device=device))
@@ -64,6 +76,7 @@ def run_product_step(p, device, seed_w=0, seed_b=1, seed_n=2, fused=False):
 
 
 def run_oracle_step(p, device, dtype=torch.float32, seed_w=0, seed_b=1, seed_n=2):
+    _seed_host_rngs(seed_b)
     states = params.init_all(p, seed_w)
     if dtype != torch.float32:
         states = {k: {n: (t.to(dtype) if t.is_floating_point() else t) for n, t in sd.items()}
@@ -109,7 +122,7 @@ def compare(out, grads, ref_out, ref_grads, verbose=False):
             if n in ZERO_GRAD:
                 # true gradient identically zero (bias in front of a batch-statistics BatchNorm): checked by
                 # norm, relative to the gradient of the same layer's weight
-                wref = gd.get(n[:-len("bias")] + "weight")
+                wref = gd.get(n[:-len("bias")] + "weight", gd.get(n[:-len("bias")] + "weight_orig"))
                 scale = float(wref.norm()) if wref is not None else 1.0
                 ratio = float(mine.double().norm()) / max(scale, 1e-30)
                 if verbose:

@@ -253,3 +253,44 @@ def test_epilogue_column_statistics(dev, kind):
     ref = torch.stack((flat.sum(0), (flat * flat).sum(0)))
     ref[0, 0] += 5.0
     assert float((stats - ref).abs().max() / ref.abs().max()) < 1e-6, kind
+
+
+@pytest.mark.parametrize("B,T,HW,Ci,Co", [(3, 7, 16, 64, 128), (2, 4, 64, 128, 64), (4, 2, 4, 64, 64), (5, 1, 4, 64, 64)])
+def test_temporal_conv_t3(dev, B, T, HW, Ci, Co):
+    """Conv3d kernel (3, 1, 1) stride (2, 1, 1) pad (1, 0, 0) (reference model.py:160-189) as even / odd frame
+    jobs: forward, data gradient, weight gradient against torch.nn.functional.conv3d, odd and even T, T = 1"""
+    side = int(HW ** 0.5)
+    x = rnd(B, Ci, T, side, side, seed=3, dev=dev)
+    w = rnd(Co - 5, Ci - 2, 3, 1, 1, seed=4, dev=dev, scale=0.05)
+    To = (T - 1) // 2 + 1
+    xl = x.permute(0, 2, 3, 4, 1).reshape(B, T, HW, Ci).contiguous()          # [B, T, HW, C]
+    xp, x_eff = split(xl, 2)
+    wp = pack_w(w.view(Co - 5, Ci - 2, 3, 1), 0, Co, Ci, 2, dev)
+    out = torch.full((B, To, HW, Co), 7.0, device=dev)
+    for job in conv.conv_t3_fwd(xp, wp, out):
+        ops.conv_gemm(job)
+    xr = x[:, :Ci - 2].double().requires_grad_(True)
+    wr = eff_weight(w, 2).double().requires_grad_(True)
+    ref = F.conv3d(xr, wr, stride=(2, 1, 1), padding=(1, 0, 0))
+    got = out.view(B, To, side, side, Co).permute(0, 4, 1, 2, 3)
+    assert rel(got[:, :Co - 5], ref) < 3e-5
+    assert float(got[:, Co - 5:].abs().max()) == 0.0
+    # backward: single bf16 operands
+    dy = rnd(B, Co, To, side, side, seed=5, dev=dev)
+    dy[:, Co - 5:] = 0
+    dyl = bf16r(dy).permute(0, 2, 3, 4, 1).reshape(B, To, HW, Co).contiguous().to(torch.bfloat16)
+    xr2 = bf16r(x[:, :Ci - 2]).double().requires_grad_(True)
+    wr2 = bf16r(w).double().requires_grad_(True)
+    F.conv3d(xr2, wr2, stride=(2, 1, 1), padding=(1, 0, 0)).backward(bf16r(dy)[:, :Co - 5].double())
+    wt = pack_w(w.view(Co - 5, Ci - 2, 3, 1), 1, Ci, Co, 1, dev)[0]
+    dx = torch.full((B, T, HW, Ci), 7.0, device=dev)
+    for job in conv.conv_t3_dgrad(dyl, wt, dx):
+        ops.conv_gemm(job)
+    gdx = dx.view(B, T, side, side, Ci).permute(0, 4, 1, 2, 3)
+    assert rel(gdx[:, :Ci - 2], xr2.grad) < 1e-5
+    assert float(gdx[:, Ci - 2:].abs().max()) == 0.0
+    dwt = torch.zeros(3, Co, Ci, device=dev)
+    for job in conv.conv_t3_wgrad(dyl, xp[0], dwt):
+        ops.conv_gemm(job)
+    gw = dwt[:, :Co - 5, :Ci - 2].permute(1, 2, 0)
+    assert rel(gw, wr2.grad.view(Co - 5, Ci - 2, 3)) < 1e-5

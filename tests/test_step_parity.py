@@ -75,6 +75,20 @@ def test_cascade_step_emulated(monkeypatch, name):
     _check(res, small_tensor_cos=0.99 if name.startswith("tiny") else None)
 
 
+def test_order_consistency_step_emulated(monkeypatch):
+    """cfg.USE_SEQ_CONSISTENCY -- the story discriminator carries the VideoEncoder
+    critic; its BCE order loss joins the discriminator loss (miscc/utils.py:110-122) and the MSE of its logits
+    the generator loss (l.155-169).  Both sides shuffle the real stories from equally seeded host generators."""
+    emulator.install(monkeypatch)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    p = presets.get("small_seq")
+    nets, out, grads, ref_out, ref_grads = _step_pair(p, torch.device("cpu"))
+    assert any(n.startswith("seq_consisten_model.") for n in ref_grads["D_st"])
+    res = harness.compare(out, grads, ref_out, ref_grads, verbose=True)
+    print(res)
+    _check(res, small_tensor_cos=0.998)
+
+
 @pytest.mark.parametrize("name", ["tiny", "tiny_cascade"])
 def test_tiny_step_emulated_vs_reference_golden(monkeypatch, name):
     """phase-1 images, discriminator losses and discriminator gradients of the REAL reference
@@ -117,7 +131,7 @@ def _check_against_golden(gold, out, grads):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["tiny", "small", "clevr", "clevr_cascade"])
+@pytest.mark.parametrize("name", ["tiny", "small", "clevr", "clevr_cascade", "clevr_seq"])
 def test_step_gpu(name):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
