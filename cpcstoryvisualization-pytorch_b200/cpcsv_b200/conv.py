@@ -89,7 +89,7 @@ def _fwd_job(a_planes, b_planes, grid, groups, taps_per_group, taps, k_blocks, o
                    dtype=dtype, pair=use_pair(grid, tile, block_n))
 
 
-def _wgrad_job(a_view, b_view, grid, taps, m_valid, npad, out, ldc, dtype=BF16, splits=None):
+def _wgrad_job(a_view, b_view, grid, taps, m_valid, npad, out, ldc, dtype=BF16, splits=None, accumulate=False):
     tile = pixel_tile(*grid, 64)
     block_n = 256 if npad % 256 == 0 else (128 if npad % 128 == 0 else 64)
     assert npad % 64 == 0
@@ -100,7 +100,7 @@ def _wgrad_job(a_view, b_view, grid, taps, m_valid, npad, out, ldc, dtype=BF16, 
     return GemmJob(mode=1, planes=1, grid=grid, tile=tile, groups=len(taps), taps_per_group=1,
                    k_blocks=0, taps=taps, a=[a_view], b=[b_view], out=out, n_valid=npad,
                    block_n=block_n, n_tiles=n_tiles, m_valid=m_valid, splits=splits, ldc=ldc,
-                   dtype=dtype)
+                   dtype=dtype, accumulate=accumulate)
 
 
 def _planes(ts, fn):
@@ -314,13 +314,14 @@ def conv_t3_dgrad(dy, wt, dx, alpha=None):
 
 
 def conv_t3_wgrad(dy, x_hi, dwt):
-    """dwt[kt][co][ci] = sum dy[b, t_out, p, co] * x[b, 2 t_out + kt - 1, p, ci]  (fp32 ``[3, Co, Ci]``)"""
+    """dwt[kt][co][ci] += sum dy[b, t_out, p, co] * x[b, 2 t_out + kt - 1, p, ci]  (fp32 ``[3, Co, Ci]``, ZEROED by
+    the caller: the two jobs share the tensor, so neither may clear it for its split-K partial sums)"""
     B, To, HW, Co = dy.shape
     T, Ci = x_hi.shape[1], x_hi.shape[-1]
     xe, xo = _even_odd(x_hi)
     jobs = [_wgrad_job(View.nhwc(dy), View.nhwc(xe), (B, To, HW), [((0, 0, 0, 0), (0, 0, 0, 0), 1 * Co * Ci)],
-                       Co, Ci, dwt, Ci)]
+                       Co, Ci, dwt, Ci, accumulate=True)]
     if T > 1:
         taps = [((0, 0, 0, 0), (0, 0, 0, -1), 0 * Co * Ci), ((0, 0, 0, 0), (0, 0, 0, 0), 2 * Co * Ci)]
-        jobs.append(_wgrad_job(View.nhwc(dy), View.nhwc(xo), (B, To, HW), taps, Co, Ci, dwt, Ci))
+        jobs.append(_wgrad_job(View.nhwc(dy), View.nhwc(xo), (B, To, HW), taps, Co, Ci, dwt, Ci, accumulate=True))
     return jobs

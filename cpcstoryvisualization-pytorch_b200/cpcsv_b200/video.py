@@ -115,9 +115,8 @@ class TemporalNode:
 
     def _wgrad(self, dz5):
         dev = dz5.device
-        # taps whose input frame never exists (T == 1: kt = 0, 2) get no job: their gradient is zero
-        dwt = torch.zeros((3, self.Co_pad, self.Ci_pad), device=dev) if self.T == 1 \
-            else _e((3, self.Co_pad, self.Ci_pad), dev)
+        # zeroed: the even- and odd-frame jobs accumulate into it (and for T == 1 taps 0 / 2 have no job at all)
+        dwt = torch.zeros((3, self.Co_pad, self.Ci_pad), device=dev)
         for job in conv.conv_t3_wgrad(dz5, self._v(self.x.hi, self.T), dwt):
             ops.conv_gemm(job)
         g = _e((self.Co, self.Ci, 3, 1), dev)

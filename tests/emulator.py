@@ -74,6 +74,11 @@ def conv_gemm(job):
     A = [_dense_view(v) for v in job.a[:job.planes]]
     B = [_dense_view(v) for v in job.b[:job.planes]]
     accumulate = job.accumulate
+    if job.splits > 1 and not accumulate:
+        # what ops.conv_gemm does for a split-K job: the WHOLE output tensor is cleared, partial tiles are combined
+        # with red.add (so two split jobs that share one output tensor must both be 'accumulate')
+        out.zero_()
+        accumulate = True
     ncols = job.n_tiles * job.block_n
     if job.mode == 0:
         assert all(s % 4 == 0 for s in job.out_strides)
