@@ -421,7 +421,22 @@ def run_large_config(args):
     else:
         st_b, im_b = 512, 2560
         eng = StepEngine(preset_dict(st_b, im_b), device, use_graph=False, grad_sync=None)
+        if args.job_log:
+            # one line per conv_gemm launch, in launch order: joins an ncu launch list (tools/stress_table.py)
+            from cpcsv_b200 import ops
+            orig, log = ops.conv_gemm, open(args.job_log, "w")
+
+            def logged(job):
+                n, h, w = job.grid
+                log.write("%s pl=%d grid=%dx%dx%d groups=%d taps=%d kb=%d nv=%d bn=%d mv=%d splits=%d pair=%d\t%.6e\n" % (
+                    "fprop/dgrad" if job.mode == 0 else "wgrad", job.planes, n, h, w, job.groups, job.taps_per_group,
+                    job.k_blocks, job.n_valid, job.block_n, job.m_valid, job.splits, int(job.pair), job_flops(job)))
+                orig(job)
+            ops.conv_gemm = logged
         ms, launches = timed(eng.step, max(2, min(args.warmup, 3)), max(2, min(args.steps, 3)))
+        if args.job_log:
+            ops.conv_gemm = orig
+            log.close()
         gf = 659.7 * st_b
         lines.append({"metric": "train stories/s", "value": st_b / ms * 1e3, "unit": "stories/s", "n_gpus": 1,
                       "steps": max(2, min(args.steps, 3)), "warmup": max(2, min(args.warmup, 3)), "ms_per_step": ms,
@@ -465,6 +480,8 @@ def main():
     ap.add_argument("--config", default="train", choices=["train", "inference", "stress"],
                     help="train = BASELINE configs[1] (the contract line); inference = configs[3] (no-grad generator "
                          "+ segmentation branch, batch sweep); stress = configs[4] (512 stories + 2560 images / step)")
+    ap.add_argument("--job-log", default=None, help="--config stress: write one line per conv_gemm launch (signature, "
+                                                    "executed FLOPs) to this file")
     ap.add_argument("--overlap-io", action="store_true",
                     help="e2e loop: stage batch i+1 on a copy stream while step i replays (GraphedStep.load_async, the "
                          "path GANTrainer.train uses to hide LOADER latency) instead of copying every batch on the "

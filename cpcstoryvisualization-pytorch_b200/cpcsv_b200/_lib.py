@@ -71,6 +71,9 @@ SIGNATURES = {
                         _i32, _i32, _p],
     "cpcsv_im2col_small": [_p, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p,
                            _i32, _i32, _p],
+    "cpcsv_enc0_lrelu_fwd": [_p, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _p, _i32, _p, _f32, _p, _p, _i32,
+                             _i32, _p],
+    "cpcsv_lrelu_bwd16": [_p, _p, _i64, _f32, _p, _p],
     "cpcsv_col2im_small": [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     "cpcsv_head_gather_tanh": [_p, _i64, _i32, _i32, _i32, _i32, _p, _p],
     "cpcsv_tanh_bwd_im2col": [_p, _i64, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],

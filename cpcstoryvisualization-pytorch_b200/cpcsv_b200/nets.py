@@ -5,6 +5,8 @@ ONE ``torch.autograd.Function`` whose inputs are the activations plus every para
 Reference call sites: generator trunk ``model.py:379-407 / 445-470``; encoders
 ``model.py:498-514, 540-556, 582-598``; ``D_GET_LOGITS.forward`` ``model.py:86-97``.
 """
+import os as _os
+
 import torch
 
 from . import conv, engine, ops
@@ -16,6 +18,7 @@ _CACHE = engine.WeightCache()
 # activation chain (they depend on the weights only).  No measurable gain on B200 (23.3 ms either
 # way): off by default, one less layer of nested stream forks.
 SN_AHEAD = False
+DIRECT_ENC0 = _os.environ.get("CPCSV_DIRECT_ENC0", "1") != "0"     # first discriminator layer as one direct kernel
 
 
 def weight_cache():
@@ -575,17 +578,30 @@ class EncoderRunner:
             return col, self._pack0("fwd")
 
         from . import streams
-        (alpha0, alphas), (col, w0p) = streams.concurrently(power_iterations, im2col, enabled=SN_AHEAD)
-        self.col = col
-        self.alpha0 = alpha0
-        z0 = T4(n, Ho, Wo, Cop)
-        z0.f32 = _e((n, Ho, Wo, Cop), dev)
-        ops.conv_gemm(conv.gemm_nt([col.hi.view(-1, 64), col.lo.view(-1, 64)], w0p,
-                                   z0.f32.view(-1, Cop), alpha=alpha0))
-        self.z0 = z0
-        act0 = BnActNode(tape, z0, None, ops.ACT_LRELU, "enc0.act")
-        a = tape.add(act0)
-        self.act0 = act0
+        # layer 0 in ONE launch (csrc/enc0.cu: conv + 1/sigma + LeakyReLU + hi/lo planes) whenever its geometry allows;
+        # otherwise im2col -> K = 64 GEMM -> activation
+        self.direct0 = DIRECT_ENC0 and Cop <= 128 and Cin in (1, 3) and H % 4 == 0 and W % 64 == 0
+        if self.direct0:
+            alpha0, alphas = power_iterations()
+            self.alpha0, self.x0 = alpha0, xd
+            a = T4(n, Ho, Wo, Cop)
+            a.hi = _e((n, Ho, Wo, Cop), dev, torch.bfloat16)
+            a.lo = _e((n, Ho, Wo, Cop), dev, torch.bfloat16)
+            ops.enc0_lrelu_fwd(xd, w0.detach(), alpha0, 0.2, a.hi, a.lo, Cop)
+            self.a0 = a
+            self.col = self.z0 = self.act0 = None
+        else:
+            (alpha0, alphas), (col, w0p) = streams.concurrently(power_iterations, im2col, enabled=SN_AHEAD)
+            self.col = col
+            self.alpha0 = alpha0
+            z0 = T4(n, Ho, Wo, Cop)
+            z0.f32 = _e((n, Ho, Wo, Cop), dev)
+            ops.conv_gemm(conv.gemm_nt([col.hi.view(-1, 64), col.lo.view(-1, 64)], w0p,
+                                       z0.f32.view(-1, Cop), alpha=alpha0))
+            self.z0 = z0
+            act0 = BnActNode(tape, z0, None, ops.ACT_LRELU, "enc0.act")
+            a = tape.add(act0)
+            self.act0 = act0
         self.layers = []
         for li, idx in enumerate((2, 5, 8)):
             cmod, bmod = enc[idx], enc[idx + 1]
@@ -600,7 +616,10 @@ class EncoderRunner:
         self.feat = a
         Cf = enc[8].weight_orig.shape[0]
         tape.finish_forward()
-        col.lo = None
+        if self.col is not None:
+            self.col.lo = None
+        else:
+            self.a0.lo = None
         return a.f32.permute(0, 3, 1, 2)[:, :Cf]
 
     def run_backward(self, grads, needs):
@@ -617,7 +636,21 @@ class EncoderRunner:
         for nd in self.tape.nodes:
             if hasattr(nd, "x"):
                 nd.x.needs_grad = True
-        self.z0.needs_grad = True
+        w0 = self._w0()
+        Co, Ci = w0.shape[0], w0.shape[1]
+        K = 16 * Ci
+        col_hi = None
+        if self.direct0:
+            self.a0.needs_grad = True
+            if need_w:
+                # the im2col matrix the layer-0 weight gradient multiplies with: built on the side branch at the START
+                # of the backward pass (it only needs the input image), consumed there at the end
+                n, Cin, H, W = self.x_shape
+                col_hi = _e((n * (H // 2) * (W // 2), 64), dev, torch.bfloat16)
+                self.tape.aux.run(lambda: ops.im2col_small(self.x0, 4, 2, 1, col_hi, None, 64))
+        else:
+            self.z0.needs_grad = True
+            col_hi = self.col.hi.view(-1, 64)
         for cn, bn, idx in reversed(self.layers):
             bn.backward(need_w)
             pg["encode_img.%d.weight" % (idx + 1)] = bn.dgamma
@@ -625,20 +658,29 @@ class EncoderRunner:
             cn.backward(need_w)
             pg["encode_img.%d.weight_orig" % idx] = cn.dW
         # layer 0
-        self.act0.backward(False)
-        dz0 = self.z0.grad16                                    # [n, 32, 32, Cop] bf16
-        w0 = self._w0()
-        Co, Ci = w0.shape[0], w0.shape[1]
-        Cop = self.z0.C
-        K = 16 * Ci
+        if self.direct0:
+            a0 = self.a0
+            dz0 = _e((a0.N, a0.H, a0.W, a0.C), dev, torch.bfloat16)
+            ops.lrelu_bwd16(a0.grad, a0.hi, 0.2, dz0)
+            a0.grad = None
+            Cop = a0.C
+        else:
+            self.act0.backward(False)
+            dz0 = self.z0.grad16                                    # [n, 32, 32, Cop] bf16
+            Cop = self.z0.C
         dz0m = dz0.view(-1, Cop)
         if need_w:
-            d = _e((Cop, 64), dev)
-            ops.conv_gemm(conv.gemm_tn(dz0m, self.col.hi.view(-1, 64), d))
-            gw = d[:Co, :K].reshape(Co, 4, 4, Ci).permute(0, 3, 1, 2).contiguous()
-            if self.sn_first is not None:
-                gw = self.sn_first.backward(gw, w0)
-            pg[self.names[0]] = gw
+            def wgrad0():
+                d = _e((Cop, 64), dev)
+                ops.conv_gemm(conv.gemm_tn(dz0m, col_hi, d))
+                gw = d[:Co, :K].reshape(Co, 4, 4, Ci).permute(0, 3, 1, 2).contiguous()
+                if self.sn_first is not None:
+                    gw = self.sn_first.backward(gw, w0)
+                pg[self.names[0]] = gw
+            if self.direct0:
+                self.tape.aux.run(wgrad0, dz0)
+            else:
+                wgrad0()
         dx = None
         if needs[0]:
             n, Cin, H, W = self.x_shape
@@ -650,7 +692,7 @@ class EncoderRunner:
         for nme, need in zip(self.names, needs[1:]):
             out.append(pg.get(nme) if need else None)
         self.tape.release()
-        self.tape = self.layers = self.act0 = self.z0 = self.col = self.feat = None
+        self.tape = self.layers = self.act0 = self.z0 = self.col = self.feat = self.a0 = self.x0 = None
         return out
 
 

@@ -233,6 +233,24 @@ def im2col_small(x, k, s, p, hi, lo, ldp, dtype=BF16):
         _stream()), "cpcsv_im2col_small")
 
 
+def enc0_lrelu_fwd(x, w, alpha, slope, hi, lo, ldp, dtype=BF16):
+    """first discriminator layer: conv4x4 s2 p1 (raw weight w [Co, C, 4, 4]) * alpha -> LeakyReLU -> NHWC planes"""
+    N, Cc, H, W = x.shape
+    sn, sc, sh, sw = x.stride()
+    assert w.is_contiguous() and tuple(w.shape[1:]) == (Cc, 4, 4)
+    _lib.check(_lib.load().cpcsv_enc0_lrelu_fwd(
+        _ptr(x, torch.float32), N, Cc, H, W, sn, sc, sh, sw, _ptr(w, torch.float32), w.shape[0],
+        _ptr(alpha, torch.float32), slope, _ptr(hi), _ptr(lo), ldp, dtype, _stream()), "cpcsv_enc0_lrelu_fwd")
+
+
+def lrelu_bwd16(dy, a_hi, slope, dz):
+    """dz (bf16) = dy * (a_hi > 0 ? 1 : slope)"""
+    assert dy.is_contiguous() and a_hi.is_contiguous() and dz.is_contiguous() and dz.dtype == torch.bfloat16
+    assert dy.numel() == a_hi.numel() == dz.numel()
+    _lib.check(_lib.load().cpcsv_lrelu_bwd16(_ptr(dy, torch.float32), _ptr(a_hi), dy.numel(), slope, _ptr(dz),
+                                             _stream()), "cpcsv_lrelu_bwd16")
+
+
 def col2im_small(dcol, N, Cc, H, W, k, s, p, dx):
     assert dx.is_contiguous()
     _lib.check(_lib.load().cpcsv_col2im_small(

@@ -136,6 +136,27 @@ class R2Plus1dStem(nn.Sequential):
             nn.ReLU(inplace=True))
 
 
+class BasicBlock(nn.Module):
+    """Importable name of the reference (model.py:115-148): the residual R(2+1)D block.  The reference defines it
+    and never instantiates it (``VideoEncoder`` is a plain chain), so it exists here for API compatibility only:
+    it holds the same children under the same names and has no kernel path."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, conv_builder, stride=1, downsample=None):
+        super(BasicBlock, self).__init__()
+        mid = (inplanes * planes * 27) // (inplanes * 9 + 3 * planes)
+        self.conv1 = nn.Sequential(conv_builder(inplanes, planes, mid, stride), nn.BatchNorm3d(planes),
+                                   nn.ReLU(inplace=True))
+        self.conv2 = nn.Sequential(conv_builder(planes, planes, mid), nn.BatchNorm3d(planes))
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        raise NotImplementedError("BasicBlock is never built by the reference's networks (model.py:150-197 uses a "
+                                  "plain Conv3d chain); there is no accelerated path for it")
+
+
 class VideoEncoder(nn.Module):
     """Order-consistency critic (reference model.py:150-210): story [B, 3, T, H, W] -> one logit per story.
     The modules below only hold parameters (same state_dict keys as the reference); the convolutions run on the

@@ -169,6 +169,17 @@ int cpcsv_pack_nchw(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, 
 int cpcsv_im2col_small(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t sn,
                        int64_t sc, int64_t sh, int64_t sw, int32_t k, int32_t s, int32_t p,
                        void* hi, void* lo, int32_t ldp, int32_t dtype, cpcsv_stream_t stream);
+/* First discriminator layer in one launch (model.py:498-500, 540-542, 582-584): Conv2d(C, Co, 4, 2, 1,
+ * bias=False) of the strided fp32 image x (C = 1 or 3, H % 4 == 0, W % 64 == 0) with the raw weight
+ * w [Co, C, 4, 4], * alpha[0] (1 / sigma of the spectral norm, or NULL), LeakyReLU(slope), written as NHWC
+ * 16-bit hi / lo (lo optional) planes with channel pitch ldp <= 128 (channels >= Co zero). */
+int cpcsv_enc0_lrelu_fwd(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, int64_t sn, int64_t sc,
+                         int64_t sh, int64_t sw, const float* w, int32_t Co, const float* alpha, float slope,
+                         void* hi, void* lo, int32_t ldp, int32_t dtype, cpcsv_stream_t stream);
+/* LeakyReLU backward from the ACTIVATED values' hi plane (the sign survives the activation):
+ * dz[i] (bf16) = dy[i] * (a_hi[i] > 0 ? 1 : slope), count % 8 == 0. */
+int cpcsv_lrelu_bwd16(const float* dy, const void* a_hi, int64_t count, float slope, void* dz,
+                      cpcsv_stream_t stream);
 /* adjoint of im2col_small: dx[n, c, h, w] (contiguous NCHW fp32) = sum over taps of dcol */
 int cpcsv_col2im_small(const float* dcol, int64_t ldc, int32_t N, int32_t C, int32_t H, int32_t W,
                        int32_t k, int32_t s, int32_t p, float* dx, cpcsv_stream_t stream);

@@ -298,6 +298,27 @@ def im2col_small(x, k, s, p, hi, lo, ldp, dtype=1):
         lo.reshape(N * L, ldp).copy_(l)
 
 
+def enc0_lrelu_fwd(x, w, alpha, slope, hi, lo, ldp, dtype=1):
+    N, Cc, H, W = x.shape
+    Co = w.shape[0]
+    assert Cc in (1, 3) and H % 4 == 0 and W % 64 == 0 and Co <= ldp <= 128 and ldp % 8 == 0
+    z = torch.nn.functional.conv2d(x.float(), w.float(), stride=2, padding=1)
+    if alpha is not None:
+        z = z * alpha.float()
+    a = torch.where(z > 0, z, slope * z).permute(0, 2, 3, 1)
+    full = torch.zeros(N, H // 2, W // 2, ldp)
+    full[..., :Co] = a
+    h, l = _split16(full, dtype)
+    hi.copy_(h.view_as(hi))
+    if lo is not None:
+        lo.copy_(l.view_as(lo))
+
+
+def lrelu_bwd16(dy, a_hi, slope, dz):
+    assert dy.numel() % 8 == 0
+    dz.copy_((dy * torch.where(a_hi.float() > 0, 1.0, slope)).to(torch.bfloat16))
+
+
 def col2im_small(dcol, N, Cc, H, W, k, s, p, dx):
     OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
     d = dcol[:, :k * k * Cc].reshape(N, OH * OW, k * k, Cc).permute(0, 3, 2, 1).reshape(N, Cc * k * k, OH * OW)

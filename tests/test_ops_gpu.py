@@ -390,3 +390,36 @@ def test_images_to_u8_matches_the_host_formula():
     assert np.array_equal(out.cpu().numpy(), ref)
     from miscc.outputs import images_to_numpy
     assert np.array_equal(images_to_numpy(x.cuda()), ref)
+
+
+@pytest.mark.parametrize("C,Co,ldp,n,strided", [(3, 124, 128, 5, False), (1, 124, 128, 3, False), (3, 31, 64, 4, True),
+                                                  (1, 8, 64, 2, False)])
+def test_first_discriminator_layer_direct_kernel(C, Co, ldp, n, strided):
+    """cpcsv_enc0_lrelu_fwd (conv4x4 s2 p1 + 1/sigma + LeakyReLU + hi/lo planes in one launch) against
+    torch.nn.functional.conv2d in fp64, and cpcsv_lrelu_bwd16 against the activation's derivative"""
+    import torch.nn.functional as F
+    dev = torch.device("cuda")
+    x = rnd(n, C, 64, 64, seed=1).to(dev)
+    if strided:     # frames of a story: [B, C, T, H, W] -> view of frame t
+        big = rnd(n, C, 3, 64, 64, seed=2).to(dev)
+        x = big[:, :, 1]
+    w = (rnd(Co, C, 4, 4, seed=3) * 0.1).to(dev)
+    alpha = torch.tensor([0.37], device=dev)
+    for dtype, t16 in ((ops.BF16, torch.bfloat16), (ops.FP16, torch.float16)):
+        hi = torch.full((n, 32, 32, ldp), 7.0, device=dev, dtype=t16)
+        lo = torch.full((n, 32, 32, ldp), 7.0, device=dev, dtype=t16)
+        ops.enc0_lrelu_fwd(x, w, alpha, 0.2, hi, lo, ldp, dtype)
+        ref = F.leaky_relu(F.conv2d(x.double(), w.double(), stride=2, padding=1) * 0.37, 0.2).permute(0, 2, 3, 1)
+        got = hi.double() + lo.double()
+        assert float((got[..., :Co] - ref).abs().max()) <= 3e-5 * float(ref.abs().max())
+        assert float(got[..., Co:].abs().max()) == 0.0
+        assert torch.equal(hi[..., :Co], ref.float().to(t16))          # hi plane = the rounded value itself
+        only_hi = torch.empty_like(hi)
+        ops.enc0_lrelu_fwd(x, w, None, 0.2, only_hi, None, ldp, dtype)
+        ref1 = F.leaky_relu(F.conv2d(x.double(), w.double(), stride=2, padding=1), 0.2).permute(0, 2, 3, 1)
+        assert float((only_hi.double()[..., :Co] - ref1).abs().max()) <= (2 ** -8) * float(ref1.abs().max())
+        dy = rnd(n, 32, 32, ldp, seed=5).to(dev)
+        dz = torch.empty(n, 32, 32, ldp, device=dev, dtype=torch.bfloat16)
+        ops.lrelu_bwd16(dy, hi, 0.2, dz)
+        want = (dy * torch.where(hi.float() > 0, 1.0, 0.2)).to(torch.bfloat16)
+        assert torch.equal(dz, want)
