@@ -182,7 +182,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * P.stage_bytes;
           uint8_t* sb = sa + P.planes * kAPlaneBytes;
-          if (kPair) {
+          if (kPair && P.mode == 1) {
+            // weight gradient as a pair: each CTA loads its own 128 output-channel columns of A (dy) and HALF of
+            // the B (x) channel block for the same 64 pixels
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
+            const uint32_t bar = mapa_u32(&full_bar[stage], 0);
+            const cpcsv_tap_t& tap = P.taps[tc.group];
+            pixel_tile_origin(P, it, n0, h0, w0);
+            const int32_t half_n = P.block_n / 2;
+            for (int pl = 0; pl < P.planes; ++pl) {
+              for (int j = 0; j < 2; ++j)
+                tma_load_5d_pair(pl ? &tmA1 : &tmA0, bar, sa + pl * kAPlaneBytes + j * 8192,
+                                 tap.a[0] + tc.m_idx * kBlockM + j * 64, w0 + tap.a[1], tap.a[2],
+                                 h0 + tap.a[3], n0);
+              for (int j = 0; j < half_n / 64; ++j)
+                tma_load_5d_pair(pl ? &tmB1 : &tmB0, bar, sb + pl * P.b_plane_bytes + j * 8192,
+                                 tap.b[0] + tc.n_idx * P.block_n + static_cast<int32_t>(rank) * half_n + j * 64,
+                                 w0 + tap.b[1], tap.b[2], h0 + tap.b[3], n0);
+            }
+          } else if (kPair) {
             // both CTAs' bytes are accounted on the leader's barrier
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
             const uint32_t bar = mapa_u32(&full_bar[stage], 0);
@@ -599,9 +617,11 @@ extern "C" int cpcsv_conv_gemm(const cpcsv_gemm_t* job, cpcsv_stream_t stream_) 
     P.taps[i] = J.taps[i];
     CPCSV_REQUIRE(J.taps[i].out_off % 4 == 0, "conv_gemm: tap %d out_off alignment", i);
   }
-  // CTA-pair mode (cta_group::2): fprop / dgrad jobs with at least two 128-row tiles
-  CPCSV_REQUIRE(J.cta_pair == 0 || (J.mode == 0 && J.block_n >= 32 && (J.block_n / 2) % 8 == 0),
-                "conv_gemm: cta_pair needs mode 0 and block_n a multiple of 16 >= 32");
+  // CTA-pair mode (cta_group::2): jobs with at least two 128-row tiles whose B tile can be halved
+  // (fprop / dgrad: any block_n >= 32 in steps of 16; wgrad: whole 64-channel atoms per CTA)
+  CPCSV_REQUIRE(J.cta_pair == 0 || (J.mode == 0 && J.block_n >= 32 && (J.block_n / 2) % 8 == 0) ||
+                    (J.mode == 1 && (J.block_n / 2) % 64 == 0),
+                "conv_gemm: cta_pair needs block_n a multiple of 16 >= 32 (mode 0) or of 128 (mode 1)");
   const bool pair = J.cta_pair != 0 && pair_mode_enabled() && P.m_tiles >= 2;
   P.m_units = pair ? (P.m_tiles + 1) / 2 : P.m_tiles;
   const int64_t total = static_cast<int64_t>(P.groups) * P.splits * P.n_tiles * P.m_units;

@@ -78,9 +78,11 @@ typedef struct {
   int32_t n_tiles;
   int32_t splits;                 /* split-K factor (>1 forces atomic accumulation) */
   int32_t accumulate;             /* 1: add into `out` instead of overwriting */
-  int32_t cta_pair;               /* mode 0: 1 = run as cta_group::2 pairs (two CTAs of a cluster share
-                                     every B tile: half the weight traffic per SM); pays off on long
-                                     jobs, costs a few microseconds of cluster launch on short ones */
+  int32_t cta_pair;               /* 1 = run as cta_group::2 pairs: two CTAs of a cluster (two 128-row M tiles)
+                                     share every B tile, each loading half of it -- half the B traffic per SM.
+                                     mode 0: block_n >= 32 in steps of 16; mode 1: block_n 128 or 256 (whole
+                                     64-channel atoms per CTA).  Pays off on long jobs, costs a few microseconds
+                                     of cluster launch on short ones */
   int64_t out_stride_n, out_stride_h, out_stride_w; /* mode 0: elements per pixel step */
   int64_t ldc;                    /* mode 1: row pitch of each output matrix (elements) */
   const float* alpha;             /* optional device scalar multiplied into the result */

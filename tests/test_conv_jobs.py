@@ -294,3 +294,26 @@ def test_temporal_conv_t3(dev, B, T, HW, Ci, Co):
         ops.conv_gemm(job)
     gw = dwt[:, :Co - 5, :Ci - 2].permute(1, 2, 0)
     assert rel(gw, wr2.grad.view(Co - 5, Ci - 2, 3)) < 1e-5
+
+
+@pytest.mark.parametrize("geom,N,H,Ci,Co", [("s1", 6, 8, 128, 256), ("s1", 20, 4, 256, 384), ("s2", 5, 16, 128, 512),
+                                             ("up", 3, 8, 384, 256), ("s1", 40, 8, 320, 256)])
+def test_wgrad_as_cta_pairs(dev, geom, N, H, Ci, Co):
+    """weight-gradient jobs with more than one 128-channel M tile run as cta_group::2 pairs (conv.WGRAD_PAIR):
+    even and odd numbers of M tiles, block_n 256 / 128 (and 64: no pair), split-K"""
+    x = bf16r(rnd(N, Ci, H, H, seed=31, dev=dev))
+    w = bf16r(rnd(Co, Ci, 4 if geom == "s2" else 3, 4 if geom == "s2" else 3, seed=32, dev=dev, scale=0.05))
+    Ho = {"s1": H, "s2": H // 2, "up": 2 * H}[geom]
+    dy = bf16r(rnd(N, Co, Ho, Ho, seed=33, dev=dev))
+    fwd = {"s1": lambda a, b: F.conv2d(a, b, padding=1), "s2": lambda a, b: F.conv2d(a, b, stride=2, padding=1),
+           "up": lambda a, b: F.conv2d(F.interpolate(a, scale_factor=2, mode="nearest"), b, padding=1)}[geom]
+    _gx, gw = _grad_refs(fwd, x, w, dy)
+    dy16, x16 = nhwc(dy).to(torch.bfloat16), nhwc(x).to(torch.bfloat16)
+    ntap = {"s1": 9, "s2": 16, "up": 16}[geom]
+    dwt = torch.full((ntap, Co, Ci), 7.0, device=dev)
+    job = {"s1": conv.conv_s1_wgrad, "s2": conv.conv_s2_wgrad, "up": conv.upconv_wgrad}[geom](dy16, x16, dwt)
+    assert job.pair == (job.block_n % 128 == 0)
+    ops.conv_gemm(job)
+    dw = torch.empty_like(w)
+    ops.unpack_conv_wgrad(dwt, Co * Ci, Ci, 2 if geom == "up" else 0, None, dw)
+    assert rel(dw, gw) < 1e-5
