@@ -17,9 +17,14 @@ ONE step counter (``state[p]["step"]`` is the same device tensor for every p), i
 had no gradient in some step still advances its bias correction -- on this path every parameter gets
 a gradient in every step.
 """
+import os
+
 import torch
 
 from . import ops
+
+# issue the update kernels on a stream of the LOWEST priority (see PackedAdam.step); CPCSV_ADAM_LOW_PRIORITY=0: off
+LOW_PRIORITY = os.environ.get("CPCSV_ADAM_LOW_PRIORITY", "1") != "0"
 
 
 class PackedAdam(torch.optim.Optimizer):
@@ -40,7 +45,7 @@ class PackedAdam(torch.optim.Optimizer):
         self._early_params, self._early_ids = [], set()
         self._armed, self._pending, self._done = False, set(), set()
         self._ticked = set()
-        self._side, self._side_used = None, False
+        self._side, self._side_used, self._low = None, False, None
         self._pre_update, self.early_fired = None, False
 
     # ---- device-side scalars ----------------------------------------------------------------
@@ -104,7 +109,7 @@ class PackedAdam(torch.optim.Optimizer):
             return
         cur = torch.cuda.current_stream()
         if self._side is None:
-            self._side = torch.cuda.Stream(device=p.device, priority=cur.priority)
+            self._side = torch.cuda.Stream(device=p.device, priority=0 if LOW_PRIORITY else cur.priority)
         self._side.wait_stream(cur)          # this gradient is complete in stream order of `cur`
         self._side_used = True
         self._pending.discard(id(p))
@@ -188,7 +193,19 @@ class PackedAdam(torch.optim.Optimizer):
             # the early part runs on the side stream: same step count / bias corrections, other parameters
             torch.cuda.current_stream().wait_stream(self._side)
             self._side_used = False
-        self._update(None)
+        if LOW_PRIORITY and torch.cuda.is_available() and any(p.is_cuda for g in self.param_groups for p in g["params"]):
+            # the update kernels are large HBM-bound grids: on a stream of the lowest priority the block scheduler
+            # hands free SM slots to the latency-bound chains of the other streams first (the conditioning-path
+            # backward at the end of the generator update stalled ~0.5 ms behind them at equal priority)
+            cur = torch.cuda.current_stream()
+            if self._low is None:
+                self._low = torch.cuda.Stream(device=cur.device, priority=0)
+            self._low.wait_stream(cur)
+            with torch.cuda.stream(self._low):
+                self._update(None)
+            cur.wait_stream(self._low)
+        else:
+            self._update(None)
         self._done.clear()
         self._ticked.clear()
         return loss
