@@ -213,6 +213,22 @@ class StateOrder:
         cls._last[tensor.data_ptr()] = (cur, ev, torch.cuda.is_current_stream_capturing())
 
 
+# ------------------------------------------------------------------------------ gradient sink
+# An optimiser that wants parameter gradients the moment a tape has computed them (optim.PackedAdam with
+# ``overlap_with_backward(..., buckets=...)``): the generator trunk is ONE autograd Function, so autograd hands all of
+# its parameter gradients over together, at the very end of its backward pass -- the sink gets each layer's
+# gradients right after that layer's weight-gradient GEMM instead.
+_GRAD_SINK = [None]
+
+
+def set_grad_sink(sink):
+    _GRAD_SINK[0] = sink
+
+
+def grad_sink():
+    return _GRAD_SINK[0]
+
+
 # ------------------------------------------------------------------------------ aux branch
 WGRAD_ON_AUX_STREAM = True
 _AUX_STREAMS = {}

@@ -288,6 +288,10 @@ class TrunkRunner:
         N, K = zmc_all.shape
         tape = Tape(_CACHE, training=G.training, need_grad=self.need_grad, stat_chunk=1 << 18)
         self.tape = tape
+        self.sink = engine.grad_sink() if self.need_grad else None
+        if self.sink is not None:
+            # this call's backward pass will offer one contribution per parameter (see run_backward)
+            self.sink.announce([self.params[n] for n in self.names])
         ngf, nseg = G.gf_dim, G.gf_dim_seg
         x0 = self._latent_planes(tape, zmc_all)
 
@@ -414,6 +418,26 @@ class TrunkRunner:
         if seg_tail:
             self._head_bwd(self.a_seg, G.img_seg[0].weight, self.seg, d_seg, need_w, pg, "img_seg.0.weight")
 
+        taken, offered = set(), set()
+        need_of = dict(zip(self.names, needs[1:]))
+
+        def offer(*names):
+            """hand finished parameter gradients to the optimiser's gradient sink (engine.grad_sink) on the weight-
+            gradient side branch, i.e. after the kernels that produce them"""
+            if self.sink is None:
+                return
+
+            def run():
+                for n in names:
+                    if n not in offered and need_of.get(n):
+                        offered.add(n)
+                        if self.sink.offer(self.params[n], pg.get(n)):
+                            taken.add(n)
+            self.tape.aux.run(run)
+
+        if d_img is not None:
+            offer("img.0.weight")
+
         def bn_conv_bwd(bn_name, conv_name, prefix_bn, prefix_conv):
             bn, cv = nodes[bn_name], nodes[conv_name]
             if bn.out.grad is None:
@@ -422,6 +446,7 @@ class TrunkRunner:
             pg[prefix_bn + ".weight"], pg[prefix_bn + ".bias"] = bn.dgamma, bn.dbeta
             cv.backward(need_w)
             pg[prefix_conv] = cv.dW
+            offer(prefix_bn + ".weight", prefix_bn + ".bias", prefix_conv)
             return True
 
         # image branch, top down; level 1 also emits the seg_c1 gradient, level 0 seg_c's
@@ -430,23 +455,29 @@ class TrunkRunner:
             if i == 1 and nodes["seg_c1"].out.grad16 is not None:
                 nodes["seg_c1"].backward(need_w)
                 pg["seg_c1.weight"] = nodes["seg_c1"].dW
+                offer("seg_c1.weight")
         self._fc_bwd("fc", need_w, pg)
+        offer("fc.1.weight", "fc.1.bias", "fc.0.weight")
         if nodes["seg_c"].out.grad16 is not None:
             nodes["seg_c"].backward(need_w)
             pg["seg_c.weight"] = nodes["seg_c"].dW
+            offer("seg_c.weight")
+        if seg_tail:
+            offer("img_seg.0.weight")
         for i in (4, 3, 2, 1):
             bn_conv_bwd("upsample%d_seg.bn" % i, "upsample%d_seg" % i, "upsample%d_seg.2" % i,
                         "upsample%d_seg.1.weight" % i)
         self._fc_bwd("fc_seg", need_w, pg)
+        offer(*self.names)        # whatever is left (layers without a gradient in this call offer None)
         self.tape.aux.join()
         dz = None
         if needs[0] and self.x0.grad is not None:
             dz = self.x0.grad.view(self.x0.N, self.x0.C)[:, :self.K]
         out = [dz]
         for n, need in zip(self.names, needs[1:]):
-            out.append(pg.get(n) if need else None)
+            out.append(pg.get(n) if need and n not in taken else None)
         self.tape.release()
-        self.tape = self.nodes = self.alias = self.a_img = self.a_seg = self.x0 = None
+        self.tape = self.nodes = self.alias = self.a_img = self.a_seg = self.x0 = self.sink = None
         return out
 
     def _all_acts(self):

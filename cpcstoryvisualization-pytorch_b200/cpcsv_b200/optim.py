@@ -46,6 +46,7 @@ class PackedAdam(torch.optim.Optimizer):
         self._armed, self._pending, self._done = False, set(), set()
         self._ticked = set()
         self._side, self._side_used, self._low = None, False, None
+        self._buckets, self._bucket_of, self._expected, self._last_event = [], {}, {}, {}
         self._pre_update, self.early_fired = None, False
 
     # ---- device-side scalars ----------------------------------------------------------------
@@ -69,28 +70,105 @@ class PackedAdam(torch.optim.Optimizer):
         return st
 
     # ---- optimiser step inside the backward pass ------------------------------------------------
-    def overlap_with_backward(self, params):
+    def overlap_with_backward(self, params, buckets=None):
         """Declare `params` (the generator trunk: 99.9 % of its bytes) as "early": once ``expect_backward``
-        has armed the optimiser, their Adam + re-layout kernels are issued on a side stream the moment the
-        LAST of their gradients has been accumulated -- while autograd still runs the rest of the backward
-        pass (the latency-bound conditioning path) -- instead of after it.  ``step()`` then only updates the
-        remaining parameters and joins the side stream.  Results are identical to a plain ``step()``."""
+        has armed the optimiser, their Adam + re-layout kernels are issued on a side stream the moment their
+        gradients are complete -- while autograd still runs the rest of the backward pass -- instead of after it.
+        ``step()`` then only updates the remaining parameters and joins the side stream.  Results are identical to
+        a plain ``step()``.
+
+        Two ways the gradients arrive.  (1) autograd: a post-accumulate hook per parameter; the update fires when
+        the LAST early parameter has its gradient.  (2) ``buckets`` (lists of parameters, e.g. one per layer): the
+        optimiser also registers as the kernel tapes' gradient sink (engine.set_grad_sink); a tape ``announce`` s the
+        parameters it will produce gradients for at forward time and ``offer`` s each layer's gradients right after
+        that layer's weight-gradient kernels, and a bucket's update fires as soon as every announced contribution
+        to its parameters has been offered -- layer by layer, under the rest of the backward pass."""
         self._early_params = [p for p in params]
         self._early_ids = {id(p) for p in self._early_params}
         for p in self._early_params:
             p.register_post_accumulate_grad_hook(self._grad_ready)
+        self._buckets, self._bucket_of = [], {}
+        if buckets:
+            for b in buckets:
+                b = [p for p in b if id(p) in self._early_ids]
+                if b:
+                    for p in b:
+                        self._bucket_of[id(p)] = len(self._buckets)
+                    self._buckets.append(b)
+            from . import engine
+            engine.set_grad_sink(self)
 
     def expect_backward(self, pre_update=None):
         """arm the early step for the NEXT backward pass only (a backward pass that is not followed by
         ``step()`` -- gradient checks -- must not be armed).  ``pre_update(params)``: called on the side
-        stream right before the early parameters are updated -- the gradient exchange between ranks
+        stream right before early parameters are updated -- the gradient exchange between ranks
         (trainer.GradSync) for exactly those parameters; ``early_fired`` tells the caller afterwards whether
-        it ran (then only the remaining parameters are left to exchange)."""
+        it ran (then ``updated_ids()`` are done and only the remaining parameters are left to exchange)."""
         self.early_fired = False
         self._pre_update = pre_update
         if self._early_params:
             self._armed = True
             self._pending = set(self._early_ids)
+
+    # ---- gradient sink of the kernel tapes (engine.grad_sink) --------------------------------------
+    def announce(self, params):
+        """a tape whose backward pass will ``offer`` exactly one contribution (possibly None) for each of
+        `params`; counted until the next ``step()``"""
+        for p in params:
+            if id(p) in self._bucket_of:
+                self._expected[id(p)] = self._expected.get(id(p), 0) + 1
+
+    def offer(self, p, grad):
+        """one tape's gradient contribution for `p` (None: that tape has none), produced on the CURRENT stream.
+        Returns True when the optimiser took it (the tape must then NOT hand it to autograd as well)."""
+        pid = id(p)
+        if not self._armed or pid not in self._bucket_of or self._expected.get(pid, 0) <= 0:
+            return False
+        cur = torch.cuda.current_stream() if p.is_cuda else None
+        if grad is not None:
+            if p.grad is None:
+                p.grad = grad
+            else:
+                last = self._last_event.get(pid)
+                if last is not None:
+                    cur.wait_event(last)         # the earlier contribution was written on another stream
+                p.grad.add_(grad)
+            if cur is not None:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self._last_event[pid] = ev
+        self._expected[pid] -= 1
+        bucket = self._buckets[self._bucket_of[pid]]
+        if any(self._expected.get(id(q), 0) > 0 for q in bucket):
+            return True
+        ready = [q for q in bucket if q.grad is not None and id(q) not in self._done]
+        if not ready:
+            return True
+        if cur is None:                      # host-logic tests on the CPU emulator: no streams
+            self._fire(ready)
+            return True
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=p.device, priority=0 if LOW_PRIORITY else cur.priority)
+        self._side.wait_stream(cur)
+        for q in bucket:
+            ev = self._last_event.get(id(q))
+            if ev is not None:
+                self._side.wait_event(ev)
+        self._side_used = True
+        with torch.cuda.stream(self._side):
+            self._fire(ready)
+        return True
+
+    def _fire(self, params):
+        if self._pre_update is not None:
+            self._pre_update(params)
+        self.early_fired = True
+        self._pending.difference_update(id(q) for q in params)
+        self._update(params)
+
+    def updated_ids(self):
+        """ids of the parameters already updated in this step (by the early paths)"""
+        return set(self._done)
 
     def early_parameters(self):
         return list(self._early_params)
@@ -119,7 +197,9 @@ class PackedAdam(torch.optim.Optimizer):
                 self._early_step()
 
     def _early_step(self):
-        params = [q for q in self._early_params if q.grad is not None]
+        params = [q for q in self._early_params if q.grad is not None and id(q) not in self._done]
+        if not params:
+            return
         if self._pre_update is not None:
             self._pre_update(params)
         self.early_fired = True
@@ -208,4 +288,6 @@ class PackedAdam(torch.optim.Optimizer):
             self._update(None)
         self._done.clear()
         self._ticked.clear()
+        self._expected.clear()
+        self._last_event.clear()
         return loss

@@ -118,9 +118,14 @@ def build_optimizers(nets, fused=None, lr_tensor_device=None):
             if k == "G" and not hasattr(net, "presample"):
                 # the trunk's Adam + re-layout kernels are issued as soon as its gradients are complete,
                 # overlapping the backward pass of the conditioning path (armed per step in train_step)
+                # -- layer by layer: one bucket per trunk module (conv / Linear weight + its BatchNorm)
                 named = dict(net.named_parameters())
-                opts[k].overlap_with_backward([named[n] for n in knets.TrunkRunner.parameter_names()
-                                               if n in named and named[n].requires_grad])
+                early = [n for n in knets.TrunkRunner.parameter_names() if n in named and named[n].requires_grad]
+                buckets = {}
+                for n in early:
+                    buckets.setdefault(n.split(".")[0], []).append(named[n])
+                opts[k].overlap_with_backward([named[n] for n in early],
+                                              buckets=list(buckets.values()) if LAYERWISE_G_ADAM else None)
         else:
             opts[k] = optim.Adam(params, lr=lr, betas=(0.5, 0.999))
     return opts
@@ -163,6 +168,7 @@ D_NETS = ("D_se", "D_im", "D_st")
 CONCURRENT_D = True     # run the three discriminators on parallel CUDA streams
 CONCURRENT_G = True     # run sample_videos / sample_images of one phase on two streams
 EARLY_G = True          # issue the generator-update forward alongside the discriminator update
+LAYERWISE_G_ADAM = os.environ.get("CPCSV_LAYERWISE_ADAM", "1") != "0"   # trunk Adam per layer, under the backward pass
 EARLY_D_REAL = True     # issue the discriminators' real-image encoder passes before the fakes exist
 step_stream = streams.step_stream
 Detached = streams.Detached
@@ -351,7 +357,7 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
         if hasattr(opts["G"], "disarm"):
             opts["G"].disarm()
     if exchange and early and opts["G"].early_fired:
-        done = {id(p) for p in opts["G"].early_parameters()}
+        done = opts["G"].updated_ids()
         grad_sync([p for p in nets["G"].parameters() if id(p) not in done])
     else:
         sync_grads(nets, ("G",), grad_sync)

@@ -192,3 +192,37 @@ def test_early_step_inside_backward_gives_the_same_update(dev):
     opt.zero_grad(set_to_none=True)
     loss(P).backward()
     assert all(torch.equal(before[k], P[k].detach()) for k in P)
+
+
+def test_generator_update_inside_backward_matches_plain_adam(dev, monkeypatch):
+    """one whole train step with the generator trunk's Adam fired from inside the backward pass -- (a) layer by
+    layer through the tapes' gradient sink, (b) once, from autograd hooks -- against (c) plain torch.optim.Adam
+    after the backward pass: same accumulated gradients (every tape's contribution counted exactly once) and the
+    same weights.  The first Adam step is sign(g)-like, so weights are compared in the mean, in units of lr."""
+    import harness
+    import trainer
+    from oracle import presets
+    p = presets.get("tiny")
+    lr = p["GENERATOR_LR"]
+    monkeypatch.setattr(trainer, "LAYERWISE_G_ADAM", True)
+    nets_a, _o, grads_a = harness.run_product_step(p, dev, fused=True)
+    sink = engine.grad_sink()
+    assert sink is not None and len(sink._buckets) >= 10
+    monkeypatch.setattr(trainer, "LAYERWISE_G_ADAM", False)
+    engine.set_grad_sink(None)
+    nets_b, _o, grads_b = harness.run_product_step(p, dev, fused=True)
+    nets_c, _o, grads_c = harness.run_product_step(p, dev, fused=False)
+    trunk = set(nets.TrunkRunner.parameter_names())
+    for n in grads_a["G"]:
+        if n in harness.ZERO_GRAD:
+            continue
+        ga, gb, gc = (g["G"][n].double().cpu().flatten() for g in (grads_a, grads_b, grads_c))
+        assert float((ga - gb).norm()) <= 1e-5 * float(gb.norm()), n       # same kernels, same contributions
+        assert float((ga - gc).norm()) <= 2e-2 * float(gc.norm()), n       # D weights differ by the optimisers' 1e-6
+    for (n, a), (_n, b), (_m, c) in zip(nets_a["G"].named_parameters(), nets_b["G"].named_parameters(),
+                                         nets_c["G"].named_parameters()):
+        if n in harness.ZERO_GRAD:
+            continue
+        a, b, c = (t.detach().double().cpu() for t in (a, b, c))
+        assert float((a - b).abs().mean()) <= 0.02 * lr, n
+        assert float((a - c).abs().mean()) <= 0.10 * lr, (n, n in trunk)
