@@ -202,8 +202,11 @@ def test_generator_update_inside_backward_matches_plain_adam(dev, monkeypatch):
     import harness
     import trainer
     from oracle import presets
-    p = presets.get("tiny")
+    # discriminator learning rate 0: their (sign-like) first Adam step would turn the GPU's summation-order noise
+    # into 2 * lr weight differences and those into percent-level differences of the generator gradients
+    p = presets.get("tiny", DISCRIMINATOR_LR=0.0)
     lr = p["GENERATOR_LR"]
+    tol = 1e-5 if dev.type == "cpu" else 2e-4
     monkeypatch.setattr(trainer, "LAYERWISE_G_ADAM", True)
     nets_a, _o, grads_a = harness.run_product_step(p, dev, fused=True)
     sink = engine.grad_sink()
@@ -217,8 +220,8 @@ def test_generator_update_inside_backward_matches_plain_adam(dev, monkeypatch):
         if n in harness.ZERO_GRAD:
             continue
         ga, gb, gc = (g["G"][n].double().cpu().flatten() for g in (grads_a, grads_b, grads_c))
-        assert float((ga - gb).norm()) <= 1e-5 * float(gb.norm()), n       # same kernels, same contributions
-        assert float((ga - gc).norm()) <= 2e-2 * float(gc.norm()), n       # D weights differ by the optimisers' 1e-6
+        assert float((ga - gb).norm()) <= tol * float(gb.norm()), n       # same kernels, same contributions
+        assert float((ga - gc).norm()) <= tol * float(gc.norm()), n
     for (n, a), (_n, b), (_m, c) in zip(nets_a["G"].named_parameters(), nets_b["G"].named_parameters(),
                                          nets_c["G"].named_parameters()):
         if n in harness.ZERO_GRAD:
