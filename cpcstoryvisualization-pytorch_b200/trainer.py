@@ -124,8 +124,12 @@ def build_optimizers(nets, fused=None, lr_tensor_device=None):
                 buckets = {}
                 for n in early:
                     buckets.setdefault(n.split(".")[0], []).append(named[n])
+                # (one rank only: with a gradient exchange every bucket costs a flat copy + a small all-reduce, measured
+                # 22.15 vs 21.68 ms / step at 2 GPUs -- there the whole trunk is exchanged and updated at once)
+                layerwise = LAYERWISE_G_ADAM and not (dist.is_available() and dist.is_initialized()
+                                                      and dist.get_world_size() > 1)
                 opts[k].overlap_with_backward([named[n] for n in early],
-                                              buckets=list(buckets.values()) if LAYERWISE_G_ADAM else None)
+                                              buckets=list(buckets.values()) if layerwise else None)
         else:
             opts[k] = optim.Adam(params, lr=lr, betas=(0.5, 0.999))
     return opts

@@ -206,7 +206,9 @@ def test_generator_update_inside_backward_matches_plain_adam(dev, monkeypatch):
     # into 2 * lr weight differences and those into percent-level differences of the generator gradients
     p = presets.get("tiny", DISCRIMINATOR_LR=0.0)
     lr = p["GENERATOR_LR"]
-    tol = 1e-5 if dev.type == "cpu" else 2e-4
+    # GPU: fp32 summation order varies run to run; one flipped bf16 rounding is 4e-3 of an element (measured 5e-4
+    # on the GRU weights' gradient); a lost or doubled contribution would be O(1)
+    tol = 1e-5 if dev.type == "cpu" else 3e-3
     monkeypatch.setattr(trainer, "LAYERWISE_G_ADAM", True)
     nets_a, _o, grads_a = harness.run_product_step(p, dev, fused=True)
     sink = engine.grad_sink()
