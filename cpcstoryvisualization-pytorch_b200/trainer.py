@@ -341,7 +341,8 @@ def sync_grads(nets, names, grad_sync, inplace=False):
                 grad_sync(list(nets[k].parameters()))
 
 
-def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=True, skip_d_wgrad=True):
+def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=True, skip_d_wgrad=True,
+               after_discriminators=None):
     """One iteration of the reference's hot loop (trainer.py:290-416).  ``x`` from
     ``prepare_inputs`` (device tensors), ``labels`` = (im_ones, im_zeros, st_ones, st_zeros).
     Returns a dict of loss tensors (no host sync)."""
@@ -350,6 +351,8 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
                                grad_sync=grad_sync if exchange else None)
     if not apply_optim:
         sync_grads(nets, D_NETS, grad_sync)
+    if after_discriminators is not None:
+        after_discriminators()      # the real images have been read for the last time (GraphedStep.load_async)
     early = apply_optim and hasattr(opts["G"], "expect_backward")
     if early:
         # the generator's Adam step starts inside the backward pass; with several ranks the gradient
@@ -431,6 +434,10 @@ class GraphedStep:
             self.loss_host = self.loss_host.pin_memory()
         self._copy_stream = self._staging = None
         self._pending = False
+        # recorded INSIDE the step (an external event node of the graph) once the discriminator stage is over:
+        # from there on nothing reads the real images, the next batch may be copied over them
+        self._inputs_free = None
+        self._io_done, self._late, self._pending_direct = None, None, False
 
     # --- static buffers ----------------------------------------------------------------------
     def fits(self, st_batch, im_batch):
@@ -447,13 +454,40 @@ class GraphedStep:
             for k, t in dst.items():
                 t.copy_(src[k], non_blocking=True)
 
+    def _early_free(self):
+        """(static buffer, batch index, key) of the inputs nothing reads after the discriminator stage: the real
+        images (the cascade generator's reconstruction loss reads the real masks in the generator stage)"""
+        keys = [(self.dev_st["images"], 0, "images"), (self.dev_im["images"], 1, "images")]
+        if not hasattr(self.nets["G"], "presample"):
+            keys.append((self.dev_im["images_seg"], 1, "images_seg"))
+        return keys
+
     def load_async(self, st_batch, im_batch):
-        """Pipelined ``load``: the host-to-device copy goes to a staging set of buffers on a copy
-        stream, so the copy of step k+1's inputs overlaps the replay of step k; the next ``step``
-        waits for it and moves staging -> static buffers with one multi-tensor device copy.
-        (Not yet exercised on a GPU -- bench.py ``--overlap-io``; ``load`` is the default.)"""
+        """Pipelined ``load`` of step k+1's inputs while step k is still being replayed (call it right after
+        ``step()``).  With the whole step in one graph the real images -- 92 % of the bytes -- go STRAIGHT into the
+        static buffers on a copy stream, as soon as step k's graph has passed its discriminator stage (an external
+        event recorded inside the graph): the copy hides under the generator stage.  The few small tensors the
+        generator stage still reads (descriptions, labels) are copied by the next ``step()`` right before its
+        replay.  Without that event (eager step, three-graph variant) everything goes to a staging set of buffers
+        and the next ``step`` moves staging -> static buffers with one multi-tensor device copy."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
+        if self._inputs_free is not None and self.graph is not None and not self.segmented:
+            if self._io_done is None:
+                self._io_done = torch.cuda.Event()
+            batches = (st_batch, im_batch)
+            early = self._early_free()
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._inputs_free)
+                for dst, bi, k in early:
+                    dst.copy_(batches[bi][k], non_blocking=True)
+                self._io_done.record(self._copy_stream)
+            taken = {id(dst) for dst, _bi, _k in early}
+            self._late = [(t, src[k]) for d, src in ((self.dev_st, st_batch), (self.dev_im, im_batch))
+                          for k, t in d.items() if id(t) not in taken]
+            self._pending_direct = True
+            return
+        if self._staging is None:
             self._staging = [{k: torch.empty_like(t) for k, t in d.items()} for d in (self.dev_st, self.dev_im)]
             self._ready, self._consumed = torch.cuda.Event(), torch.cuda.Event()
         with torch.cuda.stream(self._copy_stream):
@@ -463,6 +497,13 @@ class GraphedStep:
                     t.copy_(src[k], non_blocking=True)
             self._ready.record(self._copy_stream)
         self._pending = True
+
+    def _consume_direct(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._io_done)
+        for dst, src in self._late:
+            dst.copy_(src, non_blocking=True)
+        self._late, self._pending_direct = None, False
 
     def _consume_staging(self):
         cur = torch.cuda.current_stream()
@@ -491,7 +532,12 @@ class GraphedStep:
         from miscc.utils import accuracy_on_device
         x = prepare_inputs(self.dev_st, self.dev_im)
         with accuracy_on_device():          # no host round trip inside the step (scoped, not process-wide)
-            self._record(train_step(self.nets, self.opts, x, self.labels, self.ratio, self.grad_sync))
+            self._record(train_step(self.nets, self.opts, x, self.labels, self.ratio, self.grad_sync,
+                                    after_discriminators=self._mark_inputs_free))
+
+    def _mark_inputs_free(self):
+        if self._inputs_free is not None:
+            self._inputs_free.record()
 
     # the step in three segments, with the NCCL gradient exchange between them
     def _seg_d(self):
@@ -528,6 +574,7 @@ class GraphedStep:
             kw["capture_error_mode"] = capture_error_mode
         if not self.segmented:
             self.graph = torch.cuda.CUDAGraph()
+            self._inputs_free = torch.cuda.Event(external=True) if self.device.type == "cuda" else None
             if self.grad_sync is not None and getattr(self.grad_sync, "enabled", False):
                 kw["capture_error_mode"] = "thread_local"   # the NCCL watchdog thread keeps running
             with torch.cuda.graph(self.graph, stream=stream, **kw):
@@ -559,6 +606,8 @@ class GraphedStep:
                 p.grad = g
 
     def step(self):
+        if self._pending_direct:
+            self._consume_direct()
         if self._pending:
             self._consume_staging()
         if self.graph is None:
