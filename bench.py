@@ -482,11 +482,12 @@ def main():
                          "+ segmentation branch, batch sweep); stress = configs[4] (512 stories + 2560 images / step)")
     ap.add_argument("--job-log", default=None, help="--config stress: write one line per conv_gemm launch (signature, "
                                                     "executed FLOPs) to this file")
-    ap.add_argument("--overlap-io", action="store_true",
-                    help="e2e loop: stage batch i+1 on a copy stream while step i replays (GraphedStep.load_async, the "
-                         "path GANTrainer.train uses to hide LOADER latency) instead of copying every batch on the "
-                         "step's own stream.  With the bench's ready-made pinned batch the plain copy is faster "
-                         "(0.4 ms of PCIe time per step vs 0.6-1.3 ms measured for the staged path, gpurun_out r02_c9)")
+    ap.add_argument("--serial-io", action="store_true",
+                    help="e2e loop: copy every batch on the step's own stream before the replay (the round-1 path).  "
+                         "Default: GraphedStep.load_async, the path GANTrainer.train uses -- the real images of batch "
+                         "i+1 are copied straight into the static buffers on a copy stream once step i's graph has "
+                         "passed its discriminator stage (measured on one box: 20.41 / 20.68 vs 20.80 / 20.71 ms)")
+    ap.add_argument("--overlap-io", action="store_true", help="(default since round 2)")
     ap.add_argument("--whole-graph", action="store_true",
                     help="(default since round 2) N > 1: the NCCL all-reduces are captured inside the ONE step graph")
     ap.add_argument("--segmented", action="store_true",
@@ -523,7 +524,7 @@ def main():
     if args.segmented and world == 1:
         grad_sync = trainer.GradSync(enabled=False)
     eng = StepEngine(p, device, use_graph=not args.no_graph, grad_sync=grad_sync, segmented=args.segmented)
-    eng.overlap_io = args.overlap_io and not args.no_graph
+    eng.overlap_io = not args.serial_io and not args.no_graph and not args.segmented
 
     # warm-up (eager: builds caches, sets kernel attributes), then capture
     side = torch.cuda.Stream()
@@ -553,9 +554,10 @@ def main():
         barrier()
         e0.record()
         if with_io and eng.overlap_io:
-            # the product's pipelined input path (GraphedStep.load_async, as GANTrainer.train uses it): the
-            # pinned batch of step i+1 is copied on a copy stream into staging buffers while step i replays;
-            # all K host-to-device copies and K loss read-backs are inside the timed region
+            # the product's pipelined input path (GraphedStep.load_async, as GANTrainer.train uses it): the pinned
+            # real images of step i+1 are copied on a copy stream straight into the static buffers once step i's
+            # graph has passed its discriminator stage, the small tensors right before replay i+1; all K
+            # host-to-device copies and K loss read-backs are inside the timed region
             eng.upload()
             for i in range(args.steps):
                 eng.step()
@@ -623,7 +625,9 @@ def main():
                    "nominal_frac_of_peak": NOMINAL_GFLOP_PER_STEP / ms_step / peak},
         "e2e": {"value": stories / (ms_step_e2e * 1e-3), "unit": "stories/s",
                 "h2d_bytes_per_step": eng.h2d_bytes, "d2h_bytes_per_step": eng.loss_host.numel() * 4,
-                "ms_per_step": ms_step_e2e},
+                "ms_per_step": ms_step_e2e,
+                "io": "GraphedStep.load_async: next batch copied under the running step" if eng.overlap_io
+                      else "serial: copy, step, read-back on one stream"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": launches_per_step,
         "roofline": {"bound": "tensor", "achieved": prof["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
