@@ -17,7 +17,7 @@ _CACHE = engine.WeightCache()
 # Run the spectral-norm power iterations of a discriminator call on a side stream, ahead of the
 # activation chain (they depend on the weights only).  No measurable gain on B200 (23.3 ms either
 # way): off by default, one less layer of nested stream forks.
-SN_AHEAD = False
+SN_AHEAD = _os.environ.get("CPCSV_SN_AHEAD", "0") == "1"
 DIRECT_ENC0 = _os.environ.get("CPCSV_DIRECT_ENC0", "1") != "0"     # first discriminator layer as one direct kernel
 
 
@@ -613,12 +613,22 @@ class EncoderRunner:
         # otherwise im2col -> K = 64 GEMM -> activation
         self.direct0 = DIRECT_ENC0 and Cop <= 128 and Cin in (1, 3) and H % 4 == 0 and W % 64 == 0
         if self.direct0:
-            alpha0, alphas = power_iterations()
+            # layer 0 only needs its own 1 / sigma: the power iterations of layers 2, 5, 8 (a chain of ~15 small
+            # kernels that depends on the weights only) can run beside it
+            alpha0 = self.sn_first.forward(w0, D.training, self.need_grad) if self.sn_first is not None else None
             self.alpha0, self.x0 = alpha0, xd
-            a = T4(n, Ho, Wo, Cop)
-            a.hi = _e((n, Ho, Wo, Cop), dev, torch.bfloat16)
-            a.lo = _e((n, Ho, Wo, Cop), dev, torch.bfloat16)
-            ops.enc0_lrelu_fwd(xd, w0.detach(), alpha0, 0.2, a.hi, a.lo, Cop)
+
+            def later_sigmas():
+                return [sn.forward(enc[idx].weight_orig, D.training, self.need_grad)
+                        for sn, idx in zip(sns, (2, 5, 8))]
+
+            def layer0():
+                a = T4(n, Ho, Wo, Cop)
+                a.hi = _e((n, Ho, Wo, Cop), dev, torch.bfloat16)
+                a.lo = _e((n, Ho, Wo, Cop), dev, torch.bfloat16)
+                ops.enc0_lrelu_fwd(xd, w0.detach(), alpha0, 0.2, a.hi, a.lo, Cop)
+                return a
+            alphas, a = streams.concurrently(later_sigmas, layer0, enabled=SN_AHEAD)
             self.a0 = a
             self.col = self.z0 = self.act0 = None
         else:
