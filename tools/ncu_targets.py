@@ -46,4 +46,13 @@ if __name__ == "__main__":
         # launch 4: upsample4 weight gradient (K = 92160 pixels, split-K)
         dz = bf(N, 64, 64, 128)
         ops.conv_gemm(conv.upconv_wgrad(dz, bf(N, 32, 32, 256), torch.empty(16, 128, 256, device=dev)))
+        # launch 5: upsample2 weight gradient as cta_group::2 pairs (Co = 512: four 128-channel M tiles)
+        dz2 = bf(N, 16, 16, 512)
+        ops.conv_gemm(conv.upconv_wgrad(dz2, bf(N, 8, 8, 1024), torch.empty(16, 512, 1024, device=dev)))
+    if which in ("all", "enc0"):
+        # first discriminator layer: direct conv4x4 s2 + LeakyReLU + hi/lo planes (csrc/enc0.cu)
+        x = torch.randn(N, 3, 64, 64, device=dev)
+        w = torch.randn(124, 3, 4, 4, device=dev) * 0.05
+        hi = torch.empty(N, 32, 32, 128, device=dev, dtype=torch.bfloat16)
+        ops.enc0_lrelu_fwd(x, w, None, 0.2, hi, torch.empty_like(hi), 128)
     torch.cuda.synchronize()

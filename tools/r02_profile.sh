@@ -11,13 +11,13 @@ run launches 500 ncu --metrics gpu__time_duration.sum --clock-control none --lau
     --log-file $O/r02_launches_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline
 # 2. DRAM bytes of every conv_gemm launch of two eager steps
 run traffic 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -k regex:conv_gemm --launch-skip 681 -c 454 --csv --log-file $O/r02_gemm_traffic.csv \
+    -k regex:conv_gemm --launch-skip 654 -c 436 --csv --log-file $O/r02_gemm_traffic.csv \
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline
 # 3. full sets of the GEMM classes (pair mode) and of the head GEMM + gather
 run full 600 ncu --set full --clock-control none --import-source on -o $O/r02_ncu_targets python tools/ncu_targets.py all
 # 4. stress-512: tensor-pipe activity of every conv_gemm launch of one step
 # (application replay: kernel replay would save / restore the 65 GB working set around every launch)
 run stress 600 ncu --replay-mode application --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
-    --clock-control none -k regex:conv_gemm --launch-skip 454 -c 227 --csv --log-file $O/r02_stress_gemm.csv \
-    python bench.py --config stress --steps 2 --warmup 2
+    --clock-control none -k regex:conv_gemm --launch-skip 436 -c 218 --csv --log-file $O/r02_stress_gemm.csv \
+    python bench.py --config stress --steps 2 --warmup 2 --job-log $O/r02_stress_jobs.log
 cat $O/r02_prof_summary.log
