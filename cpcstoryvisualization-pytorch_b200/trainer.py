@@ -455,20 +455,21 @@ class GraphedStep:
                 t.copy_(src[k], non_blocking=True)
 
     def _early_free(self):
-        """(static buffer, batch index, key) of the inputs nothing reads after the discriminator stage: the real
-        images (the cascade generator's reconstruction loss reads the real masks in the generator stage)"""
-        keys = [(self.dev_st["images"], 0, "images"), (self.dev_im["images"], 1, "images")]
-        if not hasattr(self.nets["G"], "presample"):
-            keys.append((self.dev_im["images_seg"], 1, "images_seg"))
-        return keys
+        """(static buffer, batch index, key) of the inputs nothing reads after the discriminator stage: every one
+        of them -- ``_step_body`` works on private copies of the small text / label tensors, and the real images are
+        last read by the discriminators -- except the real masks of the cascade generator (its reconstruction loss
+        reads them in the generator stage)"""
+        late = {"images_seg"} if hasattr(self.nets["G"], "presample") else set()
+        return [(t, bi, k) for bi, d in enumerate((self.dev_st, self.dev_im)) for k, t in d.items()
+                if not (bi == 1 and k in late)]
 
     def load_async(self, st_batch, im_batch):
         """Pipelined ``load`` of step k+1's inputs while step k is still being replayed (call it right after
         ``step()``).  With the whole step in one graph the real images -- 92 % of the bytes -- go STRAIGHT into the
         static buffers on a copy stream, as soon as step k's graph has passed its discriminator stage (an external
-        event recorded inside the graph): the copy hides under the generator stage.  The few small tensors the
-        generator stage still reads (descriptions, labels) are copied by the next ``step()`` right before its
-        replay.  Without that event (eager step, three-graph variant) everything goes to a staging set of buffers
+        event recorded inside the graph): the copy hides under the generator stage.  So do the small text / label
+        tensors (the step works on private copies of them, ``_step_body``); only the cascade generator's real masks
+        are copied by the next ``step()`` right before its replay.  Without that event (eager step, three-graph variant) everything goes to a staging set of buffers
         and the next ``step`` moves staging -> static buffers with one multi-tensor device copy."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -531,6 +532,10 @@ class GraphedStep:
     def _step_body(self):
         from miscc.utils import accuracy_on_device
         x = prepare_inputs(self.dev_st, self.dev_im)
+        for k in ("st_labels", "im_labels", "im_content", "st_content"):
+            # views of the static input buffers that the generator stage still reads: private copies, so that the
+            # next batch may be copied over the inputs while this step is still running (load_async)
+            x[k] = x[k].clone()
         with accuracy_on_device():          # no host round trip inside the step (scoped, not process-wide)
             self._record(train_step(self.nets, self.opts, x, self.labels, self.ratio, self.grad_sync,
                                     after_discriminators=self._mark_inputs_free))

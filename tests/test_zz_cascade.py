@@ -185,6 +185,73 @@ def test_graphed_step_replay_matches_eager_gpu():
     assert float(opts["G"].param_groups[0]["lr"]) == pytest.approx(5e-5)
 
 
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("name", ["small", "small_cascade"])
+def test_load_async_feeds_every_replay_its_own_batch_gpu(name):
+    """GraphedStep.load_async: batch k+1 is copied from pinned host memory into the static input buffers WHILE the
+    graph of step k is still running (behind the external event the graph records after its discriminator stage).
+    Three different batches, zero learning rates, injected noise: the pipelined run gives, step by step, the losses
+    of a run that loads every batch serially before its replay -- no step sees a half-overwritten batch."""
+    import copy
+    import trainer
+    from oracle import params, synth
+    p = presets.get(name)
+    dev = torch.device("cuda")
+    base = harness.build_product(p, params.init_all(p, 0), dev)
+    noise = synth.make_noise(p, 2, device=dev)
+
+    def host_batch(seed):
+        b = synth.make_batch(p, seed)
+        st = {"images": b["st_real"], "description": b["st_desc"], "labels": b["st_labels"]}
+        im = {"images": b["im_real"], "description": b["im_desc"], "content": b["im_content"],
+              "labels": b["im_labels"], "images_seg": b["se_real"]}
+        return ({k: v.pin_memory() for k, v in st.items()}, {k: v.pin_memory() for k, v in im.items()})
+    batches = [host_batch(s) for s in (11, 12, 13, 14)]
+    N, B = p["IM_BATCH"], p["ST_BATCH"]
+    labels = (torch.ones(N, device=dev), torch.zeros(N, device=dev), torch.ones(B, device=dev),
+              torch.zeros(B, device=dev))
+    runs = {}
+    for mode in ("serial", "pipelined"):
+        nets = copy.deepcopy(base)
+        opts = trainer.build_capturable_optimizers(nets, dev)
+        for o in opts.values():
+            trainer.set_lr(o, 0.0)
+        st0, im0 = batches[0]
+        gs = trainer.GraphedStep(nets, opts, labels, {k: v.to(dev) for k, v in st0.items()},
+                                 {k: v.to(dev) for k, v in im0.items()}, grad_sync=None)
+        for _ in range(2):                       # eager warm-up on batch 0, then capture
+            harness.inject_noise(nets["G"], synth.NoiseFeed(noise))
+            gs.step()
+        harness.inject_noise(nets["G"], synth.NoiseFeed(noise))
+        gs.capture()
+        out = []
+        if mode == "serial":
+            for st, im in batches[1:]:
+                gs.load(st, im)
+                gs.step()
+                out.append(gs.losses())
+        else:
+            gs.load(*batches[1])
+            for i in range(1, 4):
+                gs.step()
+                if i + 1 < 4:
+                    gs.load_async(*batches[i + 1])     # right behind the replay that is still running
+                out.append(gs.losses())
+            assert gs._inputs_free is not None and gs._io_done is not None     # the direct path was taken
+        torch.cuda.synchronize()
+        runs[mode] = out
+        # the static buffers end up holding the last batch
+        assert torch.equal(gs.dev_st["images"].cpu(), batches[3][0]["images"])
+        assert torch.equal(gs.dev_im["labels"].cpu(), batches[3][1]["labels"])
+    for a, b in zip(runs["serial"], runs["pipelined"]):
+        for k, v in a.items():
+            assert abs(v - b[k]) <= 1e-3 * abs(v) + 1e-6, (k, v, b[k])
+    # and the batches really differ: step 1 and step 2 of one run do not agree
+    assert any(abs(runs["serial"][0][k] - runs["serial"][1][k]) > 5e-3 * abs(runs["serial"][0][k])
+               for k in ("im_errD", "st_errD", "se_errD"))
+
+
 # ------------------------------------------------------------------------------ eval-mode generator
 @pytest.mark.gpu
 @pytest.mark.timeout(300)
