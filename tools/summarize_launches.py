@@ -18,7 +18,7 @@ def main(path, top=40):
         v = float(r["Metric Value"].replace(",", ""))
         unit = r.get("Metric Unit", "ns")
         ns = v * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1)
-        name = r["Kernel Name"].replace("(anonymous namespace)::", "").replace("void ", "")
+        name = r["Kernel Name"].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("void ", "")
         name = re.sub(r"<.*", "", name)
         name = re.sub(r"\(.*", "", name)
         name = re.sub(r"<.*", "", name)
