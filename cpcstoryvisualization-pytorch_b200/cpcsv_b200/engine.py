@@ -87,9 +87,17 @@ class WeightCache:
     def __init__(self):
         self.d = {}
         self.epoch = 0
+        self.replays = 0
 
     def invalidate(self):
         self.epoch += 1
+
+    def note_replay(self):
+        """a captured CUDA graph that contains optimiser steps has been replayed: the weights moved without any
+        Python-side trace (no ``_version`` bump, no optimiser hook).  Plain entries packed EAGERLY are stale from
+        here on and are rebuilt at their next eager use; maintained planes were rewritten by the graph itself and
+        entries packed inside the capture belong to the graph."""
+        self.replays += 1
 
     def invalidate_params(self, param_ids, keep_maintained=False):
         """drop the entries of the given parameters (keys start with id(param)); maintained planes are
@@ -126,7 +134,9 @@ class WeightCache:
         # and planes packed eagerly must not be waited on from inside a capture: for plain entries
         # the capture state is part of the validity tag.  Maintained planes sit in persistent buffers
         # that the (captured or eager) optimiser step keeps current: valid in both states.
-        return (param._version, param.data_ptr(), self.epoch) + (() if maintained else (capturing,))
+        if maintained:
+            return (param._version, param.data_ptr(), self.epoch)
+        return (param._version, param.data_ptr(), self.epoch, capturing, 0 if capturing else self.replays)
 
     def get(self, key, param, build, spec=None, fill=None):
         """Entries remember the stream that packed them and an event recorded after the pack

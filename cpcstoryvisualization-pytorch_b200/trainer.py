@@ -615,6 +615,8 @@ class GraphedStep:
             self._consume_direct()
         if self._pending:
             self._consume_staging()
+        if self.graph is not None:
+            knets.weight_cache().note_replay()      # the replay moves the weights behind the cache's back
         if self.graph is None:
             self._step_body()
         elif not self.segmented:

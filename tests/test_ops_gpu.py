@@ -339,6 +339,20 @@ def test_planes_stay_current_across_graph_replays_that_update_the_weights():
     # no-grad generator calls run single-pass fp16 GEMMs: ~1.5e-3 relative on the images
     assert harness.rel_l2(img1, ref) < 5e-3, harness.rel_l2(img1, ref)
     assert harness.rel_l2(img0, ref) > 1e-2          # the updates really changed the output
+    # ... and again AFTER that eager call has re-packed the small plain entries (head weights, ...): replays move
+    # the weights without any Python-side trace, the owner of the graph tells the cache (GraphedStep.step does)
+    from cpcsv_b200 import nets as knets
+    for _ in range(3):
+        knets.weight_cache().note_replay()
+        graph.replay()
+    torch.cuda.synchronize()
+    img2 = run()
+    sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    feed = synth.NoiseFeed(synth.make_noise(p, 2, device=dev, calls=("images",)))
+    with torch.no_grad():
+        ref2 = Fn.sample_images(sd, x["im_motion"], x["im_content"], feed, seg=True)[1]
+    assert harness.rel_l2(img2, ref2) < 5e-3, harness.rel_l2(img2, ref2)
+    assert harness.rel_l2(img1, ref2) > 1e-2
 
 
 @pytest.mark.parametrize("Co", [1, 3])

@@ -240,3 +240,28 @@ def test_generator_update_inside_backward_matches_plain_adam(dev, monkeypatch):
         a, b, c = (t.detach().double().cpu() for t in (a, b, c))
         assert float((a - b).abs().mean()) <= (0.02 if dev.type == "cpu" else 0.10) * lr, n
         assert float((a - c).abs().mean()) <= 0.10 * lr, (n, n in trunk)
+
+
+def test_plain_cache_entries_are_rebuilt_after_a_graph_replay():
+    """weights updated inside a replayed CUDA graph leave no Python-side trace; the owner of the
+    graph calls WeightCache.note_replay() (GraphedStep.step does), after which eagerly packed plain entries are
+    rebuilt at their next use while maintained planes (rewritten by the graph's own optimiser kernels) stay"""
+    cache = engine.WeightCache()
+    w = torch.nn.Parameter(torch.randn(8, 4))
+    built = {"plain": 0, "kept": 0}
+
+    def build_plain():
+        built["plain"] += 1
+        return [w.detach().clone(), None]
+
+    def build_kept():
+        built["kept"] += 1
+        return [w.detach().clone(), None]
+    cache.get((id(w), "plain"), w, build_plain)
+    cache.get((id(w), "kept"), w, build_kept, spec=("conv", 0), fill=lambda val: None)
+    cache.get((id(w), "plain"), w, build_plain)
+    assert built == {"plain": 1, "kept": 1}
+    cache.note_replay()
+    cache.get((id(w), "plain"), w, build_plain)
+    cache.get((id(w), "kept"), w, build_kept, spec=("conv", 0), fill=lambda val: None)
+    assert built == {"plain": 2, "kept": 1}
