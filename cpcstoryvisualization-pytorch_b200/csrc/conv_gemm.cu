@@ -530,6 +530,18 @@ static bool pair_mode_enabled() {
   return on;
 }
 
+// Shared memory a SINGLE-PLANE job may take (CPCSV_GEMM_SMEM_KB, default: everything).  Below ~195 KB one
+// block of the optimiser's Adam + re-layout kernels (10-28 KB of shared memory) fits next to a resident GEMM CTA.
+static int single_plane_smem_limit() {
+  static const int v = [] {
+    const char* e = getenv("CPCSV_GEMM_SMEM_KB");
+    int kb = e ? atoi(e) : 0;
+    if (kb < 96 || kb > 227) kb = 227;
+    return kb * 1024;
+  }();
+  return v;
+}
+
 int num_sms() {
   static int n = [] {
     int dev = 0, v = 0;
@@ -631,7 +643,8 @@ extern "C" int cpcsv_conv_gemm(const cpcsv_gemm_t* job, cpcsv_stream_t stream_) 
                        pair ? 2 * kBlockM : kBlockM, static_cast<uint32_t>(J.block_n));
   P.b_plane_bytes = (pair ? J.block_n / 2 : J.block_n) * 128;
   P.stage_bytes = J.planes * (kAPlaneBytes + P.b_plane_bytes);
-  int stages = (kSmemLimit - 1024 - kBarrierBytes - kEpiBytes) / P.stage_bytes;
+  const int smem_limit = J.planes == 1 ? single_plane_smem_limit() : kSmemLimit;
+  int stages = (smem_limit - 1024 - kBarrierBytes - kEpiBytes) / P.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   CPCSV_REQUIRE(stages >= 2, "conv_gemm: tile does not fit shared memory");
   P.stages = stages;
