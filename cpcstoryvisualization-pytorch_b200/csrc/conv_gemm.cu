@@ -530,13 +530,17 @@ static bool pair_mode_enabled() {
   return on;
 }
 
-// Shared memory a SINGLE-PLANE job may take (CPCSV_GEMM_SMEM_KB, default: everything).  Below ~195 KB one
-// block of the optimiser's Adam + re-layout kernels (10-28 KB of shared memory) fits next to a resident GEMM CTA.
+// Shared memory a SINGLE-PLANE job takes (CPCSV_GEMM_SMEM_KB, 96..227; default 144 = 3 pipeline stages of a pair
+// job).  The single-plane jobs are the backward pass and the no-grad forward; with the whole 227 KB (6 stages) a
+// resident GEMM CTA leaves no room for any other block that needs shared memory, and the optimiser's Adam +
+// re-layout kernels (10-28 KB per block, issued during the backward pass) queue up behind the last GEMM.  Measured
+// (bench.py, two boxes): 227 KB 20.21 / 20.59-20.61 ms per step; 160 KB 19.97 / 20.35; 144 KB 19.87-19.96; 128 KB
+// 19.94-20.03 -- and no measurable change of the GEMMs' own serial time (15.4-15.9 ms either way).
 static int single_plane_smem_limit() {
   static const int v = [] {
     const char* e = getenv("CPCSV_GEMM_SMEM_KB");
-    int kb = e ? atoi(e) : 0;
-    if (kb < 96 || kb > 227) kb = 227;
+    int kb = e ? atoi(e) : 144;
+    if (kb < 96 || kb > 227) kb = 144;
     return kb * 1024;
   }();
   return v;
