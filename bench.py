@@ -484,9 +484,9 @@ def main():
                                                     "executed FLOPs) to this file")
     ap.add_argument("--serial-io", action="store_true",
                     help="e2e loop: copy every batch on the step's own stream before the replay (the round-1 path).  "
-                         "Default: GraphedStep.load_async, the path GANTrainer.train uses -- batch i+1 is copied to "
-                         "staging buffers on a copy stream while step i replays, one device copy moves it into the "
-                         "static buffers before replay i+1")
+                         "Default: GraphedStep.load_async, the path GANTrainer.train uses -- the real images of batch "
+                         "i+1 are copied straight into the static buffers on a copy stream once step i's graph has "
+                         "passed its discriminator stage (measured on one box: 20.41 / 20.68 vs 20.80 / 20.71 ms)")
     ap.add_argument("--overlap-io", action="store_true", help="(default since round 2)")
     ap.add_argument("--whole-graph", action="store_true",
                     help="(default since round 2) N > 1: the NCCL all-reduces are captured inside the ONE step graph")
@@ -559,9 +559,9 @@ def main():
         e0.record()
         if with_io and eng.overlap_io:
             # the product's pipelined input path (GraphedStep.load_async, as GANTrainer.train uses it): the pinned
-            # batch of step i+1 is copied on a copy stream into staging buffers while step i replays, and moved
-            # into the static buffers right before replay i+1; all K host-to-device copies and K loss
-            # read-backs are inside the timed region
+            # real images of step i+1 are copied on a copy stream straight into the static buffers once step i's
+            # graph has passed its discriminator stage, the small tensors right before replay i+1; all K
+            # host-to-device copies and K loss read-backs are inside the timed region
             eng.upload()
             for i in range(args.steps):
                 eng.step()

@@ -341,7 +341,8 @@ def sync_grads(nets, names, grad_sync, inplace=False):
                 grad_sync(list(nets[k].parameters()))
 
 
-def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=True, skip_d_wgrad=True):
+def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=True, skip_d_wgrad=True,
+               after_discriminators=None):
     """One iteration of the reference's hot loop (trainer.py:290-416).  ``x`` from
     ``prepare_inputs`` (device tensors), ``labels`` = (im_ones, im_zeros, st_ones, st_zeros).
     Returns a dict of loss tensors (no host sync)."""
@@ -350,6 +351,8 @@ def train_step(nets, opts, x, labels, ratio=1.0, grad_sync=None, apply_optim=Tru
                                grad_sync=grad_sync if exchange else None)
     if not apply_optim:
         sync_grads(nets, D_NETS, grad_sync)
+    if after_discriminators is not None:
+        after_discriminators()      # the real images have been read for the last time (GraphedStep.load_async)
     early = apply_optim and hasattr(opts["G"], "expect_backward")
     if early:
         # the generator's Adam step starts inside the backward pass; with several ranks the gradient
@@ -431,6 +434,10 @@ class GraphedStep:
             self.loss_host = self.loss_host.pin_memory()
         self._copy_stream = self._staging = None
         self._pending = False
+        # recorded INSIDE the step (an external event node of the graph) once the discriminator stage is over:
+        # from there on nothing reads the real images, the next batch may be copied over them
+        self._inputs_free = None
+        self._io_done, self._late, self._pending_direct = None, None, False
 
     # --- static buffers ----------------------------------------------------------------------
     def fits(self, st_batch, im_batch):
@@ -447,16 +454,41 @@ class GraphedStep:
             for k, t in dst.items():
                 t.copy_(src[k], non_blocking=True)
 
+    def _early_free(self):
+        """(static buffer, batch index, key) of the inputs nothing reads after the discriminator stage: every one
+        of them -- ``_step_body`` works on private copies of the small text / label tensors, and the real images are
+        last read by the discriminators -- except the real masks of the cascade generator (its reconstruction loss
+        reads them in the generator stage)"""
+        late = {"images_seg"} if hasattr(self.nets["G"], "presample") else set()
+        return [(t, bi, k) for bi, d in enumerate((self.dev_st, self.dev_im)) for k, t in d.items()
+                if not (bi == 1 and k in late)]
+
     def load_async(self, st_batch, im_batch):
-        """Pipelined ``load``: the host-to-device copy of step k+1's inputs goes to a staging set of buffers on a
-        copy stream while step k is being replayed; the next ``step`` waits for it and moves staging -> static
-        buffers with one multi-tensor device copy (11 MB, a few microseconds) right before its replay.
-        (A variant that copied straight into the static buffers behind an external event recorded inside the graph
-        was tried: a stream wait on an event-record NODE of a graph still in flight did not order reliably --
-        tests/test_zz_cascade.py::test_load_async_feeds_every_replay_its_own_batch_gpu failed intermittently -- and
-        it was removed.)"""
+        """Pipelined ``load`` of step k+1's inputs while step k is still being replayed (call it right after
+        ``step()``).  With the whole step in one graph the real images -- 92 % of the bytes -- go STRAIGHT into the
+        static buffers on a copy stream, as soon as step k's graph has passed its discriminator stage (an external
+        event recorded inside the graph): the copy hides under the generator stage.  So do the small text / label
+        tensors (the step works on private copies of them, ``_step_body``); only the cascade generator's real masks
+        are copied by the next ``step()`` right before its replay.  Without that event (eager step, three-graph variant) everything goes to a staging set of buffers
+        and the next ``step`` moves staging -> static buffers with one multi-tensor device copy."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
+        if self._inputs_free is not None and self.graph is not None and not self.segmented:
+            if self._io_done is None:
+                self._io_done = torch.cuda.Event()
+            batches = (st_batch, im_batch)
+            early = self._early_free()
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._inputs_free)
+                for dst, bi, k in early:
+                    dst.copy_(batches[bi][k], non_blocking=True)
+                self._io_done.record(self._copy_stream)
+            taken = {id(dst) for dst, _bi, _k in early}
+            self._late = [(t, src[k]) for d, src in ((self.dev_st, st_batch), (self.dev_im, im_batch))
+                          for k, t in d.items() if id(t) not in taken]
+            self._pending_direct = True
+            return
+        if self._staging is None:
             self._staging = [{k: torch.empty_like(t) for k, t in d.items()} for d in (self.dev_st, self.dev_im)]
             self._ready, self._consumed = torch.cuda.Event(), torch.cuda.Event()
         with torch.cuda.stream(self._copy_stream):
@@ -466,6 +498,13 @@ class GraphedStep:
                     t.copy_(src[k], non_blocking=True)
             self._ready.record(self._copy_stream)
         self._pending = True
+
+    def _consume_direct(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._io_done)
+        for dst, src in self._late:
+            dst.copy_(src, non_blocking=True)
+        self._late, self._pending_direct = None, False
 
     def _consume_staging(self):
         cur = torch.cuda.current_stream()
@@ -493,8 +532,17 @@ class GraphedStep:
     def _step_body(self):
         from miscc.utils import accuracy_on_device
         x = prepare_inputs(self.dev_st, self.dev_im)
+        for k in ("st_labels", "im_labels", "im_content", "st_content"):
+            # views of the static input buffers that the generator stage still reads: private copies, so that the
+            # next batch may be copied over the inputs while this step is still running (load_async)
+            x[k] = x[k].clone()
         with accuracy_on_device():          # no host round trip inside the step (scoped, not process-wide)
-            self._record(train_step(self.nets, self.opts, x, self.labels, self.ratio, self.grad_sync))
+            self._record(train_step(self.nets, self.opts, x, self.labels, self.ratio, self.grad_sync,
+                                    after_discriminators=self._mark_inputs_free))
+
+    def _mark_inputs_free(self):
+        if self._inputs_free is not None:
+            self._inputs_free.record()
 
     # the step in three segments, with the NCCL gradient exchange between them
     def _seg_d(self):
@@ -531,6 +579,7 @@ class GraphedStep:
             kw["capture_error_mode"] = capture_error_mode
         if not self.segmented:
             self.graph = torch.cuda.CUDAGraph()
+            self._inputs_free = torch.cuda.Event(external=True) if self.device.type == "cuda" else None
             if self.grad_sync is not None and getattr(self.grad_sync, "enabled", False):
                 kw["capture_error_mode"] = "thread_local"   # the NCCL watchdog thread keeps running
             with torch.cuda.graph(self.graph, stream=stream, **kw):
@@ -562,6 +611,8 @@ class GraphedStep:
                 p.grad = g
 
     def step(self):
+        if self._pending_direct:
+            self._consume_direct()
         if self._pending:
             self._consume_staging()
         if self.graph is not None:

@@ -189,10 +189,10 @@ def test_graphed_step_replay_matches_eager_gpu():
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize("name", ["small", "small_cascade"])
 def test_load_async_feeds_every_replay_its_own_batch_gpu(name):
-    """GraphedStep.load_async: batch k+1 is copied from pinned host memory to staging buffers WHILE the graph of
-    step k is still running, and moved into the static input buffers right before replay k+1.  Three different
-    batches, zero learning rates, injected noise: the pipelined run gives, step by step, the losses of a run that
-    loads every batch serially before its replay -- no step sees a half-overwritten batch."""
+    """GraphedStep.load_async: batch k+1 is copied from pinned host memory into the static input buffers WHILE the
+    graph of step k is still running (behind the external event the graph records after its discriminator stage).
+    Three different batches, zero learning rates, injected noise: the pipelined run gives, step by step, the losses
+    of a run that loads every batch serially before its replay -- no step sees a half-overwritten batch."""
     import copy
     import trainer
     from oracle import params, synth
@@ -238,7 +238,7 @@ def test_load_async_feeds_every_replay_its_own_batch_gpu(name):
                 if i + 1 < 4:
                     gs.load_async(*batches[i + 1])     # right behind the replay that is still running
                 out.append(gs.losses())
-            assert gs._staging is not None
+            assert gs._inputs_free is not None and gs._io_done is not None     # the direct path was taken
         torch.cuda.synchronize()
         runs[mode] = out
         # the static buffers end up holding the last batch
