@@ -173,7 +173,12 @@ CONCURRENT_D = True     # run the three discriminators on parallel CUDA streams
 CONCURRENT_G = True     # run sample_videos / sample_images of one phase on two streams
 EARLY_G = True          # issue the generator-update forward alongside the discriminator update
 LAYERWISE_G_ADAM = os.environ.get("CPCSV_LAYERWISE_ADAM", "1") != "0"   # trunk Adam per layer, under the backward pass
-EARLY_D_REAL = True     # issue the discriminators' real-image encoder passes before the fakes exist
+# Issue the discriminators' real-image encoder passes before the fakes exist, on detached streams.  OFF: together with
+# EARLY_G it made the STORY discriminator's losses of a graph-replayed step deviate intermittently (tools/diag_run.sh,
+# 'small' preset, zero learning rates: about 1 step in 12 with st_errD or st_errG off by 1-10 %, every other loss
+# exact; with either switch off 60 of 60 steps agree to 1e-5).  The race was not found; the early passes bought no
+# measurable time any more (20.07 / 20.03 ms without vs 20.08 ms with them), so they are opt-in (CPCSV_EARLY_D_REAL=1).
+EARLY_D_REAL = os.environ.get("CPCSV_EARLY_D_REAL", "0") == "1"
 step_stream = streams.step_stream
 Detached = streams.Detached
 
