@@ -148,7 +148,9 @@ def test_step_gpu(name):
     # no-grad generator call are averaged over far fewer products; the emulator of the kernel contract gives
     # 0.99924 on 'small', tests/test_step_parity.py::test_small_step_emulated) and 'tiny' has 2- and 4-channel
     # layers dominated by a few elements: per network >= 0.999 everywhere, per tensor >= 0.998 / 0.99 there.
-    _check(res, small_tensor_cos={"tiny": 0.99, "small": 0.998}.get(name))
+    # clevr_cascade: the conditioning nets' small weight tensors sit at 0.9990 +- 0.0003 run to run (c_net.0.weight
+    # 0.99899 in one run of 12); per network the cascade step is >= 0.9995
+    _check(res, small_tensor_cos={"tiny": 0.99, "small": 0.998, "clevr_cascade": 0.998}.get(name))
 
 
 @pytest.mark.gpu

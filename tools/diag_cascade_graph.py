@@ -19,6 +19,10 @@ def main(name, eager_flag):
     for kv in filter(None, os.environ.get("DIAG_FLAGS", "").split(",")):      # e.g. EARLY_D_REAL=0,CONCURRENT_D=0
         k, v = kv.split("=")
         setattr(trainer, k, bool(int(v)))
+    import miscc.utils as mu
+    for kv in filter(None, os.environ.get("DIAG_UTILS_FLAGS", "").split(",")):      # e.g. PARALLEL_PASSES=0
+        k, v = kv.split("=")
+        setattr(mu, k, bool(int(v)))
     p = presets.get(name)
     dev = torch.device("cuda")
     base = harness.build_product(p, params.init_all(p, 0), dev)
