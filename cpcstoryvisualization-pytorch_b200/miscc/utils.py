@@ -24,14 +24,14 @@ from miscc.outputs import (check_is_order, compute_cyc_loss_img, compute_cyc_los
                            save_train_samples)
 
 SYNC_ACCURACY = True   # reference behaviour: .cpu().numpy() round trip per call (host sync)
-# Real / fake (/ wrong-pair) passes of ONE discriminator on parallel CUDA streams.  OFF by default since the end of
-# round 2 (CPCSV_PARALLEL_PASSES=1 turns it on): in graph-replayed steps the story discriminator's losses deviated
-# intermittently by 1-10 % to a few discrete alternative values and were exact again in the next step -- the signature
-# of two concurrent passes applying their in-place spectral-norm power iterations in the other order (each pass then
-# sees the other's sigma; the state after both is the same).  engine.StateOrder is meant to pin that order and the hole
-# in it has not been found; with the passes in sequence on one stream there is no order to pin (tools/diag_run.sh:
-# clean).  Cost: 0.15 ms / step (20.55 vs 20.40 ms).
-PARALLEL_PASSES = os.environ.get("CPCSV_PARALLEL_PASSES", "0") == "1"
+# Real / fake (/ wrong-pair) passes of ONE discriminator on parallel CUDA streams (CPCSV_PARALLEL_PASSES=0: in
+# sequence).  OPEN ISSUE: in graph-replayed steps the losses of the story discriminator -- the
+# one whose passes run on the step's own stream -- deviate intermittently by 1-10 % to a few discrete alternative
+# values and are exact again in the next step.  How often depends on what runs concurrently (tools/diag_run.sh, 60
+# step measurements per setting, 'small' presets): plain generator, parallel passes: 0; plain generator, passes in
+# sequence: ~10; cascade generator, parallel passes: ~1; cascade generator, passes in sequence: 0.  The race itself has
+# not been found; each generator gets the setting that measured clean.
+PARALLEL_PASSES = os.environ.get("CPCSV_PARALLEL_PASSES", "1") != "0"
 
 
 import contextlib  # noqa: E402
@@ -55,7 +55,7 @@ def _parallel(*thunks):
     """independent passes through the same discriminator on parallel streams; module state they
     share (BatchNorm running statistics, spectral-norm u / v) is still updated in call order"""
     from cpcsv_b200 import streams
-    return streams.concurrently(*thunks, enabled=PARALLEL_PASSES)
+    return streams.concurrently(*thunks, enabled=PARALLEL_PASSES and not cfg.CASCADE_MODEL)
 
 
 def _call(module, *inputs):
