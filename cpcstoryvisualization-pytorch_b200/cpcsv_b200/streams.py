@@ -16,6 +16,7 @@ LOW_PRIORITY = -1
 _POOLS = {}             # (kind, device, parent stream id) -> [streams]
 _LENT = {}              # same key -> number of pool streams lent to forks that are still open
 _DETACHED_OPEN = [0]    # detached branches issued and not yet joined
+_FORK_DEPTH = [0]       # forks (concurrently) currently being issued: a nested join must not forget ordered-state events
 
 
 def _borrow(kind, parent, n, priority=HIGH_PRIORITY):
@@ -59,6 +60,7 @@ def concurrently(*thunks, enabled=True):
         return [t() for t in thunks]
     main = torch.cuda.current_stream()
     key, streams = _borrow("fork", main, len(thunks) - 1)
+    _FORK_DEPTH[0] += 1
     try:
         results = [None] * len(thunks)
         for st in streams:
@@ -70,8 +72,13 @@ def concurrently(*thunks, enabled=True):
         for st in streams:
             main.wait_stream(st)
     finally:
+        _FORK_DEPTH[0] -= 1
         _give_back(key, len(streams))
-    knets.sync_point(streams, reset_state_order=_DETACHED_OPEN[0] == 0)
+    # the ordered-state events (engine.StateOrder) may only be forgotten once EVERYTHING has been joined: the join of
+    # a fork nested inside one branch of an outer fork comes before the outer fork's later branches are even issued,
+    # and those still have to wait for this branch's in-place updates (found by tests/streamcheck.py: the second
+    # generator call of a phase did not wait for the first one's BatchNorm running-statistics updates)
+    knets.sync_point(streams, reset_state_order=_DETACHED_OPEN[0] == 0 and _FORK_DEPTH[0] == 0)
     return results
 
 
