@@ -54,8 +54,10 @@ def _one_step_impl(monkeypatch, name, flags, util_flags, break_state_order, skip
 @pytest.mark.parametrize("name,flags,util_flags,skip_backward", [
     ("tiny", (), (), False),                                   # whole step incl. the optimiser kernels
     ("tiny", (("EARLY_G", False),), (), True),                 # (found the nested-join reset of streams.concurrently)
-    ("tiny_cascade", (), (), True),
-    # the other settings under which replayed steps deviated on the GPU (a minute each): CPCSV_STREAMCHECK_ALL=1
+    # the cascade step and the other settings under which replayed steps deviated on the GPU (up to a minute each):
+    # CPCSV_STREAMCHECK_ALL=1
+    pytest.param("tiny_cascade", (), (), True, marks=pytest.mark.skipif(
+        os.environ.get("CPCSV_STREAMCHECK_ALL") != "1", reason="set CPCSV_STREAMCHECK_ALL=1")),
     pytest.param("tiny", (("EARLY_D_REAL", True),), (), True, marks=pytest.mark.skipif(
         os.environ.get("CPCSV_STREAMCHECK_ALL") != "1", reason="set CPCSV_STREAMCHECK_ALL=1")),
     pytest.param("tiny", (), (("PARALLEL_PASSES", False),), True, marks=pytest.mark.skipif(
