@@ -182,7 +182,12 @@ def sync_point(streams=None, reset_state_order=True):
     ordered module state are still running detached."""
     if reset_state_order:
         engine.StateOrder.reset()
-    _CACHE.mark_synced(streams)
+        # Only then may the cache forget who packed what: "joined into the current stream" orders the pack before
+        # every LATER consumer only if that consumer descends from the current stream.  A detached branch (it waits
+        # for the stage's start event, not for this join) or a later branch of an enclosing fork does not -- found by
+        # tests/streamcheck.py on the cascade generator: the early generator forward read head / mask-conv planes that
+        # the no-grad call had packed on another stream, without waiting for the pack.
+        _CACHE.mark_synced(streams)
 
 
 def join_prefetch(handle):

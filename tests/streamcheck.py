@@ -18,6 +18,7 @@ bounding boxes of strided views (interleaved views may be reported falsely: read
 """
 import contextlib
 import sys
+import weakref
 
 import torch
 from torch.utils._python_dispatch import TorchDispatchMode
@@ -89,7 +90,8 @@ class FakeEvent:
         return True
 
 
-STATE = {"current": None, "default": None, "in_backward": 0, "races": [], "log": {}, "keep": [], "enabled": False}
+STATE = {"current": None, "default": None, "in_backward": 0, "races": [], "log": {}, "keep": [], "enabled": False,
+         "alloc": {}, "recorded": {}, "frees": [], "track_frees": False, "pending": {}}
 
 
 @contextlib.contextmanager
@@ -150,7 +152,56 @@ def _access(t, write, opname):
     recs.append((lo, hi, ts, cur.id, write, opname, _where()))
     if len(recs) > 64:          # keep the last writer(s) and recent readers
         del recs[:len(recs) - 64]
-    STATE["keep"].append(t)     # never let the CPU allocator recycle an address inside one check
+    if STATE["track_frees"]:
+        # storage lifetimes: the log of a storage dies with it (the CPU allocator recycles addresses), and its death
+        # is checked against the stream-ordered allocator's rule (see _freed)
+        if len(recs) == 1:
+            weakref.finalize(t.untyped_storage(), _freed, key)
+    else:
+        STATE["keep"].append(t)     # never let the CPU allocator recycle an address inside one check
+
+
+def _freed(key):
+    """A storage dies NOW (host order).  CUDA's caching allocator gives its block back to the pool of the stream it
+    was allocated on (A): the next allocation on A may take it at once.  Safe only if every access by another stream X
+    is already ordered before A's future work, i.e. covered by A's clock -- or was announced with record_stream."""
+    recs = STATE["log"].pop(key, None)
+    alloc = STATE["alloc"].pop(key, None)
+    rec_streams = STATE["recorded"].pop(key, ())
+    if not recs or alloc is None or not STATE["enabled"]:
+        return
+    a_stream, a_op, a_where, a_bytes = alloc
+    pend = []
+    for (lo, hi, ts, sid, write, op, where) in recs:
+        if sid == a_stream.id or sid in rec_streams:
+            continue
+        if a_stream.clock.get(sid, 0) >= ts[sid]:
+            continue
+        pend.append((sid, ts[sid], op, where))
+    if pend:
+        # not a hazard yet: it becomes one when a LATER allocation on the same stream can take the block while those
+        # accesses are still unordered (checked in _allocated)
+        STATE["pending"].setdefault(a_stream.id, []).append(
+            {"bytes": a_bytes, "alloc": (a_op, a_where), "uses": pend, "in_backward": STATE["in_backward"] > 0})
+
+
+def _allocated(stream, nbytes, opname):
+    """a fresh allocation on `stream`: may reuse any block freed earlier on this stream that is at least as large"""
+    pend = STATE["pending"].get(stream.id)
+    if not pend:
+        return
+    keep = []
+    for p in pend:
+        p["uses"] = [u for u in p["uses"] if stream.clock.get(u[0], 0) < u[1]]
+        if not p["uses"]:
+            continue            # the stream has caught up with every foreign access in the meantime
+        if nbytes <= p["bytes"]:
+            STATE["frees"].append({"alloc": ("%s (%d B)" % (p["alloc"][0], p["bytes"]), "S%d" % stream.id, p["alloc"][1]),
+                                   "use": (p["uses"][0][2], "S%d" % p["uses"][0][0], p["uses"][0][3]),
+                                   "reuser": (opname, nbytes, _where()), "in_backward": p["in_backward"]})
+        else:
+            keep.append(p)
+    STATE["pending"][stream.id] = keep
 
 
 class Checker(TorchDispatchMode):
@@ -186,17 +237,23 @@ class Checker(TorchDispatchMode):
         outs = out if isinstance(out, (list, tuple)) else [out]
         for o in outs:
             if isinstance(o, torch.Tensor) and o.untyped_storage().data_ptr() not in seen and o.numel():
+                k = o.untyped_storage().data_ptr()
+                if STATE["track_frees"] and k not in STATE["log"]:
+                    nb = o.untyped_storage().nbytes()
+                    _allocated(STATE["current"], nb, name)
+                    STATE["alloc"][k] = (STATE["current"], name, _where(), nb)
                 _access(o, True, name)          # a fresh result: its first writer
         return out
 
 
 @contextlib.contextmanager
-def installed(monkeypatch, skip_backward=False):
+def installed(monkeypatch, skip_backward=False, track_frees=False):
     """fake streams + forced is_cuda + dispatch logging; yields the STATE dict (``races`` after the block).
     ``skip_backward``: ``Tensor.backward`` does nothing (forward schedule only: half the run time; the optimiser
     steps then have no gradients to apply)"""
     FakeStream.all.clear()
-    STATE.update(current=FakeStream(), races=[], log={}, keep=[], in_backward=0, enabled=True)
+    STATE.update(current=FakeStream(), races=[], log={}, keep=[], in_backward=0, enabled=True, alloc={}, recorded={},
+                 frees=[], track_frees=track_frees, pending={})
     STATE["default"] = STATE["current"]
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: STATE["current"])
@@ -207,7 +264,9 @@ def installed(monkeypatch, skip_backward=False):
     monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
     monkeypatch.setattr(torch.cuda, "synchronize", _global_sync)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
-    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+    def record_stream(self, st):
+        STATE["recorded"].setdefault(self.untyped_storage().data_ptr(), set()).add(st.id)
+    monkeypatch.setattr(torch.Tensor, "record_stream", record_stream, raising=False)
     orig_backward = torch.Tensor.backward
 
     def backward(self, *a, **k):
@@ -239,3 +298,15 @@ def summarize(races, limit=12):
         if len(lines) >= limit:
             break
     return "%d unordered conflicting accesses (%d distinct)\n" % (len(races), len(seen)) + "\n".join(lines)
+
+
+def summarize_frees(frees, limit=20):
+    seen, lines = {}, []
+    for r in frees:
+        key = (r["alloc"][0], r["alloc"][2], r["use"][0], r["use"][2], r["reuser"][0], r["reuser"][2])
+        seen[key] = seen.get(key, 0) + 1
+    for (aop, awhere, uop, uwhere, rop, rwhere), n in sorted(seen.items(), key=lambda kv: -kv[1])[:limit]:
+        lines.append("%4d x block allocated by %s [%s]\n        still used on another stream by %s [%s]\n"
+                     "        when the allocation stream allocates again: %s [%s]" % (n, aop, awhere, uop, uwhere, rop, rwhere))
+    return "%d possible block reuses under a foreign reader / writer (%d distinct)\n" % (len(frees), len(seen)) + \
+        "\n".join(lines)
