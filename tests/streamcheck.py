@@ -91,7 +91,7 @@ class FakeEvent:
 
 
 STATE = {"current": None, "default": None, "in_backward": 0, "races": [], "log": {}, "keep": [], "enabled": False,
-         "alloc": {}, "recorded": {}, "frees": [], "track_frees": False, "pending": {}}
+         "alloc": {}, "recorded": {}, "frees": [], "track_frees": False, "pending": {}, "custom_backward": 0}
 
 
 @contextlib.contextmanager
@@ -208,7 +208,7 @@ class Checker(TorchDispatchMode):
     def __torch_dispatch__(self, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
         out = func(*args, **kwargs)
-        if not STATE["enabled"] or STATE["in_backward"]:
+        if not STATE["enabled"] or (STATE["in_backward"] and not STATE["custom_backward"]):
             return out
         name = str(func)
         schema = getattr(func, "_schema", None)
@@ -253,7 +253,7 @@ def installed(monkeypatch, skip_backward=False, track_frees=False):
     steps then have no gradients to apply)"""
     FakeStream.all.clear()
     STATE.update(current=FakeStream(), races=[], log={}, keep=[], in_backward=0, enabled=True, alloc={}, recorded={},
-                 frees=[], track_frees=track_frees, pending={})
+                 frees=[], track_frees=track_frees, pending={}, custom_backward=0)
     STATE["default"] = STATE["current"]
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: STATE["current"])
@@ -278,6 +278,29 @@ def installed(monkeypatch, skip_backward=False, track_frees=False):
         finally:
             STATE["in_backward"] -= 1
     monkeypatch.setattr(torch.Tensor, "backward", backward)
+    # Backward passes of the product's own autograd Function (nets.TapeFn: every kernel tape) run, as under the real
+    # autograd engine, on the stream their forward pass ran on; the engine makes that stream wait for the producer of
+    # the incoming gradients (approximated here by the stream that is current when the node runs: at least as much
+    # ordering as the real engine gives) and, at the end of backward(), makes the calling stream wait for it.
+    from cpcsv_b200 import nets as _nets
+    fwd0, bwd0 = _nets.TapeFn.forward, _nets.TapeFn.backward
+
+    def t_forward(ctx, runner, *tensors):
+        ctx.fake_stream = STATE["current"]
+        return fwd0(ctx, runner, *tensors)
+
+    def t_backward(ctx, *grads):
+        caller, st = STATE["current"], ctx.fake_stream
+        st.wait_stream(caller)
+        STATE["custom_backward"] += 1
+        try:
+            with fake_stream_ctx(st):
+                return bwd0(ctx, *grads)
+        finally:
+            STATE["custom_backward"] -= 1
+            caller.wait_stream(st)
+    monkeypatch.setattr(_nets.TapeFn, "forward", staticmethod(t_forward))
+    monkeypatch.setattr(_nets.TapeFn, "backward", staticmethod(t_backward))
     with Checker():
         try:
             yield STATE
